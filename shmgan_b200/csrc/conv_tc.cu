@@ -1,0 +1,713 @@
+// conv_tc.cu -- bf16 implicit-GEMM convolutions on the 5th-gen tensor cores (tcgen05.mma, fp32 accumulators in TMEM),
+// operands staged in shared memory by TMA with 128-byte swizzle, one persistent warp-specialised CTA per SM.
+//
+//   D[m, n] = sum_{tap} sum_{k} A[lattice(m) * IS + off_tap, k] * Wt[tap][n][k]
+//
+//   m  : 128 lattice points per tile = a BI x BH x BW box of (image, row, col) -- loaded per tap by ONE 4-D TMA box whose
+//        out-of-range coordinates are zero-filled by the hardware, which IS the TF 'SAME' padding
+//   n  : output channels (BN = 64 or 128 per tile), k : reduction channels in chunks of 64 (= one 128-byte swizzle row)
+//
+// Replaces the cuDNN kernels TF dispatches for Conv2D / Conv2DTranspose forward and dgrad
+// (ShmGANwithSSpecSeg.py:244-326, :365, :387, :410-411; tape.gradient :859,:868).
+#include "common.cuh"
+#include <cuda.h>
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp reads TMEM lane (base_lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+
+// smem matrix descriptor, 128-byte swizzle, rows of 128 bytes, 8-row groups 1024 bytes apart (K-major operand)
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;      // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: bf16 x bf16 -> fp32, M x N, A/B major bits
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward / dgrad kernel
+// ------------------------------------------------------------------------------------------------
+struct TcParams {
+    int ntaps; int dy[9], dx[9], wrow[9];
+    int kchunks;                 // K / 64
+    int Qh, Qw, BW, BH, BI;      // lattice size and the tile box (BI*BH*BW == 128)
+    int tiles_x, tiles_y;        // tiles per image row / column
+    int m_tiles, n_tiles;
+    int IS;                      // input traversal stride
+    int Hout, Wout, OS, py, px, ldout, Nn;
+    const float* bias; int act;
+    bf16* out;
+    float* stats;                // optional [Nimg][Nn][2] fp32 (sum, sumsq) of the stored activations
+};
+
+constexpr int TC_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
+constexpr int A_BYTES = 128 * 128;       // 128 rows x 64 bf16
+
+template <int BN>
+struct TcCfg {
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 64) ? 8 : 6;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+    using Cfg = TcCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::STAGES * A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;                          // [STAGES]
+    uint64_t* empty = bars + Cfg::STAGES;           // [STAGES]
+    uint64_t* tfull = bars + 2 * Cfg::STAGES;       // [2]
+    uint64_t* tempty = tfull + 2;                   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total_tiles = p.m_tiles * p.n_tiles;
+    const int niter = p.ntaps * p.kchunks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+                const int per_img = p.tiles_x * p.tiles_y;
+                int img0, qy0, qx0;
+                if (p.BI > 1) { img0 = mt * p.BI; qy0 = 0; qx0 = 0; }
+                else { img0 = mt / per_img; const int r = mt - img0 * per_img; qy0 = (r / p.tiles_x) * p.BH; qx0 = (r % p.tiles_x) * p.BW; }
+                for (int t = 0; t < p.ntaps; ++t) {
+                    const int cy = qy0 * p.IS + p.dy[t], cx = qx0 * p.IS + p.dx[t];
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(&empty[stage], phase ^ 1);
+                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                        tma_load_4d(sA + stage * A_BYTES, &tmA, &full[stage], kc * 64, cx, cy, img0);
+                        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kc * 64, p.wrow[t] + nt * BN);
+                        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+            int stage = 0; uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int it = 0; it < niter; ++it) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint64_t adesc = make_desc_sw128(smem_u32(sA + stage * A_BYTES), 16, 1024);
+                    const uint64_t bdesc = make_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES), 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)      // 4 x (K = 16) per 64-channel chunk: +32 bytes inside the swizzle row
+                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
+                    umma_commit(&empty[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[as]);
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers -> bias + activation -> bf16 -> global =====
+        const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
+        const int row = quad * 32 + lane;             // accumulator row = lattice point within the tile
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+            const int per_img = p.tiles_x * p.tiles_y;
+            int img, qy, qx;
+            {
+                const int x = row % p.BW, y = (row / p.BW) % p.BH, i = row / (p.BW * p.BH);
+                if (p.BI > 1) { img = mt * p.BI + i; qy = y; qx = x; }
+                else { const int im = mt / per_img; const int r = mt - im * per_img; img = im; qy = (r / p.tiles_x) * p.BH + y; qx = (r % p.tiles_x) * p.BW + x; }
+            }
+            const int oy = qy * p.OS + p.py, ox = qx * p.OS + p.px;
+            const bool ok = oy < p.Hout && ox < p.Wout;
+            bf16* dst = p.out + ((long long)(img * p.Hout + oy) * p.Wout + ox) * p.ldout + nt * BN;
+            mbar_wait(&tfull[as], (local >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(r[j]);
+                    if (p.bias) x += __ldg(p.bias + nt * BN + c * 32 + j);
+                    v[j] = act_fwd(x, p.act);
+                }
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 u;
+                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+                        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+                        *reinterpret_cast<uint4*>(dst + c * 32 + j) = u;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 4-D activation map: dims (C, W, H, N), bf16, box (64, bw, bh, bi), traversal stride `is` on W and H
+int encode_act(CUtensorMap* tm, const void* base, int C, int W, int H, int N, int ld, int bw, int bh, int bi, int is) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)(bw * is - (is - 1)), (cuuint32_t)(bh * is - (is - 1)), (cuuint32_t)bi};
+    cuuint32_t estr[4] = {1, (cuuint32_t)is, (cuuint32_t)is, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled(activation C=%d W=%d H=%d N=%d ld=%d box=%d,%d,%d is=%d) failed: %d", C, W, H, N, ld, bw, bh, bi, is, (int)r);
+    return SHM_OK;
+}
+// 2-D weight map: dims (K, rows), bf16, box (64, bn)
+int encode_w(CUtensorMap* tm, const void* base, int K, long long rows, int bn) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled(weights K=%d rows=%lld) failed: %d", K, rows, (int)r);
+    return SHM_OK;
+}
+
+inline void out_dims(const shm_conv_desc* d, int& Ho, int& Wo) {
+    if (d->transposed) { Ho = d->H * d->stride; Wo = d->W * d->stride; }
+    else { Ho = cdiv(d->H, d->stride); Wo = cdiv(d->W, d->stride); }
+}
+
+// choose the 128-point tile box for a lattice Qh x Qw over N images; returns false when it does not tile exactly
+bool pick_box(int N, int Qh, int Qw, int& BW, int& BH, int& BI) {
+    BW = Qw >= 128 ? 128 : Qw;
+    if (BW <= 0 || 128 % BW != 0 || Qw % BW != 0) return false;
+    BH = 128 / BW;
+    if (BH > Qh) BH = Qh;
+    if (Qh % BH != 0) return false;
+    BI = 128 / (BW * BH);
+    if (BI * BW * BH != 128) return false;
+    if (BI > 1 && (N % BI != 0)) return false;
+    return true;
+}
+
+struct Geometry {
+    // operand A tensor (what TMA reads), lattice, output tensor
+    int Hin, Win, ldin, K;
+    int Qh, Qw, IS;
+    int Hout, Wout, ldout, Nn, OS;
+};
+
+int launch_tc(const Geometry& g, int N, const void* in, const void* w_tc, int wrows_total, const float* bias, int act, void* out,
+              const int* tdy, const int* tdx, const int* twrow, int ntaps, int py, int px, cudaStream_t st) {
+    TcParams p{};
+    if (!pick_box(N, g.Qh, g.Qw, p.BW, p.BH, p.BI)) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: lattice %dx%d (N=%d) does not tile into 128-point boxes", g.Qh, g.Qw, N);
+    p.ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) { p.dy[t] = tdy[t]; p.dx[t] = tdx[t]; p.wrow[t] = twrow[t]; }
+    p.kchunks = g.K / 64;
+    p.Qh = g.Qh; p.Qw = g.Qw; p.IS = g.IS;
+    p.tiles_x = g.Qw / p.BW; p.tiles_y = g.Qh / p.BH;
+    p.m_tiles = (int)((long long)N * g.Qh * g.Qw / 128);
+    const int BN = (g.Nn % 128 == 0) ? 128 : 64;
+    p.n_tiles = g.Nn / BN;
+    p.Hout = g.Hout; p.Wout = g.Wout; p.OS = g.OS; p.py = py; p.px = px; p.ldout = g.ldout; p.Nn = g.Nn;
+    p.bias = bias; p.act = act; p.out = (bf16*)out; p.stats = nullptr;
+    CUtensorMap tmA, tmB;
+    if (int rc = encode_act(&tmA, in, g.K, g.Win, g.Hin, N, g.ldin, p.BW, p.BH, p.BI, g.IS)) return rc;
+    if (int rc = encode_w(&tmB, w_tc, g.K, wrows_total, BN)) return rc;
+    const int total = p.m_tiles * p.n_tiles;
+    int grid = shm_num_sms();
+    if (grid > total) grid = total;
+    if (ntaps == 0 || total == 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: empty problem");
+    if (BN == 128) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM); attr = true; }
+        conv_tc_kernel<128><<<grid, TC_THREADS, TcCfg<128>::SMEM, st>>>(tmA, tmB, p);
+    } else {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM); attr = true; }
+        conv_tc_kernel<64><<<grid, TC_THREADS, TcCfg<64>::SMEM, st>>>(tmA, tmB, p);
+    }
+    SHM_CHECK_LAUNCH("conv_tc_kernel");
+    return SHM_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// wgrad kernel:  dW[tap][a][b] += sum_{lattice q} A[q*SA + offA_tap, a] * B[q*SB + offB_tap, b]
+//   GEMM M = 128 "a" channels (two 64-channel M-blocks; for 64-channel layers the two blocks are two TAPS),
+//   N = BN "b" channels, K = lattice points in chunks of 64 (split over CTAs; fp32 atomics into dW).
+//   Both operands are MN-major in shared memory: a TMA box is [64 points][64 channels] = rows of 128 bytes.
+// ------------------------------------------------------------------------------------------------
+struct WgParams {
+    int nblocks;                       // M-blocks = ntaps * Ca/64
+    int cblocks;                       // Ca / 64
+    int ntaps; int day[9], dax[9], dby[9], dbx[9]; long long woff[9];
+    int Qh, Qw, BW, BH, BI, tiles_x, tiles_y;
+    int SA, SB;
+    int kblocks, kb_per_split;
+    int m_tiles, n_tiles;
+    int ldw;                           // elements between consecutive "a" rows of dW (= Cb)
+    float* dW;
+};
+
+constexpr int WG_STAGES = 6;
+template <int BN>
+struct WgCfg {
+    static constexpr int A_ST = 2 * 8192;
+    static constexpr int B_ST = (BN / 64) * 8192;
+    static constexpr int STAGE_BYTES = A_ST + B_ST;
+    static constexpr int SMEM = WG_STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const WgParams p) {
+    using Cfg = WgCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + WG_STAGES * Cfg::A_ST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WG_STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + WG_STAGES;
+    uint64_t* tfull = bars + 2 * WG_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x % p.n_tiles;
+    const int mt = (blockIdx.x / p.n_tiles) % p.m_tiles;
+    const int split = blockIdx.x / (p.n_tiles * p.m_tiles);
+    const int kb0 = split * p.kb_per_split;
+    int kb1 = kb0 + p.kb_per_split; if (kb1 > p.kblocks) kb1 = p.kblocks;
+    // the two M-blocks of this tile: (tap, channel block)
+    const int blk0 = mt * 2, blk1 = (mt * 2 + 1 < p.nblocks) ? mt * 2 + 1 : mt * 2;
+    const int tap0 = blk0 / p.cblocks, cb0 = blk0 % p.cblocks, tap1 = blk1 / p.cblocks, cb1 = blk1 % p.cblocks;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int s = 0; s < WG_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const int per_img = p.tiles_x * p.tiles_y;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                int img0, qy0, qx0;
+                if (p.BI > 1) { img0 = kb * p.BI; qy0 = 0; qx0 = 0; }
+                else { img0 = kb / per_img; const int r = kb - img0 * per_img; qy0 = (r / p.tiles_x) * p.BH; qx0 = (r % p.tiles_x) * p.BW; }
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                uint8_t* a = sA + stage * Cfg::A_ST;
+                uint8_t* b = sB + stage * Cfg::B_ST;
+                tma_load_4d(a, &tmA, &full[stage], cb0 * 64, qx0 * p.SA + p.dax[tap0], qy0 * p.SA + p.day[tap0], img0);
+                tma_load_4d(a + 8192, &tmA, &full[stage], cb1 * 64, qx0 * p.SA + p.dax[tap1], qy0 * p.SA + p.day[tap1], img0);
+                // the B operand is shifted by its own tap offset (zero for Conv2D where B = dy): both M-blocks of a tile must
+                // therefore share the B offset, which holds because offB != 0 only when cblocks >= 2 pairs blocks of ONE tap
+#pragma unroll
+                for (int j = 0; j < BN / 64; ++j)
+                    tma_load_4d(b + j * 8192, &tmB, &full[stage], nt * BN + j * 64, qx0 * p.SB + p.dbx[tap0], qy0 * p.SB + p.dby[tap0], img0);
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                // MN-major SW128: 64-channel atoms LBO = 8192 bytes apart, 8-point K groups SBO = 1024 bytes apart
+                const uint64_t adesc = make_desc_sw128(smem_u32(sA + stage * Cfg::A_ST), 8192, 1024);
+                const uint64_t bdesc = make_desc_sw128(smem_u32(sB + stage * Cfg::B_ST), 8192, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)      // 16 points per MMA = 2048 bytes
+                    umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb > kb0) || (k > 0));
+                umma_commit(&empty[stage]);
+                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull);
+        }
+    } else if (kb1 > kb0) {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int half = row >> 6;
+        const bool ok = !(half == 1 && blk1 == blk0);          // odd M-block count: upper half is a duplicate
+        const int tap = half ? tap1 : tap0, cb = half ? cb1 : cb0;
+        float* dst = p.dW + p.woff[tap] + (long long)(cb * 64 + (row & 63)) * p.ldw + nt * BN;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(c * 32), r);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) atomicAdd(dst + c * 32 + j, __uint_as_float(r[j]));
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+bool pick_box64(int N, int Qh, int Qw, int& BW, int& BH, int& BI) {
+    BW = Qw >= 64 ? 64 : Qw;
+    if (BW <= 0 || 64 % BW != 0 || Qw % BW != 0) return false;
+    BH = 64 / BW;
+    if (BH > Qh) BH = Qh;
+    if (Qh % BH != 0) return false;
+    BI = 64 / (BW * BH);
+    if (BI * BW * BH != 64) return false;
+    if (BI > 1 && (N % BI != 0)) return false;
+    return true;
+}
+
+// weights -> bf16 [tap][n][k]
+__global__ void prep_w_kernel(const float* __restrict__ w, bf16* __restrict__ o, int K, int Nn, long long tap_elems, int w_ks, int w_ns, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % K);
+        const long long t2 = i / K;
+        const int n = (int)(t2 % Nn);
+        const long long tap = t2 / Nn;
+        o[i] = __float2bfloat16_rn(__ldg(w + tap * tap_elems + (long long)k * w_ks + (long long)n * w_ns));
+    }
+}
+
+int tc_check(const shm_conv_desc* d) {
+    SHM_REQUIRE(d != nullptr, "conv desc is NULL");
+    if (d->dtype != SHM_BF16) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: needs dtype bf16");
+    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: Cin=%d / Cout=%d must be multiples of 64", d->Cin, d->Cout);
+    if (d->ldx % 8 != 0 || d->ldy % 8 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: ld must be a multiple of 8");
+    if (d->kh < 1 || d->kh > 3 || d->kw < 1 || d->kw > 3 || (d->stride != 1 && d->stride != 2)) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: kernel/stride unsupported");
+    if (d->transposed && d->stride != 2) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: transposed conv needs stride 2");
+    return SHM_OK;
+}
+
+}  // namespace
+
+extern "C" int64_t shm_conv2d_tc_weight_elems(const shm_conv_desc* d) {
+    if (!d) return 0;
+    return (int64_t)d->kh * d->kw * d->Cin * d->Cout;
+}
+
+extern "C" int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, void* w_tc, int for_dgrad, void* stream) {
+    if (int rc = tc_check(d)) return rc;
+    SHM_REQUIRE(w && w_tc, "shm_conv2d_tc_prep_weights: NULL buffer");
+    // GEMM reduction dim K / output dim Nn and the strides of (k, n) inside one Keras tap slice
+    int K, Nn, w_ks, w_ns;
+    if (!d->transposed) {          // (kh,kw,Cin,Cout)
+        if (!for_dgrad) { K = d->Cin; Nn = d->Cout; w_ks = d->Cout; w_ns = 1; }
+        else            { K = d->Cout; Nn = d->Cin; w_ks = 1; w_ns = d->Cout; }
+    } else {                       // (kh,kw,Cout,Cin)
+        if (!for_dgrad) { K = d->Cin; Nn = d->Cout; w_ks = 1; w_ns = d->Cin; }
+        else            { K = d->Cout; Nn = d->Cin; w_ks = d->Cin; w_ns = 1; }
+    }
+    const long long total = (long long)d->kh * d->kw * d->Cin * d->Cout;
+    long long g = cdiv64(total, 256);
+    if (g > shm_num_sms() * 16) g = shm_num_sms() * 16;
+    prep_w_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_tc, K, Nn, (long long)d->Cin * d->Cout, w_ks, w_ns, total);
+    SHM_CHECK_LAUNCH("prep_w_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad) {
+    if (tc_check(d) != SHM_OK) return 0;
+    int Ho, Wo; out_dims(d, Ho, Wo);
+    int BW, BH, BI;
+    (void)for_dgrad;
+    // in every form the lattice is the SMALL image: Ho x Wo of a strided conv, H x W of a transposed conv
+    const int Qh = d->transposed ? d->H : Ho, Qw = d->transposed ? d->W : Wo;
+    if (d->stride == 2 && ((d->transposed ? Ho : d->H) % 2 != 0 || (d->transposed ? Wo : d->W) % 2 != 0)) return 0;
+    return pick_box(d->N, Qh, Qw, BW, BH, BI) ? 1 : 0;
+}
+
+// forward: Conv2D (gather form) or Conv2DTranspose (scatter-by-parity form, 4 launches)
+extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, void* stream) {
+    if (int rc = tc_check(d)) return rc;
+    SHM_REQUIRE(x && w_tc && y, "shm_conv2d_tc_fwd: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int Ho, Wo; out_dims(d, Ho, Wo);
+    const int s = d->stride;
+    const int wrows = d->kh * d->kw * d->Cout;
+    int tdy[9], tdx[9], twr[9];
+    if (!d->transposed) {
+        const int pby = same_pad_before(d->H, d->kh, s), pbx = same_pad_before(d->W, d->kw, s);
+        int nt = 0;
+        for (int ky = 0; ky < d->kh; ++ky)
+            for (int kx = 0; kx < d->kw; ++kx) { tdy[nt] = ky - pby; tdx[nt] = kx - pbx; twr[nt] = (ky * d->kw + kx) * d->Cout; ++nt; }
+        Geometry g{d->H, d->W, d->ldx, d->Cin, Ho, Wo, s, Ho, Wo, d->ldy, d->Cout, 1};
+        return launch_tc(g, d->N, x, w_tc, wrows, bias, d->act, y, tdy, tdx, twr, nt, 0, 0, st);
+    }
+    // transposed: out[p] = sum_{o,k: s*o + k - pb = p} x[o] W[k];  p = s*q + r
+    const int pby = same_pad_before(Ho, d->kh, s), pbx = same_pad_before(Wo, d->kw, s);
+    for (int ry = 0; ry < s; ++ry)
+        for (int rx = 0; rx < s; ++rx) {
+            int nt = 0;
+            for (int ky = 0; ky < d->kh; ++ky) {
+                if (((ry + pby - ky) % s) != 0) continue;
+                for (int kx = 0; kx < d->kw; ++kx) {
+                    if (((rx + pbx - kx) % s) != 0) continue;
+                    tdy[nt] = (ry + pby - ky) / s; tdx[nt] = (rx + pbx - kx) / s; twr[nt] = (ky * d->kw + kx) * d->Cout; ++nt;
+                }
+            }
+            if (nt == 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: parity class without taps (k < stride)");
+            Geometry g{d->H, d->W, d->ldx, d->Cin, d->H, d->W, 1, Ho, Wo, d->ldy, d->Cout, s};
+            if (int rc = launch_tc(g, d->N, x, w_tc, wrows, bias, d->act, y, tdy, tdx, twr, nt, ry, rx, st)) return rc;
+        }
+    return SHM_OK;
+}
+
+// dgrad: dx = dL/dx from dy = dL/d(pre-activation); w_tc prepared with for_dgrad = 1
+extern "C" int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const void* w_tc, void* dx, void* stream) {
+    if (int rc = tc_check(d)) return rc;
+    SHM_REQUIRE(dy && w_tc && dx, "shm_conv2d_tc_dgrad: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int Ho, Wo; out_dims(d, Ho, Wo);
+    const int s = d->stride;
+    const int wrows = d->kh * d->kw * d->Cin;
+    int tdy[9], tdx[9], twr[9];
+    if (d->transposed) {
+        // dx[o] = sum_k dy[s*o + k - pb] W[k]^T : gather at stride s from the big image
+        const int pby = same_pad_before(Ho, d->kh, s), pbx = same_pad_before(Wo, d->kw, s);
+        int nt = 0;
+        for (int ky = 0; ky < d->kh; ++ky)
+            for (int kx = 0; kx < d->kw; ++kx) { tdy[nt] = ky - pby; tdx[nt] = kx - pbx; twr[nt] = (ky * d->kw + kx) * d->Cin; ++nt; }
+        Geometry g{Ho, Wo, d->ldy, d->Cout, d->H, d->W, s, d->H, d->W, d->ldx, d->Cin, 1};
+        return launch_tc(g, d->N, dy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, tdy, tdx, twr, nt, 0, 0, st);
+    }
+    // Conv2D dgrad: dx[p] = sum_{o,k: s*o + k - pb = p} dy[o] W[k]^T  (scatter by parity; one class when s == 1)
+    const int pby = same_pad_before(d->H, d->kh, s), pbx = same_pad_before(d->W, d->kw, s);
+    for (int ry = 0; ry < s; ++ry)
+        for (int rx = 0; rx < s; ++rx) {
+            int nt = 0;
+            for (int ky = 0; ky < d->kh; ++ky) {
+                if (((ry + pby - ky) % s) != 0) continue;
+                for (int kx = 0; kx < d->kw; ++kx) {
+                    if (((rx + pbx - kx) % s) != 0) continue;
+                    tdy[nt] = (ry + pby - ky) / s; tdx[nt] = (rx + pbx - kx) / s; twr[nt] = (ky * d->kw + kx) * d->Cin; ++nt;
+                }
+            }
+            if (nt == 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: parity class without taps");
+            Geometry g{Ho, Wo, d->ldy, d->Cout, cdiv(d->H - ry, s), cdiv(d->W - rx, s), 1, d->H, d->W, d->ldx, d->Cin, s};
+            if (int rc = launch_tc(g, d->N, dy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, tdy, tdx, twr, nt, ry, rx, st)) return rc;
+        }
+    return SHM_OK;
+}
+
+// wgrad: dw += dL/dw in the Keras layout (fp32 atomics).  x and dy are bf16.
+extern "C" int shm_conv2d_tc_wgrad(const shm_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
+    if (int rc = tc_check(d)) return rc;
+    SHM_REQUIRE(x && dy && dw, "shm_conv2d_tc_wgrad: NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int Ho, Wo; out_dims(d, Ho, Wo);
+    const int s = d->stride;
+    WgParams p{};
+    const void *A, *B;
+    int Ca, Cb, HA, WA, lda, HB, WB, ldb;
+    p.ntaps = 0;
+    if (!d->transposed) {
+        // dW[tap][ci][co] = sum_q x[q*s + k - pb, ci] dy[q, co]
+        A = x; Ca = d->Cin; HA = d->H; WA = d->W; lda = d->ldx; p.SA = s;
+        B = dy; Cb = d->Cout; HB = Ho; WB = Wo; ldb = d->ldy; p.SB = 1;
+        p.Qh = Ho; p.Qw = Wo;
+        const int pby = same_pad_before(d->H, d->kh, s), pbx = same_pad_before(d->W, d->kw, s);
+        for (int ky = 0; ky < d->kh; ++ky)
+            for (int kx = 0; kx < d->kw; ++kx) {
+                const int t = p.ntaps++;
+                p.day[t] = ky - pby; p.dax[t] = kx - pbx; p.dby[t] = 0; p.dbx[t] = 0;
+                p.woff[t] = (long long)(ky * d->kw + kx) * d->Cin * d->Cout;
+            }
+    } else {
+        // dW[tap][co][ci] = sum_o dy[o*s + k - pb, co] x[o, ci]
+        A = dy; Ca = d->Cout; HA = Ho; WA = Wo; lda = d->ldy; p.SA = s;
+        B = x; Cb = d->Cin; HB = d->H; WB = d->W; ldb = d->ldx; p.SB = 1;
+        p.Qh = d->H; p.Qw = d->W;
+        const int pby = same_pad_before(Ho, d->kh, s), pbx = same_pad_before(Wo, d->kw, s);
+        for (int ky = 0; ky < d->kh; ++ky)
+            for (int kx = 0; kx < d->kw; ++kx) {
+                const int t = p.ntaps++;
+                p.day[t] = ky - pby; p.dax[t] = kx - pbx; p.dby[t] = 0; p.dbx[t] = 0;
+                p.woff[t] = (long long)(ky * d->kw + kx) * d->Cin * d->Cout;
+            }
+    }
+    if (!pick_box64(d->N, p.Qh, p.Qw, p.BW, p.BH, p.BI)) SHM_FAIL(SHM_EUNSUPPORTED, "wgrad_tc: lattice %dx%d does not tile into 64-point boxes", p.Qh, p.Qw);
+    p.tiles_x = p.Qw / p.BW; p.tiles_y = p.Qh / p.BH;
+    p.cblocks = Ca / 64;
+    p.nblocks = p.ntaps * p.cblocks;
+    p.m_tiles = (p.nblocks + 1) / 2;
+    const int BN = (Cb % 128 == 0) ? 128 : 64;
+    p.n_tiles = Cb / BN;
+    p.kblocks = (int)((long long)d->N * p.Qh * p.Qw / 64);
+    p.ldw = Cb; p.dW = dw;
+    // split K so that the grid covers the SMs ~2x, keeping >= 8 K-blocks per CTA
+    const int tiles = p.m_tiles * p.n_tiles;
+    int splits = cdiv(shm_num_sms() * 2, tiles);
+    if (splits > cdiv(p.kblocks, 8)) splits = cdiv(p.kblocks, 8);
+    if (splits < 1) splits = 1;
+    p.kb_per_split = cdiv(p.kblocks, splits);
+    splits = cdiv(p.kblocks, p.kb_per_split);
+    CUtensorMap tmA, tmB;
+    if (int rc = encode_act(&tmA, A, Ca, WA, HA, d->N, lda, p.BW, p.BH, p.BI, p.SA)) return rc;
+    if (int rc = encode_act(&tmB, B, Cb, WB, HB, d->N, ldb, p.BW, p.BH, p.BI, p.SB)) return rc;
+    const int grid = tiles * splits;
+    if (BN == 128) {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<128>::SMEM); attr = true; }
+        wgrad_tc_kernel<128><<<grid, TC_THREADS, WgCfg<128>::SMEM, st>>>(tmA, tmB, p);
+    } else {
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<64>::SMEM); attr = true; }
+        wgrad_tc_kernel<64><<<grid, TC_THREADS, WgCfg<64>::SMEM, st>>>(tmA, tmB, p);
+    }
+    SHM_CHECK_LAUNCH("wgrad_tc_kernel");
+    return SHM_OK;
+}

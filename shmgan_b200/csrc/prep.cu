@@ -1,0 +1,305 @@
+// prep.cu -- polarimetric preprocessing and colour-space kernels (pure HBM-bandwidth work).
+//   pseudo-diffuse min-of-4          utils.py:102-106
+//   rgb->yuv + whole-image std scale  ShmGANwithSSpecSeg.py:480-484, :1271-1309
+//   averageCbCr                       :505
+//   generator input assembly          :509-531, :576-594, test.py:227-235
+//   yuv->rgb of concat(Y, CbCr)       :544-553, :613-624
+#include "common.cuh"
+
+namespace {
+
+// tf.image.rgb_to_yuv / yuv_to_rgb kernels (out = in @ K)
+__device__ __forceinline__ void rgb2yuv(float r, float g, float b, float& y, float& u, float& v) {
+    y = 0.299f * r + 0.587f * g + 0.114f * b;
+    u = -0.14714119f * r + -0.28886916f * g + 0.43601035f * b;
+    v = 0.61497538f * r + -0.51496512f * g + -0.10001026f * b;
+}
+__device__ __forceinline__ void yuv2rgb(float y, float u, float v, float& r, float& g, float& b) {
+    r = y + 1.13988303f * v;
+    g = y + -0.394642334f * u + -0.58062185f * v;
+    b = y + 2.03206185f * u;
+}
+
+inline int flat_grid(long long total, int block = 256) {
+    long long g = cdiv64(total, block);
+    const long long cap = (long long)shm_num_sms() * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+// ---- pseudo diffuse ---------------------------------------------------------------------------
+__global__ void min4_f32_kernel(const float4* __restrict__ a, const float4* __restrict__ b, const float4* __restrict__ c,
+                                const float4* __restrict__ d, float4* __restrict__ o, long long n4) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 x = __ldg(a + i), y = __ldg(b + i), z = __ldg(c + i), w = __ldg(d + i);
+        float4 r;
+        r.x = fminf(fminf(x.x, y.x), fminf(z.x, w.x));
+        r.y = fminf(fminf(x.y, y.y), fminf(z.y, w.y));
+        r.z = fminf(fminf(x.z, y.z), fminf(z.z, w.z));
+        r.w = fminf(fminf(x.w, y.w), fminf(z.w, w.w));
+        o[i] = r;
+    }
+}
+__global__ void min4_u8_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const uint4* __restrict__ c,
+                               const uint4* __restrict__ d, uint4* __restrict__ o, long long n16) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (long long)gridDim.x * blockDim.x) {
+        const uint4 x = __ldg(a + i), y = __ldg(b + i), z = __ldg(c + i), w = __ldg(d + i);
+        uint4 r;
+        r.x = __vminu4(__vminu4(x.x, y.x), __vminu4(z.x, w.x));
+        r.y = __vminu4(__vminu4(x.y, y.y), __vminu4(z.y, w.y));
+        r.z = __vminu4(__vminu4(x.z, y.z), __vminu4(z.z, w.z));
+        r.w = __vminu4(__vminu4(x.w, y.w), __vminu4(z.w, w.w));
+        o[i] = r;
+    }
+}
+__global__ void min4_bf16_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, const uint4* __restrict__ c,
+                                 const uint4* __restrict__ d, uint4* __restrict__ o, long long n8) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        uint4 x = __ldg(a + i), y = __ldg(b + i), z = __ldg(c + i), w = __ldg(d + i), r;
+        const __nv_bfloat162* px = reinterpret_cast<const __nv_bfloat162*>(&x);
+        const __nv_bfloat162* py = reinterpret_cast<const __nv_bfloat162*>(&y);
+        const __nv_bfloat162* pz = reinterpret_cast<const __nv_bfloat162*>(&z);
+        const __nv_bfloat162* pw = reinterpret_cast<const __nv_bfloat162*>(&w);
+        __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pr[j] = __hmin2(__hmin2(px[j], py[j]), __hmin2(pz[j], pw[j]));
+        o[i] = r;
+    }
+}
+template <typename T>
+__global__ void min4_tail_kernel(const T* a, const T* b, const T* c, const T* d, T* o, long long beg, long long n) {
+    for (long long i = beg + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        T m = a[i];
+        if (b[i] < m) m = b[i];
+        if (c[i] < m) m = c[i];
+        if (d[i] < m) m = d[i];
+        o[i] = m;
+    }
+}
+
+// ---- yuv stats / standardise -------------------------------------------------------------------
+// one block handles a pixel range of one image; sums[n] += (sum v, sum v^2) over the 3 yuv channels
+__global__ void __launch_bounds__(256) yuv_stats_kernel(const float* __restrict__ rgb, int HW, double* __restrict__ sums, int ppb) {
+    __shared__ double sm[32];
+    const int n = blockIdx.y;
+    const float* base = rgb + (long long)n * HW * 3;
+    const int pbeg = blockIdx.x * ppb, pend = min(pbeg + ppb, HW);
+    float s = 0.f, q = 0.f;
+    // 4 pixels = 12 floats = 3 float4 per thread iteration (HW % 4 == 0 and ppb % 4 == 0 enforced by the host)
+    for (int p = pbeg + threadIdx.x * 4; p < pend; p += blockDim.x * 4) {
+        const float4* src = reinterpret_cast<const float4*>(base + (long long)p * 3);
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        const float px[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float y, u, v;
+            rgb2yuv(px[3 * j], px[3 * j + 1], px[3 * j + 2], y, u, v);
+            s += y + u + v;
+            q = fmaf(y, y, fmaf(u, u, fmaf(v, v, q)));
+        }
+    }
+    const double bs = block_sum((double)s, sm);
+    const double bq = block_sum((double)q, sm);
+    if (threadIdx.x == 0) { atomicAdd(&sums[n * 2 + 0], bs); atomicAdd(&sums[n * 2 + 1], bq); }
+}
+
+__global__ void __launch_bounds__(256) yuv_standardize_kernel(const float* __restrict__ rgb, int HW, const double* __restrict__ sums,
+                                                              float* __restrict__ yuv, float* __restrict__ scale, int ppb) {
+    const int n = blockIdx.y;
+    const double cnt = (double)HW * 3.0;
+    const double mean = sums[n * 2] / cnt;
+    double var = sums[n * 2 + 1] / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    float sc = (float)sqrt(var);
+    sc = fmaxf(sc, 1.0f / 256.0f);          // rsqrt(num_pixels = 65536), ShmGANwithSSpecSeg.py:1280,1299
+    if (blockIdx.x == 0 && threadIdx.x == 0) scale[n] = sc;
+    const float inv = 1.0f / sc;
+    const float* base = rgb + (long long)n * HW * 3;
+    float* ob = yuv + (long long)n * HW * 3;
+    const int pbeg = blockIdx.x * ppb, pend = min(pbeg + ppb, HW);
+    for (int p = pbeg + threadIdx.x * 4; p < pend; p += blockDim.x * 4) {
+        const float4* src = reinterpret_cast<const float4*>(base + (long long)p * 3);
+        const float4 a = __ldg(src), b = __ldg(src + 1), c = __ldg(src + 2);
+        const float px[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        float o[12];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float y, u, v;
+            rgb2yuv(px[3 * j], px[3 * j + 1], px[3 * j + 2], y, u, v);
+            o[3 * j] = y / sc; o[3 * j + 1] = u / sc; o[3 * j + 2] = v / sc;
+        }
+        (void)inv;
+        float4* dst = reinterpret_cast<float4*>(ob + (long long)p * 3);
+        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        dst[2] = make_float4(o[8], o[9], o[10], o[11]);
+    }
+}
+
+__global__ void avg_cbcr_kernel(const float* __restrict__ y0, const float* __restrict__ y1, const float* __restrict__ y2,
+                                const float* __restrict__ y3, const float* __restrict__ y4, float* __restrict__ out, long long npix) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        const long long i = p * 3;
+        const float u = (((y0[i + 1] + y1[i + 1]) + y2[i + 1]) + y3[i + 1]) + y4[i + 1];
+        const float v = (((y0[i + 2] + y1[i + 2]) + y2[i + 2]) + y3[i + 2]) + y4[i + 2];
+        reinterpret_cast<float2*>(out)[p] = make_float2(u / 5.0f, v / 5.0f);
+    }
+}
+
+struct AsmSrc { const float* p[5]; int ld[5]; };
+
+template <typename T>
+__global__ void assemble_kernel(AsmSrc s, int onehot, T* __restrict__ out, long long npix) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        T* o = out + p * 10;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) stf(o + j, s.p[j] ? __ldg(s.p[j] + p * s.ld[j]) : 0.f);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) stf(o + 5 + j, j == onehot ? 1.f : 0.f);
+    }
+}
+
+struct Slots { int s[5]; int n; };
+template <typename T>
+__global__ void assemble_bwd_kernel(const T* __restrict__ din, Slots sl, float* __restrict__ dgen, long long npix) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int j = 0; j < sl.n; ++j) acc += ldf(din + p * 10 + sl.s[j]);
+        dgen[p] += acc;
+    }
+}
+
+template <typename T>
+__global__ void yuv2rgb_kernel(const float* __restrict__ Y, const float* __restrict__ cbcr, long long npix_c, float* __restrict__ rgb,
+                               T* __restrict__ rgb_lp, long long npix) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        const float2 uv = __ldg(reinterpret_cast<const float2*>(cbcr) + (p % npix_c));
+        float r, g, b;
+        yuv2rgb(__ldg(Y + p), uv.x, uv.y, r, g, b);
+        if (rgb) { rgb[p * 3] = r; rgb[p * 3 + 1] = g; rgb[p * 3 + 2] = b; }
+        if (rgb_lp) { stf(rgb_lp + p * 3, r); stf(rgb_lp + p * 3 + 1, g); stf(rgb_lp + p * 3 + 2, b); }
+    }
+}
+
+template <typename T>
+__global__ void yuv2rgb_bwd_kernel(const float* __restrict__ da, const T* __restrict__ db, float* __restrict__ dY, long long npix, int accumulate) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        float acc = accumulate ? dY[p] : 0.f;
+        // d/dY of (r,g,b) = (1,1,1): first row of the yuv->rgb kernel
+        if (da) acc += (da[p * 3] + da[p * 3 + 1]) + da[p * 3 + 2];
+        if (db) acc += (ldf(db + p * 3) + ldf(db + p * 3 + 1)) + ldf(db + p * 3 + 2);
+        dY[p] = acc;
+    }
+}
+
+}  // namespace
+
+extern "C" int shm_pseudo_diffuse_min4(const void* i0, const void* i45, const void* i90, const void* i135, void* out, int64_t n,
+                                       int dtype, void* stream) {
+    SHM_REQUIRE(i0 && i45 && i90 && i135 && out && n >= 0, "shm_pseudo_diffuse_min4: bad args");
+    if (n == 0) return SHM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const uintptr_t al = reinterpret_cast<uintptr_t>(i0) | reinterpret_cast<uintptr_t>(i45) | reinterpret_cast<uintptr_t>(i90) |
+                         reinterpret_cast<uintptr_t>(i135) | reinterpret_cast<uintptr_t>(out);
+    const bool aligned = (al & 15) == 0;
+    const int esize = dtype == 0 ? 4 : (dtype == 1 ? 2 : 1);
+    SHM_REQUIRE(dtype >= 0 && dtype <= 2, "shm_pseudo_diffuse_min4: dtype %d (0 f32, 1 bf16, 2 u8)", dtype);
+    const int per = 16 / esize;
+    const long long nv = aligned ? n / per : 0;
+    if (nv > 0) {
+        const int grid = flat_grid(nv);
+        if (dtype == 0) min4_f32_kernel<<<grid, 256, 0, st>>>((const float4*)i0, (const float4*)i45, (const float4*)i90, (const float4*)i135, (float4*)out, nv);
+        else if (dtype == 1) min4_bf16_kernel<<<grid, 256, 0, st>>>((const uint4*)i0, (const uint4*)i45, (const uint4*)i90, (const uint4*)i135, (uint4*)out, nv);
+        else min4_u8_kernel<<<grid, 256, 0, st>>>((const uint4*)i0, (const uint4*)i45, (const uint4*)i90, (const uint4*)i135, (uint4*)out, nv);
+        SHM_CHECK_LAUNCH("min4_kernel");
+    }
+    const long long done = nv * per;
+    if (done < n) {
+        const int grid = flat_grid(n - done);
+        if (dtype == 0) min4_tail_kernel<float><<<grid, 256, 0, st>>>((const float*)i0, (const float*)i45, (const float*)i90, (const float*)i135, (float*)out, done, n);
+        else if (dtype == 1) min4_tail_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)i0, (const bf16*)i45, (const bf16*)i90, (const bf16*)i135, (bf16*)out, done, n);
+        else min4_tail_kernel<unsigned char><<<grid, 256, 0, st>>>((const unsigned char*)i0, (const unsigned char*)i45, (const unsigned char*)i90, (const unsigned char*)i135, (unsigned char*)out, done, n);
+        SHM_CHECK_LAUNCH("min4_tail_kernel");
+    }
+    return SHM_OK;
+}
+
+static inline int yuv_ppb(int HW, int N) {
+    long long want = (long long)shm_num_sms() * 8 / (N > 0 ? N : 1);
+    if (want < 1) want = 1;
+    long long ppb = cdiv64(HW, want);
+    if (ppb < 1024) ppb = 1024;
+    if (ppb > 65536) ppb = 65536;       // <= 256 pixels (768 values) per fp32 partial
+    return (int)(cdiv64(ppb, 4) * 4);
+}
+
+extern "C" int shm_yuv_stats(const float* rgb, int N, int HW, double* sums, void* stream) {
+    SHM_REQUIRE(rgb && sums && N > 0 && HW > 0, "shm_yuv_stats: bad args");
+    SHM_REQUIRE(HW % 4 == 0 && (reinterpret_cast<uintptr_t>(rgb) & 15) == 0, "shm_yuv_stats: HW must be a multiple of 4 and rgb 16B-aligned");
+    const int ppb = yuv_ppb(HW, N);
+    yuv_stats_kernel<<<dim3(cdiv(HW, ppb), N), 256, 0, (cudaStream_t)stream>>>(rgb, HW, sums, ppb);
+    SHM_CHECK_LAUNCH("yuv_stats_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_yuv_standardize(const float* rgb, int N, int HW, const double* sums, float* yuv, float* scale, void* stream) {
+    SHM_REQUIRE(rgb && sums && yuv && scale && N > 0 && HW > 0, "shm_yuv_standardize: bad args");
+    SHM_REQUIRE(HW % 4 == 0 && ((reinterpret_cast<uintptr_t>(rgb) | reinterpret_cast<uintptr_t>(yuv)) & 15) == 0,
+                "shm_yuv_standardize: HW must be a multiple of 4 and buffers 16B-aligned");
+    const int ppb = yuv_ppb(HW, N);
+    yuv_standardize_kernel<<<dim3(cdiv(HW, ppb), N), 256, 0, (cudaStream_t)stream>>>(rgb, HW, sums, yuv, scale, ppb);
+    SHM_CHECK_LAUNCH("yuv_standardize_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_avg_cbcr(const float* y0, const float* y1, const float* y2, const float* y3, const float* y4, float* out,
+                            int64_t npix, void* stream) {
+    SHM_REQUIRE(y0 && y1 && y2 && y3 && y4 && out && npix > 0, "shm_avg_cbcr: bad args");
+    avg_cbcr_kernel<<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(y0, y1, y2, y3, y4, out, npix);
+    SHM_CHECK_LAUNCH("avg_cbcr_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_assemble_input(const float* const src[5], const int32_t src_ld[5], int onehot, void* out, int64_t npix, int dtype, void* stream) {
+    SHM_REQUIRE(src && src_ld && out && npix > 0 && onehot >= 0 && onehot < 5, "shm_assemble_input: bad args");
+    AsmSrc s;
+    for (int j = 0; j < 5; ++j) { s.p[j] = src[j]; s.ld[j] = src_ld[j]; }
+    DISPATCH_DTYPE(dtype, T, {
+        assemble_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(s, onehot, (T*)out, npix);
+        SHM_CHECK_LAUNCH("assemble_kernel");
+        return SHM_OK;
+    })
+}
+
+extern "C" int shm_assemble_bwd(const void* din, int dtype, const int32_t slots[5], int nslots, float* dgen, int64_t npix, void* stream) {
+    SHM_REQUIRE(din && dgen && npix > 0 && nslots >= 0 && nslots <= 5, "shm_assemble_bwd: bad args");
+    if (nslots == 0) return SHM_OK;
+    Slots sl; sl.n = nslots;
+    for (int j = 0; j < 5; ++j) sl.s[j] = j < nslots ? slots[j] : 0;
+    for (int j = 0; j < nslots; ++j) SHM_REQUIRE(slots[j] >= 0 && slots[j] < 5, "shm_assemble_bwd: slot out of range");
+    DISPATCH_DTYPE(dtype, T, {
+        assemble_bwd_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>((const T*)din, sl, dgen, npix);
+        SHM_CHECK_LAUNCH("assemble_bwd_kernel");
+        return SHM_OK;
+    })
+}
+
+extern "C" int shm_yuv2rgb(const float* Y, const float* cbcr, int64_t npix_cbcr, float* rgb, void* rgb_lp, int dtype_lp, int64_t npix, void* stream) {
+    SHM_REQUIRE(Y && cbcr && (rgb || rgb_lp) && npix > 0 && npix_cbcr > 0, "shm_yuv2rgb: bad args");
+    SHM_REQUIRE(npix % npix_cbcr == 0, "shm_yuv2rgb: npix %% npix_cbcr != 0");
+    DISPATCH_DTYPE(dtype_lp, T, {
+        yuv2rgb_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(Y, cbcr, npix_cbcr, rgb, (T*)rgb_lp, npix);
+        SHM_CHECK_LAUNCH("yuv2rgb_kernel");
+        return SHM_OK;
+    })
+}
+
+extern "C" int shm_yuv2rgb_bwd(const float* drgb_f32, const void* drgb_lp, int dtype_lp, float* dY, int64_t npix, int accumulate, void* stream) {
+    SHM_REQUIRE((drgb_f32 || drgb_lp) && dY && npix > 0, "shm_yuv2rgb_bwd: bad args");
+    DISPATCH_DTYPE(dtype_lp, T, {
+        yuv2rgb_bwd_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(drgb_f32, (const T*)drgb_lp, dY, npix, accumulate);
+        SHM_CHECK_LAUNCH("yuv2rgb_bwd_kernel");
+        return SHM_OK;
+    })
+}

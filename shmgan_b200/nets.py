@@ -1,0 +1,477 @@
+"""The three networks of the SHMGAN hot path, orchestrated layer by layer over libshmgan kernels.
+
+  Generator      build_generator       ShmGANwithSSpecSeg.py:228-327  (+ attention_layer :404-412, live mask)
+  Discriminator  build_discriminator   ShmGANwithSSpecSeg.py:343-389
+  SpecSeg        SpecSeg               SpecSeg.py:27-98 (predict only)
+
+Parameters live in ONE flat fp32 buffer per network (Keras creation order, Keras layouts) with matching flat
+gradient / Adam m / Adam v buffers, so clip+Adam is a single launch and the data-parallel all-reduce works on
+contiguous buckets.  Forward passes save exactly what the hand-written backward needs (post-activation conv outputs,
+instance-norm sums, layer inputs); concat is never materialised: producers write into channel slices.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .ops import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, Conv
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter inventory (names / shapes / initialisers follow the reference layer by layer)
+# ------------------------------------------------------------------------------------------------
+def generator_specs(filter_size=64, live_mask=True):
+    """[(name, shape, kind)].  kind: w N(0,.02) (:200) | b zeros | g IN gamma = 1 | be IN beta N(0,.02) (frozen, Q2)."""
+    specs, N, cin = [], filter_size, 10
+    for lvl in range(1, 5):
+        for ab in "ab":
+            specs += [(f"enc{lvl}{ab}.w", (3, 3, cin, N), "w"), (f"enc{lvl}{ab}.b", (N,), "b"),
+                      (f"enc{lvl}{ab}.in_gamma", (N,), "g"), (f"enc{lvl}{ab}.in_beta", (N,), "be")]
+            cin = N
+        if live_mask:
+            specs += [(f"attn{lvl}a.w", (3, 3, 1, N), "w"), (f"attn{lvl}a.b", (N,), "b"),
+                      (f"attn{lvl}b.w", (3, 3, N, N), "w"), (f"attn{lvl}b.b", (N,), "b")]
+        if lvl < 4:
+            N *= 2
+    for i in (1, 2):
+        specs += [(f"bott{i}.w", (1, 1, N, N), "w"), (f"bott{i}.b", (N,), "b"),
+                  (f"bott{i}.in_gamma", (N,), "g"), (f"bott{i}.in_beta", (N,), "be")]
+    cin = N
+    for u in range(1, 5):
+        if u > 1:
+            N //= 2
+        specs += [(f"up{u}T.w", (3, 3, N, cin), "w"), (f"up{u}T.b", (N,), "b")]
+        cin = 2 * N
+        for ab in "ab":
+            specs += [(f"dec{u}{ab}.w", (3, 3, cin, N), "w"), (f"dec{u}{ab}.b", (N,), "b"),
+                      (f"dec{u}{ab}.in_gamma", (N,), "g"), (f"dec{u}{ab}.in_beta", (N,), "be")]
+            cin = N
+    specs += [("out.w", (1, 1, cin, 1), "w"), ("out.b", (1,), "b")]
+    return specs
+
+
+def discriminator_specs(image_size, filter_size=64, live_mask=True):
+    specs, N, cin = [], filter_size, 3
+    for i, mult in enumerate((1, 2, 4, 8), start=1):
+        specs += [(f"d{i}.w", (3, 3, cin, N * mult), "w"),
+                  (f"d{i}.in_gamma", (N * mult,), "g"), (f"d{i}.in_beta", (N * mult,), "be")]
+        cin = N * mult
+    if live_mask:
+        specs += [("dattn_a.w", (3, 3, 1, cin), "w"), ("dattn_a.b", (cin,), "b"),
+                  ("dattn_b.w", (3, 3, cin, cin), "w"), ("dattn_b.b", (cin,), "b")]
+    specs += [("d5.w", (3, 3, cin, N * 16), "w"), ("d5.in_gamma", (N * 16,), "g"), ("d5.in_beta", (N * 16,), "be")]
+    cin = N * 16
+    specs += [("head.w", (3, 3, cin, 1), "w")]
+    s32 = image_size // 32
+    specs += [("dense.w", (s32 * s32 * cin, 5), "w")]
+    return specs
+
+
+def specseg_specs():
+    specs, cin = [], 1
+    for i, c in enumerate((16, 32, 64, 128, 256), start=1):
+        specs += [(f"c{i}a.w", (3, 3, cin, c), "w5"), (f"c{i}a.b", (c,), "b"),
+                  (f"c{i}b.w", (3, 3, c, c), "w5"), (f"c{i}b.b", (c,), "b"),
+                  (f"bn{i}.gamma", (c,), "g"), (f"bn{i}.beta", (c,), "b"),
+                  (f"bn{i}.mean", (c,), "b"), (f"bn{i}.var", (c,), "g")]
+        cin = c
+    for i, c in zip((6, 7, 8, 9), (128, 64, 32, 16)):
+        specs += [(f"u{i}.w", (2, 2, c, cin), "glorot"), (f"u{i}.b", (c,), "b"),
+                  (f"c{i}a.w", (3, 3, 2 * c, c), "w5"), (f"c{i}a.b", (c,), "b"),
+                  (f"c{i}b.w", (3, 3, c, c), "w5"), (f"c{i}b.b", (c,), "b")]
+        cin = c
+    specs += [("out.w", (1, 1, 16, 1), "glorot"), ("out.b", (1,), "b")]
+    return specs
+
+
+def _is_trainable(name: str) -> bool:
+    return not (name.endswith("in_gamma") or name.endswith("in_beta") or name.startswith("bn"))
+
+
+class ParamStore:
+    """Flat fp32 parameter buffer with named views; trainable entries first (so grads / Adam state cover a prefix)."""
+
+    def __init__(self, specs, device="cuda", seed=42, trainable=True):
+        order = [s for s in specs if _is_trainable(s[0])] + [s for s in specs if not _is_trainable(s[0])]
+        self.specs = specs
+        self.offsets: Dict[str, tuple] = OrderedDict()
+        off = 0
+        for name, shape, _ in order:
+            n = math.prod(shape)
+            self.offsets[name] = (off, n, shape)
+            off += (n + 3) // 4 * 4                       # keep every view 16-byte aligned
+            if _is_trainable(name):
+                self.n_train = off
+        self.total = off
+        self.flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        self.views: Dict[str, torch.Tensor] = OrderedDict(
+            (k, self.flat[o:o + n].view(shape)) for k, (o, n, shape) in self.offsets.items())
+        self.grad = self.m = self.v = None
+        self.gviews: Dict[str, torch.Tensor] = {}
+        if trainable:
+            self.grad = torch.zeros(self.n_train, dtype=torch.float32, device=device)
+            self.m = torch.zeros_like(self.grad)
+            self.v = torch.zeros_like(self.grad)
+            self.gviews = OrderedDict((k, self.grad[o:o + n].view(shape)) for k, (o, n, shape) in self.offsets.items()
+                                      if _is_trainable(k))
+        self.version = 0
+        self.step = 0
+        self.init(seed)
+
+    def init(self, seed):
+        """Seeded reference initialisers (host RNG; one H2D copy)."""
+        g = torch.Generator().manual_seed(seed)
+        host = torch.zeros(self.total, dtype=torch.float32)
+        for name, shape, kind in self.specs:
+            o, n, _ = self.offsets[name]
+            if kind == "w":
+                t = torch.randn(shape, generator=g, dtype=torch.float64) * 0.02
+            elif kind == "w5":
+                t = torch.randn(shape, generator=g, dtype=torch.float64) * 0.05
+            elif kind == "glorot":
+                rf = math.prod(shape[:-2])
+                fan_in, fan_out = shape[-1] * rf, shape[-2] * rf
+                if shape[0] == 1:
+                    fan_in, fan_out = shape[-2], shape[-1]
+                t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * math.sqrt(6.0 / (fan_in + fan_out))
+            elif kind == "be":
+                t = torch.randn(shape, generator=g, dtype=torch.float64) * 0.02
+            elif kind == "g":
+                t = torch.ones(shape, dtype=torch.float64)
+            else:
+                t = torch.zeros(shape, dtype=torch.float64)
+            host[o:o + n] = t.reshape(-1).float()
+        self.flat.copy_(host)
+        self.version += 1
+
+    def load(self, named: Dict[str, torch.Tensor]):
+        """Imports parameters given in the reference (Keras) layouts, e.g. the oracle's OrderedDict."""
+        host = self.flat.cpu()
+        for k, t in named.items():
+            o, n, shape = self.offsets[k]
+            assert tuple(t.shape) == tuple(shape), (k, t.shape, shape)
+            host[o:o + n] = t.detach().reshape(-1).float().cpu()
+        self.flat.copy_(host)
+        self.version += 1
+
+    def export(self) -> Dict[str, torch.Tensor]:
+        host = self.flat.cpu()
+        return OrderedDict((k, host[o:o + n].view(shape).clone()) for k, (o, n, shape) in self.offsets.items())
+
+    def export_grads(self) -> Dict[str, torch.Tensor]:
+        host = self.grad.cpu()
+        return OrderedDict((k, host[o:o + n].view(shape).clone()) for k, (o, n, shape) in self.offsets.items() if _is_trainable(k))
+
+    def bind(self, conv: Conv):
+        conv.w = self.views[conv.name + ".w"]
+        conv.dw = self.gviews.get(conv.name + ".w")
+        if conv.has_bias:
+            conv.b = self.views[conv.name + ".b"]
+            conv.db = self.gviews.get(conv.name + ".b")
+        return conv
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def adam_step(self, lr0=2e-5, beta1=0.5, beta2=0.99, eps=1e-7, clip=1.0, gscale=1.0,
+                  decay_steps=10000.0, decay_rate=0.95):
+        """clip_by_value(+-1) + Keras Adam with ExponentialDecay (ShmGANwithSSpecSeg.py:169-175, :860-871)."""
+        t = self.step + 1
+        lr = lr0 * decay_rate ** (self.step / decay_steps)
+        lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        ops.call("shm_clip_adam", ops._p(self.flat), ops._p(self.grad), ops._p(self.m), ops._p(self.v), self.n_train,
+                 lr_t, beta1, beta2, eps, clip, gscale, ops._stream())
+        self.step += 1
+        self.version += 1
+
+
+# ------------------------------------------------------------------------------------------------
+# Generator
+# ------------------------------------------------------------------------------------------------
+class _CLI:
+    """Conv -> (+bias) -> LeakyReLU -> InstanceNorm (ShmGANwithSSpecSeg.py:244-245, :386-389)."""
+
+    def __init__(self, store: ParamStore, name, cin, cout, k=3, stride=1, bias=True):
+        self.conv = store.bind(Conv(name, k, k, cin, cout, stride=stride, act=ACT_LRELU, bias=bias))
+        self.gamma = store.views[name + ".in_gamma"]
+        self.beta = store.views[name + ".in_beta"]
+
+
+class Generator:
+    def __init__(self, filter_size=64, live_mask=True, dtype=torch.float32, device="cuda", seed=42, tensor_core=True):
+        self.N0, self.live_mask, self.dtype, self.tc = filter_size, live_mask, dtype, tensor_core
+        self.store = ParamStore(generator_specs(filter_size, live_mask), device, seed)
+        s, N, cin = self.store, filter_size, 10
+        self.enc, self.attn, self.dec, self.up = [], [], [], []
+        for lvl in range(1, 5):
+            a = _CLI(s, f"enc{lvl}a", cin, N)
+            b = _CLI(s, f"enc{lvl}b", N, N)
+            self.enc.append((a, b))
+            if live_mask:
+                self.attn.append((s.bind(Conv(f"attn{lvl}a", 3, 3, 1, N)), s.bind(Conv(f"attn{lvl}b", 3, 3, N, N))))
+            cin = N
+            if lvl < 4:
+                N *= 2
+        self.bott = [_CLI(s, "bott1", N, N, k=1), _CLI(s, "bott2", N, N, k=1)]
+        cin = N
+        for u in range(1, 5):
+            if u > 1:
+                N //= 2
+            self.up.append(s.bind(Conv(f"up{u}T", 3, 3, cin, N, stride=2, transposed=True)))
+            self.dec.append((_CLI(s, f"dec{u}a", 2 * N, N), _CLI(s, f"dec{u}b", N, N)))
+            cin = N
+        self.out = s.bind(Conv("out", 1, 1, cin, 1))
+
+    # -- helpers -----------------------------------------------------------------------------------
+    def _conv(self, c: Conv, x, y=None):
+        return c.fwd(x, y, self.tc, self.store.version)
+
+    def attention(self, mask: torch.Tensor):
+        """attention_layer on a live mask: level 1 un-pooled, then MaxPool2 chain; 2 x [Conv3x3 + LeakyReLU] per level.
+        Returns (features, saved) ; computed ONCE per step and shared by every generator pass."""
+        feats, saved, pooled = [], [], ops.cast(mask, self.dtype) if mask.dtype != self.dtype else mask
+        for lvl in range(4):
+            if lvl > 0:
+                pooled = ops.maxpool(pooled, 2)
+            ca, cb = self.attn[lvl]
+            a1 = self._conv(ca, pooled)
+            a2 = self._conv(cb, a1)
+            feats.append(a2)
+            saved.append((pooled, a1, a2))
+        return feats, saved
+
+    def attention_backward(self, saved, dattn: List[torch.Tensor]):
+        """dattn[lvl] = sum over passes of d(skip)."""
+        for lvl in range(4):
+            pooled, a1, a2 = saved[lvl]
+            ca, cb = self.attn[lvl]
+            d2 = ops.act_bwd(dattn[lvl], a2, ACT_LRELU)
+            cb.wgrad(a1, d2, self.tc)
+            d1 = cb.dgrad(d2, a1.shape, None, self.tc, self.store.version)
+            d1 = ops.act_bwd(d1, a1, ACT_LRELU)
+            ca.wgrad(pooled, d1, self.tc)
+
+    def forward(self, x: torch.Tensor, attn: Optional[List[torch.Tensor]] = None, save: bool = False):
+        """x [B,S,S,10] (self.dtype) -> y [B,S,S,1].  attn: per-level features [Ba,...] broadcast as n % Ba."""
+        B, S = x.shape[0], x.shape[1]
+        tape = {"x": x, "enc": [], "dec": [], "bott": []} if save else None
+        h, cats = x, []
+        for lvl in range(4):
+            a, b = self.enc[lvl]
+            C = a.conv.cout
+            za = self._conv(a.conv, h)
+            sa = ops.inorm_stats(za)
+            ya, _ = ops.inorm_apply(za, sa, a.gamma, a.beta)
+            zb = self._conv(b.conv, ya)
+            sb = ops.inorm_stats(zb)
+            cat = ops.new((B, zb.shape[1], zb.shape[2], 2 * C), self.dtype)
+            _, pool = ops.inorm_apply(zb, sb, b.gamma, b.beta, add=None if attn is None else attn[lvl], out=cat[..., C:], pooled=True)
+            cats.append(cat)
+            if save:
+                tape["enc"].append((h, za, sa, ya, zb, sb))
+            h = pool
+        for bl in self.bott:
+            z = self._conv(bl.conv, h)
+            sz = ops.inorm_stats(z)
+            y, _ = ops.inorm_apply(z, sz, bl.gamma, bl.beta)
+            if save:
+                tape["bott"].append((h, z, sz))
+            h = y
+        for u in range(4):
+            cat = cats[3 - u]
+            C = cat.shape[3] // 2
+            self._conv(self.up[u], h, cat[..., :C])
+            a, b = self.dec[u]
+            za = self._conv(a.conv, cat)
+            sa = ops.inorm_stats(za)
+            ya, _ = ops.inorm_apply(za, sa, a.gamma, a.beta)
+            zb = self._conv(b.conv, ya)
+            sb = ops.inorm_stats(zb)
+            yb, _ = ops.inorm_apply(zb, sb, b.gamma, b.beta)
+            if save:
+                tape["dec"].append((h, cat, za, sa, ya, zb, sb))
+            h = yb
+        y = self._conv(self.out, h)
+        if save:
+            tape["last"] = (h, y)
+            return y, tape
+        return y
+
+    def _cli_bwd(self, blk: _CLI, x_in, z, sums, dyA=None, dyP=None, need_dx=True):
+        dpre = ops.inorm_bwd(z, sums, blk.gamma, dyA, dyP, ACT_LRELU)
+        blk.conv.wgrad(x_in, dpre, self.tc)
+        if not need_dx:
+            return None
+        return blk.conv.dgrad(dpre, x_in.shape, None, self.tc, self.store.version)
+
+    def backward(self, tape, dy: torch.Tensor, dattn: Optional[List[torch.Tensor]] = None, attn_nb: int = 0,
+                 need_dx: bool = False):
+        """Accumulates weight gradients into the store; dattn[lvl] (+)= batch-group sums of d(skip) when given.
+        Returns d(x) [B,S,S,10] if need_dx."""
+        v = self.store.version
+        h, y = tape["last"]
+        dpre = ops.act_bwd(dy, y, ACT_LRELU)
+        self.out.wgrad(h, dpre, self.tc)
+        dh = self.out.dgrad(dpre, h.shape, None, self.tc, v)
+        dskips = [None] * 4
+        for u in (3, 2, 1, 0):
+            hin, cat, za, sa, ya, zb, sb = tape["dec"][u]
+            a, b = self.dec[u]
+            C = cat.shape[3] // 2
+            dya = self._cli_bwd(b, ya, zb, sb, dyA=dh)
+            dcat = self._cli_bwd(a, cat, za, sa, dyA=dya)
+            dup = ops.act_bwd(dcat[..., :C], cat[..., :C], ACT_LRELU)
+            self.up[u].wgrad(hin, dup, self.tc)
+            dh = self.up[u].dgrad(dup, hin.shape, None, self.tc, v)
+            dskips[3 - u] = dcat[..., C:]
+        for i in (1, 0):
+            hin, z, sz = tape["bott"][i]
+            dh = self._cli_bwd(self.bott[i], hin, z, sz, dyA=dh)
+        dx = None
+        for lvl in (3, 2, 1, 0):
+            hin, za, sa, ya, zb, sb = tape["enc"][lvl]
+            a, b = self.enc[lvl]
+            dya = self._cli_bwd(b, ya, zb, sb, dyA=dskips[lvl], dyP=dh)
+            if dattn is not None:
+                ops.group_sum(dskips[lvl], attn_nb, dattn[lvl], accumulate=True)
+            last = lvl == 0
+            dh = self._cli_bwd(a, hin, za, sa, dyA=dya, need_dx=(not last) or need_dx)
+            if last:
+                dx = dh
+        return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# Discriminator
+# ------------------------------------------------------------------------------------------------
+class Discriminator:
+    def __init__(self, image_size, filter_size=64, live_mask=True, dtype=torch.float32, device="cuda", seed=43,
+                 tensor_core=True, dropout=0.2):
+        self.S, self.live_mask, self.dtype, self.tc, self.dropout = image_size, live_mask, dtype, tensor_core, dropout
+        self.store = ParamStore(discriminator_specs(image_size, filter_size, live_mask), device, seed)
+        s, N, cin = self.store, filter_size, 3
+        self.blocks = []
+        for i, mult in enumerate((1, 2, 4, 8, 16), start=1):
+            self.blocks.append(_CLI(s, f"d{i}", cin, N * mult, stride=2, bias=False))
+            cin = N * mult
+        if live_mask:
+            self.attn = (s.bind(Conv("dattn_a", 3, 3, 1, N * 8)), s.bind(Conv("dattn_b", 3, 3, N * 8, N * 8)))
+        self.head = s.bind(Conv("head", 3, 3, cin, 1, bias=False))
+        self.dense_w = s.views["dense.w"]
+        self.dense_dw = s.gviews["dense.w"]
+
+    def attention(self, mask):
+        """MaxPool16(mask) -> 2 x [Conv3x3 + LeakyReLU] @512 (ShmGANwithSSpecSeg.py:358, :404-412)."""
+        m = ops.cast(mask, self.dtype) if mask.dtype != self.dtype else mask
+        pooled = ops.maxpool(m, 16)
+        a1 = self.attn[0].fwd(pooled, None, self.tc, self.store.version)
+        a2 = self.attn[1].fwd(a1, None, self.tc, self.store.version)
+        return a2, (pooled, a1, a2)
+
+    def attention_backward(self, saved, dattn):
+        pooled, a1, a2 = saved
+        d2 = ops.act_bwd(dattn, a2, ACT_LRELU)
+        self.attn[1].wgrad(a1, d2, self.tc)
+        d1 = self.attn[1].dgrad(d2, a1.shape, None, self.tc, self.store.version)
+        d1 = ops.act_bwd(d1, a1, ACT_LRELU)
+        self.attn[0].wgrad(pooled, d1, self.tc)
+
+    def forward(self, x, attn=None, noise=None, keep=None, save=False):
+        """x [B,S,S,3] -> (rf [B,S/32,S/32,1], cls [B,5] fp32).  noise / keep: the GaussianNoise(0.1) / Dropout(0.2)
+        draws of a training=True call (:352, :363); None = training=False."""
+        v = self.store.version
+        h = x if noise is None else ops.add(x, noise)
+        tape = {"layers": []} if save else None
+        for i, bl in enumerate(self.blocks):
+            z = bl.conv.fwd(h, None, self.tc, v)
+            sz = ops.inorm_stats(z)
+            y, _ = ops.inorm_apply(z, sz, bl.gamma, bl.beta, add=attn if i == 3 else None)
+            if save:
+                tape["layers"].append((h, z, sz))
+            h = y
+        y5 = h
+        if keep is not None:
+            h = ops.mul_mask(y5, keep, 1.0 / (1.0 - self.dropout))
+        rf = self.head.fwd(h, None, self.tc, v)
+        cls = ops.dense_fwd(h, self.dense_w)
+        if save:
+            tape.update(h5=h, rf=rf, keep=keep)
+            return rf, cls, tape
+        return rf, cls
+
+    def backward(self, tape, d_rf, d_cls=None, n: Optional[int] = None, wgrad=True, need_dx=False, dattn=None, attn_nb=0):
+        """Back-propagates seeds (d_rf [n,s,s,1], d_cls [n,5] fp32 or None) through the first n images of a saved pass.
+        wgrad=False gives the dgrad-only sweep that carries the generator loss back to the image."""
+        v = self.store.version
+        sub = (lambda t: t) if n is None else (lambda t: None if t is None else t[:n])
+        h5, rf, keep = sub(tape["h5"]), sub(tape["rf"]), sub(tape["keep"])
+        dpre = ops.act_bwd(ops.cast(d_rf, self.dtype), rf, ACT_LRELU)
+        if wgrad:
+            self.head.wgrad(h5, dpre, self.tc)
+        dh = self.head.dgrad(dpre, h5.shape, None, self.tc, v)
+        if d_cls is not None:
+            if wgrad:
+                ops.dense_wgrad(h5, d_cls, self.dense_dw)
+            dh = ops.add(dh, ops.dense_dgrad(d_cls, self.dense_w, h5))
+        if keep is not None:
+            dh = ops.mul_mask(dh, keep, 1.0 / (1.0 - self.dropout))
+        for i in (4, 3, 2, 1, 0):
+            hin, z, sz = (sub(t) for t in tape["layers"][i])
+            bl = self.blocks[i]
+            if i == 3 and dattn is not None:
+                ops.group_sum(dh, attn_nb, dattn, accumulate=True)
+            dpre = ops.inorm_bwd(z, sz, bl.gamma, dyA=dh, act=ACT_LRELU)
+            if wgrad:
+                bl.conv.wgrad(hin, dpre, self.tc)
+            if i > 0 or need_dx:
+                dh = bl.conv.dgrad(dpre, hin.shape, None, self.tc, v)
+        return dh if need_dx else None
+
+
+# ------------------------------------------------------------------------------------------------
+# SpecSeg (predict only)
+# ------------------------------------------------------------------------------------------------
+class SpecSegNet:
+    """SpecSeg U-Net (SpecSeg.py:27-98) at predict time: Dropout inactive, BatchNorm on moving statistics."""
+
+    def __init__(self, dtype=torch.float32, device="cuda", seed=44, tensor_core=True):
+        self.dtype, self.tc = dtype, tensor_core
+        self.store = ParamStore(specseg_specs(), device, seed, trainable=False)
+        s, cin = self.store, 1
+        self.enc, self.dec = [], []
+        for i, c in enumerate((16, 32, 64, 128, 256), start=1):
+            self.enc.append((s.bind(Conv(f"c{i}a", 3, 3, cin, c, act=ACT_RELU)), s.bind(Conv(f"c{i}b", 3, 3, c, c, act=ACT_RELU)), i))
+            cin = c
+        for i, c in zip((6, 7, 8, 9), (128, 64, 32, 16)):
+            self.dec.append((s.bind(Conv(f"u{i}", 2, 2, cin, c, stride=2, transposed=True, act=ACT_NONE)),
+                             s.bind(Conv(f"c{i}a", 3, 3, 2 * c, c, act=ACT_RELU)), s.bind(Conv(f"c{i}b", 3, 3, c, c, act=ACT_RELU))))
+            cin = c
+        self.out = s.bind(Conv("out", 1, 1, 16, 1, act=ACT_SIGMOID))
+
+    def predict(self, x: torch.Tensor, verbose=0) -> torch.Tensor:
+        """x [B,S,S,1] -> sigmoid probabilities [B,S,S,1] in the same dtype (SpecSeg.predict, ShmGANwithSSpecSeg.py:492)."""
+        v = self.store.version
+        sv = self.store.views
+        B = x.shape[0]
+        h, cats = x, []
+        for ca, cb, i in self.enc:
+            h = ca.fwd(h, None, self.tc, v)
+            h = cb.fwd(h, None, self.tc, v)
+            c = cb.cout
+            bn = (sv[f"bn{i}.gamma"], sv[f"bn{i}.beta"], sv[f"bn{i}.mean"], sv[f"bn{i}.var"])
+            if i < 5:
+                cat = ops.new((B, h.shape[1], h.shape[2], 2 * c), self.dtype)     # [up, skip] (SpecSeg.py:65)
+                _, h = ops.bn_eval(h, *bn, out=cat[..., c:], pooled=True)
+                cats.append(cat)
+            else:
+                h, _ = ops.bn_eval(h, *bn)
+        for (up, ca, cb), cat in zip(self.dec, reversed(cats)):
+            c = up.cout
+            up.fwd(h, cat[..., :c], self.tc, v)
+            h = ca.fwd(cat, None, self.tc, v)
+            h = cb.fwd(h, None, self.tc, v)
+        return self.out.fwd(h, None, self.tc, v)

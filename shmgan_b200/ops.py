@@ -1,0 +1,321 @@
+"""Thin tensor-level wrappers over the C ABI.  Tensors are torch CUDA tensors used purely as buffer carriers:
+NHWC activations, possibly channel-slices of a wider buffer (pixel stride ld = tensor.stride(-2)).
+Every function launches libshmgan kernels on torch's current CUDA stream; nothing falls back to torch math."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32, ConvDesc, call  # noqa: F401
+
+IN_EPS = 1e-6       # ShmGANwithSSpecSeg.py:245
+BN_EPS = 1e-3       # Keras BatchNormalization default (SpecSeg.py:37)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError("unsupported dtype %s" % t.dtype)
+
+
+def tdtype(code: int):
+    return torch.float32 if code == F32 else torch.bfloat16
+
+
+def ld(t: Optional[torch.Tensor]) -> int:
+    """Pixel stride of an NHWC tensor / channel-slice view."""
+    if t is None:
+        return 0
+    assert t.stride(-1) == 1 or t.shape[-1] == 1, "channel axis must be unit-stride"
+    return t.stride(-2)
+
+
+def _check_nhwc(t: torch.Tensor):
+    n, h, w, _ = t.shape
+    l = t.stride(2)
+    assert t.stride(1) == w * l and (n == 1 or t.stride(0) == h * w * l), "tensor is not a dense NHWC pixel grid"
+
+
+def new(shape, dtype, device="cuda"):
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution layer: geometry + which kernel family serves it
+# ------------------------------------------------------------------------------------------------
+class Conv:
+    """One Conv2D / Conv2DTranspose layer of the reference (Keras weight layouts), bound to slices of a flat
+    parameter / gradient buffer.  `tc` = use the tcgen05 bf16 kernels when the shape allows."""
+
+    def __init__(self, name, kh, kw, cin, cout, stride=1, transposed=False, act=ACT_LRELU, bias=True):
+        self.name, self.kh, self.kw, self.cin, self.cout = name, kh, kw, cin, cout
+        self.stride, self.transposed, self.act, self.has_bias = stride, transposed, act, bias
+        self.w = self.b = self.dw = self.db = None          # views set by ParamStore.bind
+        self.w_tc = self.w_tc_d = None                      # bf16 [tap][n][k] copies for the tensor-core path
+        self.tc_version = -1
+
+    def wshape(self):
+        return (self.kh, self.kw, self.cout, self.cin) if self.transposed else (self.kh, self.kw, self.cin, self.cout)
+
+    def out_hw(self, h, w):
+        if self.transposed:
+            return h * self.stride, w * self.stride
+        return -(-h // self.stride), -(-w // self.stride)
+
+    def desc(self, n, h, w, ldx, ldy, dtype, act=None) -> ConvDesc:
+        return ConvDesc(n, h, w, self.cin, self.cout, self.kh, self.kw, self.stride, int(self.transposed),
+                        self.act if act is None else act, ldx, ldy, dtype, 0)
+
+    # -- tensor-core weights ---------------------------------------------------------------------
+    def refresh_tc(self, version: int):
+        """Re-lays the fp32 master weights out as bf16 [tap][n][k] for fwd and dgrad (once per optimiser step)."""
+        if self.tc_version == version:
+            return
+        d = self.desc(1, 16, 16, self.cin, self.cout, BF16)
+        if self.w_tc is None:
+            n = self.kh * self.kw * self.cin * self.cout
+            self.w_tc = new((n,), torch.bfloat16)
+            self.w_tc_d = new((n,), torch.bfloat16)
+        call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), _p(self.w_tc), 0, _stream())
+        call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), _p(self.w_tc_d), 1, _stream())
+        self.tc_version = version
+
+    def tc_ok(self, d: ConvDesc) -> bool:
+        return (d.dtype == BF16 and self.cin % 64 == 0 and self.cout % 64 == 0
+                and bool(call("shm_conv2d_tc_supported", C.byref(d), 0)))
+
+    # -- forward / backward ------------------------------------------------------------------------
+    def fwd(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, tc: bool = True, version: int = 0):
+        n, h, w, _ = x.shape
+        ho, wo = self.out_hw(h, w)
+        if y is None:
+            y = new((n, ho, wo, self.cout), x.dtype)
+        d = self.desc(n, h, w, ld(x), ld(y), dt(x))
+        if tc and self.tc_ok(d):
+            self.refresh_tc(version)
+            call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b), _p(y), _stream())
+        else:
+            call("shm_conv2d_fwd", C.byref(d), _p(x), _p(self.w), _p(self.b), _p(y), _stream())
+        return y
+
+    def dgrad(self, dy: torch.Tensor, x_shape, dx: Optional[torch.Tensor] = None, tc: bool = True, version: int = 0):
+        """dx from dy = dL/d(pre-activation)."""
+        n, h, w, _ = x_shape
+        if dx is None:
+            dx = new((n, h, w, self.cin), dy.dtype)
+        d = self.desc(n, h, w, ld(dx), ld(dy), dt(dy), ACT_NONE)
+        if tc and self.tc_ok(d):
+            self.refresh_tc(version)
+            call("shm_conv2d_tc_dgrad", C.byref(d), _p(dy), _p(self.w_tc_d), _p(dx), _stream())
+        else:
+            call("shm_conv2d_dgrad", C.byref(d), _p(dy), _p(self.w), _p(dx), 0, _stream())
+        return dx
+
+    def wgrad(self, x: torch.Tensor, dy: torch.Tensor, tc: bool = True):
+        """dw += , db += (gradients accumulate: weights are shared by several passes)."""
+        n, h, w, _ = x.shape
+        d = self.desc(n, h, w, ld(x), ld(dy), dt(x), ACT_NONE)
+        if tc and self.tc_ok(d):
+            call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _stream())
+            if self.has_bias:
+                call("shm_colsum", _p(dy), dy.shape[0] * dy.shape[1] * dy.shape[2], self.cout, ld(dy), dt(dy), _p(self.db), _stream())
+        else:
+            call("shm_conv2d_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _p(self.db) if self.has_bias else None, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# instance norm (+pool, +add, +slice placement) and friends
+# ------------------------------------------------------------------------------------------------
+def inorm_stats(x: torch.Tensor) -> torch.Tensor:
+    n, h, w, c = x.shape
+    sums = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    call("shm_inorm_stats", _p(x), n, h * w, c, ld(x), dt(x), _p(sums), _stream())
+    return sums
+
+
+def inorm_apply(x, sums, gamma, beta, add=None, out=None, pooled=False, want_out=True):
+    """Returns (out, pooled).  add: [nadd,H,W,C] broadcast over the batch as n % nadd."""
+    n, h, w, c = x.shape
+    if out is None and want_out:
+        out = new((n, h, w, c), x.dtype)
+    pl = new((n, h // 2, w // 2, c), x.dtype) if pooled else None
+    call("shm_inorm_apply", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), _p(gamma), _p(beta), IN_EPS,
+         _p(add), ld(add), 0 if add is None else add.shape[0], _p(out), ld(out), _p(pl), ld(pl), _stream())
+    return out, pl
+
+
+def inorm_bwd(x, sums, gamma, dyA=None, dyP=None, act=ACT_LRELU, dx=None):
+    """dL/d(pre-activation of the producing conv) from dL/dy, y = IN(x), x = post-activation conv output."""
+    n, h, w, c = x.shape
+    bs = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    call("shm_inorm_bwd_stats", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), IN_EPS, _p(dyA), ld(dyA), _p(dyP), ld(dyP), _p(bs), _stream())
+    if dx is None:
+        dx = new((n, h, w, c), x.dtype)
+    call("shm_inorm_bwd_apply", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), _p(gamma), IN_EPS, _p(dyA), ld(dyA), _p(dyP), ld(dyP),
+         _p(bs), act, _p(dx), ld(dx), _stream())
+    return dx
+
+
+def act_bwd(dy, y, act, out=None):
+    n, h, w, c = y.shape
+    if out is None:
+        out = new((n, h, w, c), y.dtype)
+    call("shm_act_bwd", _p(dy), ld(dy), _p(y), ld(y), _p(out), ld(out), n * h * w, c, act, dt(y), _stream())
+    return out
+
+
+def maxpool(x, k):
+    n, h, w, c = x.shape
+    y = new((n, h // k, w // k, c), x.dtype)
+    call("shm_maxpool", _p(x), n, h, w, c, ld(x), k, _p(y), ld(y), dt(x), _stream())
+    return y
+
+
+def bn_eval(x, gamma, beta, mean, var, out=None, pooled=False):
+    n, h, w, c = x.shape
+    if out is None:
+        out = new((n, h, w, c), x.dtype)
+    pl = new((n, h // 2, w // 2, c), x.dtype) if pooled else None
+    call("shm_bn_eval", _p(x), n, h, w, c, ld(x), dt(x), _p(gamma), _p(beta), _p(mean), _p(var), BN_EPS, _p(out), ld(out), _p(pl), ld(pl), _stream())
+    return out, pl
+
+
+def add(a, b, out=None):
+    n, h, w, c = a.shape
+    if out is None:
+        out = new((n, h, w, c), a.dtype)
+    call("shm_add", _p(a), ld(a), _p(b), ld(b), _p(out), ld(out), n * h * w, c, dt(a), _stream())
+    return out
+
+
+def group_sum(src, nb, dst, accumulate):
+    """dst[b] (+)= sum_r src[r*nb + b]."""
+    n, h, w, c = src.shape
+    call("shm_group_sum", _p(src), ld(src), n // nb, nb * h * w, c, _p(dst), ld(dst), int(accumulate), dt(src), _stream())
+    return dst
+
+
+def mul_mask(x, keep, scale):
+    out = torch.empty_like(x)
+    call("shm_mul_mask", _p(x), _p(keep), _p(out), x.numel(), float(scale), dt(x), _stream())
+    return out
+
+
+def cast(x, dtype):
+    if x.dtype == dtype:
+        return x
+    assert x.is_contiguous()
+    out = torch.empty(x.shape, dtype=dtype, device=x.device)
+    call("shm_cast", _p(x), dt(x), _p(out), dt(out), x.numel(), _stream())
+    return out
+
+
+def cast_into(src, dst):
+    """dst[...] = src[...] for NHWC tensors / channel-slice views of equal shape (strided copy + dtype conversion)."""
+    c = src.shape[-1]
+    call("shm_cast2d", _p(src), dt(src), ld(src), _p(dst), dt(dst), ld(dst), src.numel() // c, c, _stream())
+    return dst
+
+
+def rng_normal(shape, seed, offset, sigma, dtype):
+    out = new(shape, dtype)
+    call("shm_rng_normal", _p(out), out.numel(), seed, offset, float(sigma), dt(out), _stream())
+    return out
+
+
+def rng_keep(shape, seed, offset, keep_prob, dtype):
+    out = new(shape, dtype)
+    call("shm_rng_keep", _p(out), out.numel(), seed, offset, float(keep_prob), dt(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# dense head
+# ------------------------------------------------------------------------------------------------
+def dense_fwd(x, w):
+    b = x.shape[0]
+    k = x.numel() // b
+    out = new((b, w.shape[1]), torch.float32)
+    call("shm_dense_fwd", _p(x), _p(w), _p(out), b, k, w.shape[1], dt(x), _stream())
+    return out
+
+
+def dense_dgrad(dout, w, like):
+    dx = torch.empty_like(like)
+    b = like.shape[0]
+    call("shm_dense_dgrad", _p(dout), _p(w), _p(dx), b, like.numel() // b, w.shape[1], dt(dx), _stream())
+    return dx
+
+
+def dense_wgrad(x, dout, dw):
+    b = x.shape[0]
+    call("shm_dense_wgrad", _p(x), _p(dout), _p(dw), b, x.numel() // b, dw.shape[1], dt(x), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# preprocessing
+# ------------------------------------------------------------------------------------------------
+def pseudo_diffuse_min4(i0, i45, i90, i135):
+    """calculate_estimate_diffuse (utils.py:102-106).  fp32 / bf16 / uint8."""
+    code = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}[i0.dtype]
+    out = torch.empty_like(i0)
+    call("shm_pseudo_diffuse_min4", _p(i0), _p(i45), _p(i90), _p(i135), _p(out), i0.numel(), code, _stream())
+    return out
+
+
+def yuv_standardize(rgb):
+    """rgb [N,H,W,3] fp32 -> (standardised yuv [N,H,W,3] fp32, scale [N])."""
+    n, h, w, _ = rgb.shape
+    sums = torch.zeros((n, 2), dtype=torch.float64, device=rgb.device)
+    call("shm_yuv_stats", _p(rgb), n, h * w, _p(sums), _stream())
+    yuv = torch.empty_like(rgb)
+    scale = new((n,), torch.float32)
+    call("shm_yuv_standardize", _p(rgb), n, h * w, _p(sums), _p(yuv), _p(scale), _stream())
+    return yuv, scale
+
+
+def avg_cbcr(ds: Sequence[torch.Tensor]):
+    n, h, w, _ = ds[0].shape
+    out = new((n, h, w, 2), torch.float32)
+    call("shm_avg_cbcr", _p(ds[0]), _p(ds[1]), _p(ds[2]), _p(ds[3]), _p(ds[4]), _p(out), n * h * w, _stream())
+    return out
+
+
+def assemble_input(srcs, src_lds, onehot, out):
+    """srcs: 5 fp32 tensors (or None = zeros) giving one value per pixel at stride src_lds[j]; out [N,H,W,10]."""
+    arr_p = (C.c_void_p * 5)(*[None if s is None else s.data_ptr() for s in srcs])
+    arr_l = (C.c_int32 * 5)(*src_lds)
+    npix = out.numel() // 10
+    call("shm_assemble_input", C.cast(arr_p, C.POINTER(C.c_void_p)), arr_l, onehot, _p(out), npix, dt(out), _stream())
+    return out
+
+
+def assemble_bwd(din, slots, dgen):
+    arr = (C.c_int32 * 5)(*(list(slots) + [0] * (5 - len(slots))))
+    call("shm_assemble_bwd", _p(din), dt(din), arr, len(slots), _p(dgen), din.numel() // 10, _stream())
+
+
+def yuv2rgb(Y, cbcr, rgb=None, lp=None):
+    """Y [N,H,W,1] fp32, cbcr [Nc,H,W,2] fp32 broadcast over N as n % Nc -> rgb [N,H,W,3] fp32 and / or a bf16 copy `lp`
+    (the discriminator's input in bf16 mode).  Outputs must be dense."""
+    n, h, w, _ = Y.shape
+    call("shm_yuv2rgb", _p(Y), _p(cbcr), cbcr.numel() // 2, _p(rgb), _p(lp), BF16 if lp is not None else F32, n * h * w, _stream())
+    return rgb, lp
+
+
+def yuv2rgb_bwd(drgb_f32, drgb_lp, dY, accumulate):
+    code = dt(drgb_lp) if drgb_lp is not None else F32
+    call("shm_yuv2rgb_bwd", _p(drgb_f32), _p(drgb_lp), code, _p(dY), dY.numel(), int(accumulate), _stream())
