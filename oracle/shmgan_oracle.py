@@ -32,9 +32,9 @@ __all__ = [
     "specseg_param_specs", "init_params", "generator_forward", "attention_features",
     "discriminator_forward", "specseg_forward", "rgb_to_yuv", "yuv_to_rgb",
     "per_image_standardization", "rescale_01", "ssim", "gram_matrix", "pseudo_diffuse_min4",
-    "assemble_g1_input", "assemble_cyclic_inputs", "train_step_losses", "train_step_grads",
+    "assemble_g1_input", "assemble_cyclic_inputs", "train_step_losses", "softmax_ce", "train_step_grads",
     "keras_adam_lr", "keras_adam_update", "inference_step", "count_params",
-    "RGB2YUV", "YUV2RGB", "LRELU_ALPHA", "IN_EPS", "BN_EPS",
+    "RGB2YUV", "YUV2RGB", "LRELU_ALPHA", "IN_EPS", "BN_EPS", "bf16_storage",
 ]
 
 LRELU_ALPHA = 0.2      # tf.nn.leaky_relu default (ShmGANwithSSpecSeg.py:244 activation=tf.nn.leaky_relu)
@@ -75,7 +75,7 @@ def conv2d_same(x, w, b=None, stride: int = 1):
     _, pt, pb = tf_same_pad(x.shape[1], kh, stride)
     _, pl, pr = tf_same_pad(x.shape[2], kw, stride)
     xp = F.pad(_nchw(x), (pl, pr, pt, pb))
-    y = F.conv2d(xp, w.permute(3, 2, 0, 1), b, stride=stride)
+    y = F.conv2d(xp, w.permute(3, 2, 0, 1).contiguous(), b, stride=stride)
     return _nhwc(y)
 
 
@@ -90,7 +90,7 @@ def conv2d_transpose_same(x, w, b=None, stride: int = 2):
     H, W = x.shape[1], x.shape[2]
     _, pt, _ = tf_same_pad(H * stride, kh, stride)
     _, pl, _ = tf_same_pad(W * stride, kw, stride)
-    y = F.conv_transpose2d(_nchw(x), w.permute(3, 2, 0, 1), b, stride=stride)
+    y = F.conv_transpose2d(_nchw(x), w.permute(3, 2, 0, 1).contiguous(), b, stride=stride)
     y = y[:, :, pt:pt + H * stride, pl:pl + W * stride]
     return _nhwc(y)
 
@@ -249,47 +249,67 @@ def count_params(specs, trainable_only: bool = False) -> int:
 # --------------------------------------------------------------------------------------
 # models
 # --------------------------------------------------------------------------------------
-def _cli(p, name, x, stride=1, bias=True):
-    """Conv -> (+bias) -> LeakyReLU -> InstanceNorm.  ShmGANwithSSpecSeg.py:244-245 / :386-389."""
-    z = leaky_relu(conv2d_same(x, p[name + ".w"], p[name + ".b"] if bias else None, stride))
+def _ident(t):
+    return t
+
+
+def bf16_storage(t):
+    """Storage-precision model of the bf16 execution mode: round to the bf16 grid where the CUDA path stores an
+    activation, with a straight-through gradient.  Passed as `q=` to the model functions below it gives the reference the
+    bf16 kernels are held to (same quantisation points, exact arithmetic in between); `q=None` is the plain reference."""
+    r = t.detach().to(torch.float32).to(torch.bfloat16).to(t.dtype)
+    return t + (r - t.detach())
+
+
+def _cli_parts(p, name, x, stride=1, bias=True, q=_ident):
+    """Conv -> (+bias) -> LeakyReLU -> InstanceNorm (ShmGANwithSSpecSeg.py:244-245 / :386-389); returns the un-stored
+    normalised tensor (the caller stores it, possibly after a fused add / pool)."""
+    z = q(leaky_relu(conv2d_same(x, p[name + ".w"], p[name + ".b"] if bias else None, stride)))
     return instance_norm(z, p[name + ".in_gamma"], p[name + ".in_beta"])
 
 
-def attention_features(p, mask, prefix="attn", levels=(1, 2, 3, 4)):
+def _cli(p, name, x, stride=1, bias=True, q=_ident):
+    return q(_cli_parts(p, name, x, stride, bias, q))
+
+
+def attention_features(p, mask, prefix="attn", levels=(1, 2, 3, 4), q=None):
     """attention_layer (:404-412) evaluated on a live mask: level 1 un-pooled, then MaxPool2 chain."""
+    q = q or _ident
     feats = []
     pooled = mask
     for lvl in levels:
         if lvl > 1:
             pooled = max_pool(pooled, 2)
-        a = leaky_relu(conv2d_same(pooled, p[f"{prefix}{lvl}a.w"], p[f"{prefix}{lvl}a.b"]))
-        a = leaky_relu(conv2d_same(a, p[f"{prefix}{lvl}b.w"], p[f"{prefix}{lvl}b.b"]))
+        a = q(leaky_relu(conv2d_same(pooled, p[f"{prefix}{lvl}a.w"], p[f"{prefix}{lvl}a.b"])))
+        a = q(leaky_relu(conv2d_same(a, p[f"{prefix}{lvl}b.w"], p[f"{prefix}{lvl}b.b"])))
         feats.append(a)
     return feats
 
 
-def generator_forward(p, x, mask=None, return_intermediates: bool = False):
-    """build_generator (:228-327).  mask=None reproduces the as-written graph (attn == 0, Q1)."""
+def generator_forward(p, x, mask=None, return_intermediates: bool = False, q=None):
+    """build_generator (:228-327).  mask=None reproduces the as-written graph (attn == 0, Q1).
+    The attention features are computed first and added where each skip is formed, which is the same arithmetic as the
+    reference's later `down_k + attn_k` (:290-293)."""
+    q = q or _ident
     inter = {}
+    attn = attention_features(p, mask, q=q) if mask is not None else None
+    if attn is not None:
+        inter["attn"] = attn
     skips = []
     h = x
     for lvl in range(1, 5):
-        h = _cli(p, f"enc{lvl}a", h)
-        h = _cli(p, f"enc{lvl}b", h)
-        skips.append(h)
-        h = avg_pool2(h)
-    h = _cli(p, "bott1", h)
-    h = _cli(p, "bott2", h)
-    if mask is not None:
-        attn = attention_features(p, mask)
-        skips = [s + a for s, a in zip(skips, attn)]          # :290-293 (add, not multiply)
-        inter["attn"] = attn
+        h = _cli(p, f"enc{lvl}a", h, q=q)
+        y = _cli_parts(p, f"enc{lvl}b", h, q=q)
+        skips.append(q(y + attn[lvl - 1]) if attn is not None else q(y))      # :290-293 (add, not multiply)
+        h = q(avg_pool2(y))                                                    # :249
+    h = _cli(p, "bott1", h, q=q)
+    h = _cli(p, "bott2", h, q=q)
     for u in range(1, 5):
-        up = leaky_relu(conv2d_transpose_same(h, p[f"up{u}T.w"], p[f"up{u}T.b"], 2))   # :298
+        up = q(leaky_relu(conv2d_transpose_same(h, p[f"up{u}T.w"], p[f"up{u}T.b"], 2)))   # :298
         h = torch.cat([up, skips[4 - u]], dim=3)                                        # :299
-        h = _cli(p, f"dec{u}a", h)
-        h = _cli(p, f"dec{u}b", h)
-    y = leaky_relu(conv2d_same(h, p["out.w"], p["out.b"]))                              # :326
+        h = _cli(p, f"dec{u}a", h, q=q)
+        h = _cli(p, f"dec{u}b", h, q=q)
+    y = q(leaky_relu(conv2d_same(h, p["out.w"], p["out.b"])))                           # :326
     if return_intermediates:
         inter["skips"] = skips
         return y, inter
@@ -297,46 +317,51 @@ def generator_forward(p, x, mask=None, return_intermediates: bool = False):
 
 
 def discriminator_forward(p, x, mask=None, training: bool = False, noise=None, keep=None,
-                          dropout_rate: float = 0.2):
+                          dropout_rate: float = 0.2, q=None):
     """build_discriminator (:343-380).  noise: N(0,0.1) tensor added to x when training (:352);
     keep: {0,1} tensor for Dropout(0.2) on the d5 output when training (:363), scaled 1/(1-rate)."""
+    q = q or _ident
     h = x
     if training and noise is not None:
-        h = h + noise
-    for i in (1, 2, 3, 4):
-        h = _cli(p, f"d{i}", h, stride=2, bias=False)
+        h = q(h + noise)
+    for i in (1, 2, 3):
+        h = _cli(p, f"d{i}", h, stride=2, bias=False, q=q)
+    y4 = _cli_parts(p, "d4", h, stride=2, bias=False, q=q)
     if mask is not None:
         pooled = max_pool(mask, 16)                                                     # :358
-        a = leaky_relu(conv2d_same(pooled, p["dattn_a.w"], p["dattn_a.b"]))
-        a = leaky_relu(conv2d_same(a, p["dattn_b.w"], p["dattn_b.b"]))
-        h = h + a                                                                       # :359
-    h = _cli(p, "d5", h, stride=2, bias=False)
+        a = q(leaky_relu(conv2d_same(pooled, p["dattn_a.w"], p["dattn_a.b"])))
+        a = q(leaky_relu(conv2d_same(a, p["dattn_b.w"], p["dattn_b.b"])))
+        y4 = y4 + a                                                                     # :359
+    h = q(y4)
+    h = _cli(p, "d5", h, stride=2, bias=False, q=q)
     if training and keep is not None:
-        h = h * keep / (1.0 - dropout_rate)
-    rf = leaky_relu(conv2d_same(h, p["head.w"], None, 1))                               # :365-369
+        h = q(h * keep * (1.0 / (1.0 - dropout_rate)))
+    rf = q(leaky_relu(conv2d_same(h, p["head.w"], None, 1)))                            # :365-369
     cls = h.reshape(h.shape[0], -1) @ p["dense.w"]                                      # :371-375
     return rf, cls
 
 
-def specseg_forward(p, x):
+def specseg_forward(p, x, q=None):
     """SpecSeg U-Net at predict time (SpecSeg.py:27-98): dropout inactive, BN uses moving stats."""
+    q = q or _ident
+
     def bn(h, i):
         return (h - p[f"bn{i}.mean"]) * torch.rsqrt(p[f"bn{i}.var"] + BN_EPS) * p[f"bn{i}.gamma"] + p[f"bn{i}.beta"]
     skips = []
     h = x
     for i in range(1, 6):
-        h = F.relu(conv2d_same(h, p[f"c{i}a.w"], p[f"c{i}a.b"]))
-        h = F.relu(conv2d_same(h, p[f"c{i}b.w"], p[f"c{i}b.b"]))
-        h = bn(h, i)
+        h = q(F.relu(conv2d_same(h, p[f"c{i}a.w"], p[f"c{i}a.b"])))
+        h = q(F.relu(conv2d_same(h, p[f"c{i}b.w"], p[f"c{i}b.b"])))
+        h = q(bn(h, i))
         if i < 5:
             skips.append(h)
             h = max_pool(h, 2)
     for i in (6, 7, 8, 9):
-        up = conv2d_transpose_same(h, p[f"u{i}.w"], p[f"u{i}.b"], 2)
+        up = q(conv2d_transpose_same(h, p[f"u{i}.w"], p[f"u{i}.b"], 2))
         h = torch.cat([up, skips[9 - i]], dim=3)
-        h = F.relu(conv2d_same(h, p[f"c{i}a.w"], p[f"c{i}a.b"]))
-        h = F.relu(conv2d_same(h, p[f"c{i}b.w"], p[f"c{i}b.b"]))
-    return torch.sigmoid(conv2d_same(h, p["out.w"], p["out.b"]))
+        h = q(F.relu(conv2d_same(h, p[f"c{i}a.w"], p[f"c{i}a.b"])))
+        h = q(F.relu(conv2d_same(h, p[f"c{i}b.w"], p[f"c{i}b.b"])))
+    return q(torch.sigmoid(conv2d_same(h, p["out.w"], p["out.b"])))
 
 
 # --------------------------------------------------------------------------------------
@@ -437,11 +462,13 @@ def assemble_cyclic_inputs(Y, gen_Y, bits):
 def train_step_losses(Gp, Dp, origs: Sequence[torch.Tensor], mask, bits: Sequence[bool], T: float,
                       d_noise: Optional[Sequence[torch.Tensor]] = None,
                       d_keep: Optional[Sequence[torch.Tensor]] = None,
-                      live_mask: bool = True, per_image: bool = True):
+                      live_mask: bool = True, per_image: bool = True, q=None):
     """The taped region of train_step (:495-844).  origs = (orig0, orig45, orig90, orig135, origED),
     each [B,S,S,3] in [0,1].  mask = SpecSeg.predict(I90_Ych) (:492), passed in (outside the tape).
     d_noise / d_keep: the GaussianNoise / Dropout draws for the two training=True D calls (D1, D2).
-    Batch semantics: CE / SSIM terms are means over the batch."""
+    Batch semantics: CE / SSIM terms are means over the batch.
+    q: storage-precision model (`bf16_storage`) applied where the bf16 execution mode stores network inputs / activations."""
+    q = q or _ident
     S = origs[0].shape[1]
     gmask = mask if live_mask else None
     ds = [per_image_standardization(rgb_to_yuv(o), per_image)[0] for o in origs]        # :480-484
@@ -449,22 +476,22 @@ def train_step_losses(Gp, Dp, origs: Sequence[torch.Tensor], mask, bits: Sequenc
     avgCbCr = (ds[0][..., 1:] + ds[1][..., 1:] + ds[2][..., 1:] + ds[3][..., 1:] + ds[4][..., 1:]) / 5.0
     out = {"ds_yuv": ds, "avgCbCr": avgCbCr}
 
-    gen_input = assemble_g1_input(Y, bits)                                              # :531
-    gen_Y = generator_forward(Gp, gen_input, gmask)                                     # :538
+    gen_input = q(assemble_g1_input(Y, bits))                                           # :531
+    gen_Y = generator_forward(Gp, gen_input, gmask, q=q)                                # :538
     gen_rgb = yuv_to_rgb(torch.cat([gen_Y, avgCbCr], dim=3))                            # :544,553
     n1 = d_noise[0] if d_noise is not None else None
     n2 = d_noise[1] if d_noise is not None else None
     k1 = d_keep[0] if d_keep is not None else None
     k2 = d_keep[1] if d_keep is not None else None
-    rf_gen, cls_gen = discriminator_forward(Dp, gen_rgb, gmask, True, n1, k1)           # :559
-    rf_tgt, cls_tgt = discriminator_forward(Dp, origs[4], gmask, True, n2, k2)          # :563
+    rf_gen, cls_gen = discriminator_forward(Dp, q(gen_rgb), gmask, True, n1, k1, q=q)   # :559
+    rf_tgt, cls_tgt = discriminator_forward(Dp, q(origs[4]), gmask, True, n2, k2, q=q)  # :563
 
-    cyc_in = assemble_cyclic_inputs(Y, gen_Y, bits)                                     # :576-594
-    cyc_Y = [generator_forward(Gp, ci, gmask) for ci in cyc_in]                         # :603-607
+    cyc_in = [q(c) for c in assemble_cyclic_inputs(Y, gen_Y, bits)]                     # :576-594
+    cyc_Y = [generator_forward(Gp, ci, gmask, q=q) for ci in cyc_in]                    # :603-607
     cyc_yuv = [torch.cat([cy, avgCbCr], dim=3) for cy in cyc_Y]                         # :613-617
     cyc_rgb = [yuv_to_rgb(c) for c in cyc_yuv]                                          # :620-624
-    d3 = [discriminator_forward(Dp, c, gmask, False) for c in cyc_rgb]                  # :627-631
-    d4 = [discriminator_forward(Dp, o, gmask, False) for o in origs]                    # :638-642
+    d3 = [discriminator_forward(Dp, q(c), gmask, False, q=q) for c in cyc_rgb]          # :627-631
+    d4 = [discriminator_forward(Dp, q(o), gmask, False, q=q) for o in origs]            # :638-642
 
     def sqd(a, t):
         return ((a - t) ** 2).mean()
@@ -520,12 +547,12 @@ def _trainable(p):
 
 
 def train_step_grads(Gp, Dp, origs, mask, bits, T, d_noise=None, d_keep=None, live_mask=True,
-                     per_image=True, clip: bool = True):
+                     per_image=True, clip: bool = True, q=None):
     """:859-871: grads of (total_D + total_Cls) w.r.t. D vars and of total_G w.r.t. G vars, then
     clip_by_value(+-1).  Returns (losses, gradsG: OrderedDict, gradsD: OrderedDict)."""
     Gp = OrderedDict((k, v.detach().clone().requires_grad_(k in _trainable(Gp))) for k, v in Gp.items())
     Dp = OrderedDict((k, v.detach().clone().requires_grad_(k in _trainable(Dp))) for k, v in Dp.items())
-    L = train_step_losses(Gp, Dp, origs, mask, bits, T, d_noise, d_keep, live_mask, per_image)
+    L = train_step_losses(Gp, Dp, origs, mask, bits, T, d_noise, d_keep, live_mask, per_image, q)
     dnames, gnames = _trainable(Dp), _trainable(Gp)
     gD = torch.autograd.grad(L["total_Discriminator_loss"] + L["total_Classification_loss"],
                              [Dp[k] for k in dnames], retain_graph=True, allow_unused=True)

@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(256) inorm_stats_kernel(const T* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 4; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][4 + j] = q[j]; }
     __syncthreads();
-    if (threadIdx.x < TX * 8) {
-        const int t = threadIdx.x / 8, j = threadIdx.x % 8;
+    for (int e = threadIdx.x; e < TX * 8; e += 256) {      // TX * 8 partial columns (up to 512) over 256 threads
+        const int t = e / 8, j = e % 8;
         const int cgo = blockIdx.y * TX + t;
         if (cgo * 4 < C) {
             double acc = 0.0;
@@ -170,8 +170,8 @@ __global__ void __launch_bounds__(256) inorm_bwd_stats_kernel(const T* __restric
 #pragma unroll
     for (int j = 0; j < 4; ++j) { red[threadIdx.x][j] = s[j]; red[threadIdx.x][4 + j] = q[j]; }
     __syncthreads();
-    if (threadIdx.x < TX * 8) {
-        const int t = threadIdx.x / 8, j = threadIdx.x % 8;
+    for (int e = threadIdx.x; e < TX * 8; e += 256) {      // TX * 8 partial columns (up to 512) over 256 threads
+        const int t = e / 8, j = e % 8;
         const int cgo = blockIdx.y * TX + t;
         if (cgo * 4 < C) {
             double acc = 0.0;
@@ -256,9 +256,8 @@ __global__ void __launch_bounds__(256) bn_eval_kernel(const T* __restrict__ x, i
                 mx.x = fmaxf(mx.x, y.x); mx.y = fmaxf(mx.y, y.y); mx.z = fmaxf(mx.z, y.z); mx.w = fmaxf(mx.w, y.w);
             }
             // the pooled value must be the max of the STORED (rounded) values so that bf16 matches a separate pool pass
-            T tmp[4];
-            stf(&tmp[0], mx.x); stf(&tmp[1], mx.y); stf(&tmp[2], mx.z); stf(&tmp[3], mx.w);
-            st4(pb + (long long)u * ldp, make_float4(ldf(&tmp[0]), ldf(&tmp[1]), ldf(&tmp[2]), ldf(&tmp[3])));
+            // (rounding is monotone, so max-then-round == round-then-max)
+            st4(pb + (long long)u * ldp, mx);
         }
     } else {
         const int ubeg = blockIdx.x * upb, uend = min(ubeg + upb, HW);

@@ -1,0 +1,433 @@
+"""Host-side mirror of the reference's Python surface for the hot path (class ShmGANwithSSpecSeg, ShmGANwithSSpecSeg.py:96-875;
+inference body test.py:218-297; SpecSeg.py:27-98).  Same names, argument meaning and published attributes, so main.py /
+test.py style callers drop in; every number is produced by libshmgan kernels (no torch math, no CPU fallback).
+
+What differs from the reference, on purpose:
+  * tensors are torch CUDA tensors (NHWC fp32 in [0,1]) instead of tf tensors;
+  * the batch may be > 1: one train_step call batches the 5 cyclic generator passes (5B images) and the 12 discriminator passes
+    (2B with noise/dropout + 10B without) into a handful of large launches; per-image statistics (Q5), batch-mean losses (Q6);
+  * the SpecSeg mask is a LIVE input of the attention branch (Q1); `live_mask=False` reproduces the as-written graph;
+  * random draws are explicit: `drop_bits` (5 Bernoulli(0.5) bits, :509-521), `TARGET_LABELS` (:986), noise / dropout seeds;
+  * precision: dtype "fp32" = exact-fp32 SIMT kernels (parity mode), "bf16" = tcgen05 tensor-core kernels, fp32 master weights.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import random
+from types import SimpleNamespace
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import losses as LS
+from . import nets, ops
+from .ops import _p, _stream, call
+
+__all__ = ["ShmGANwithSSpecSeg", "SpecSeg", "default_args"]
+
+
+def default_args(**kw):
+    """The argparse defaults of main.py:30-70 (only the flags the hot path reads), overridable by keyword."""
+    a = dict(c_dim=5, image_size=128, batch_size=1, num_epochs=200, num_iteration_decay=100000, g_lr=2e-5, d_lr=2e-5,
+             n_critic=5, beta1=0.5, beta2=0.99, d_repeat_num=6, mode="train", data_dir="", model_save_dir="./models",
+             checkpoint_save_dir="./checkpoints", result_dir="./results", log_dir="./logs/train", log_step=1,
+             checkpoint_save_step=10, filter_size=64)
+    a.update(kw)
+    return SimpleNamespace(**a)
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    return ops.cast(t.contiguous(), torch.float32)
+
+
+class _GeneratorModel:
+    """What build_generator returns: callable like the Keras model, G(x[B,S,S,10] fp32, training) -> [B,S,S,1] fp32.
+    `mask` ([B or 1,S,S,1], SpecSeg probabilities) feeds the attention branch (live-mask mode)."""
+
+    def __init__(self, net: nets.Generator):
+        self.net = net
+        self.trainable = True
+
+    def __call__(self, x, training=False, mask=None):
+        n = self.net
+        attn = None
+        if mask is not None and n.live_mask:
+            attn, _ = n.attention(ops.cast(mask.contiguous(), n.dtype))
+        y = n.forward(ops.cast(x.contiguous(), n.dtype), attn)
+        return _f32(y)
+
+    @property
+    def trainable_variables(self):
+        return [v for k, v in self.net.store.views.items() if k in self.net.store.gviews]
+
+
+class _DiscriminatorModel:
+    """What build_discriminator returns: D(x[B,S,S,3] fp32, training) -> (real/fake map [B,S/32,S/32,1], logits [B,5]).
+    training=True draws GaussianNoise(0.1) and Dropout(0.2) (:352, :363) from the counter-based RNG with `seed`."""
+
+    def __init__(self, net: nets.Discriminator):
+        self.net = net
+        self.trainable = True
+        self.calls = 0
+
+    def __call__(self, x, training=False, mask=None, seed=0):
+        n = self.net
+        attn = None
+        if mask is not None and n.live_mask:
+            attn, _ = n.attention(ops.cast(mask.contiguous(), n.dtype))
+        xd = ops.cast(x.contiguous(), n.dtype)
+        noise = keep = None
+        if training:
+            B, S = x.shape[0], x.shape[1]
+            noise = ops.rng_normal(tuple(x.shape), seed, 2 * self.calls << 32, 0.1, n.dtype)
+            keep = ops.rng_keep((B, S // 32, S // 32, n.blocks[-1].conv.cout), seed, (2 * self.calls + 1) << 32, 1.0 - n.dropout, n.dtype)
+            self.calls += 1
+        rf, cls = n.forward(xd, attn, noise, keep)
+        return _f32(rf), cls
+
+    @property
+    def trainable_variables(self):
+        return [v for k, v in self.net.store.views.items() if k in self.net.store.gviews]
+
+
+class SpecSeg:
+    """SpecSeg(H, W, C) of SpecSeg.py:27; `.predict(x[B,S,S,1], verbose=0)` -> sigmoid probabilities [B,S,S,1] fp32.
+    The reference loads specsegv3_chkpt.h5 (absent from the checkout); weights here are the seeded reference initialisers
+    unless `load()` is given a Keras-layout dict."""
+
+    def __init__(self, H, W, C=1, dtype=torch.float32, seed=44, tensor_core=True):
+        assert C == 1, "SpecSeg takes a single-channel (Y) image"
+        assert H % 16 == 0 and W % 16 == 0, "SpecSeg needs sides divisible by 16 (4 pooling levels)"
+        self.net = nets.SpecSegNet(dtype, seed=seed, tensor_core=tensor_core)
+
+    def load(self, named):
+        self.net.store.load(named)
+
+    def predict(self, x, verbose=0):
+        y = self.net.predict(ops.cast(x.contiguous(), self.net.dtype))
+        return _f32(y)
+
+
+class ShmGANwithSSpecSeg:
+    """ShmGANwithSSpecSeg(args) (ShmGANwithSSpecSeg.py:96).  Extra keyword arguments select the B200 execution mode."""
+
+    def __init__(self, args, dtype: str = "fp32", live_mask: bool = True, tensor_core: bool = True, seed: int = 25,
+                 process_group=None, device: Optional[int] = None):
+        self.c_dim = 5                                      # :192 (args.c_dim is overridden)
+        self.image_size = args.image_size
+        self.batch_size = args.batch_size
+        self.num_epochs = getattr(args, "num_epochs", 1)
+        self.num_iteration_decay = getattr(args, "num_iteration_decay", 100000)
+        self.g_lr, self.d_lr = args.g_lr, getattr(args, "d_lr", args.g_lr)   # d_lr is ignored by the reference too (:169-174)
+        self.n_critic = getattr(args, "n_critic", 5)
+        self.beta1, self.beta2 = args.beta1, args.beta2
+        self.d_repeat_num = getattr(args, "d_repeat_num", 6)
+        self.mode = getattr(args, "mode", "train")
+        for k in ("data_dir", "model_save_dir", "checkpoint_save_dir", "result_dir", "log_dir", "log_step", "checkpoint_save_step"):
+            setattr(self, k, getattr(args, k, None))
+        self.filter_size = args.filter_size
+        self.seed = seed
+        self.randomness = 0.50                              # :159
+        self.dropout_amnt = 0.2                             # :160
+        self.TARGET_LABELS = 0.90                           # :161; the train loop redraws it per step (:986)
+        self.use_lsgan = True
+        self.gradmapD, self.gradmapG = {}, {}
+        self.epoch = 0
+        self.stddev_arr, self.mean_arr, self.variance_arr = [], [], []      # datasetLoader.py:42-44
+        assert dtype in ("fp32", "bf16")
+        assert self.image_size % 32 == 0, "image_size must be a multiple of 32 (5 stride-2 discriminator blocks)"
+        self.dtype = torch.float32 if dtype == "fp32" else torch.bfloat16
+        self.live_mask = live_mask
+        self.tensor_core = tensor_core and dtype == "bf16"
+        self.pg = process_group
+        if device is not None:
+            torch.cuda.set_device(device)
+        self.specular_candidate = torch.zeros((1, self.image_size, self.image_size, 1), device="cuda")   # :206
+        self.G = self.D = self.SpecSeg = None
+        self._rng = random.Random(seed)
+        self.drop_bits: Optional[Sequence[bool]] = None     # set to pin the 5 Bernoulli draws of the next step
+        self.d_noise = self.d_keep = None                   # set to pin the GaussianNoise / Dropout draws ([2B,...] tensors)
+        self.noise_seed = seed
+        self.step_count = 0
+        self.table = LS.LossTable()
+        self._reducer = None
+
+    # -- model builders (same names as the reference) --------------------------------------------------------------
+    def build_generator(self):
+        """build_generator (:228-327) with the live mask-attention branch (:404-412)."""
+        net = nets.Generator(self.filter_size, self.live_mask, self.dtype, seed=42, tensor_core=self.tensor_core)
+        return _GeneratorModel(net)
+
+    def build_discriminator(self):
+        """build_discriminator (:343-380)."""
+        net = nets.Discriminator(self.image_size, self.filter_size, self.live_mask, self.dtype, seed=43,
+                                 tensor_core=self.tensor_core, dropout=self.dropout_amnt)
+        return _DiscriminatorModel(net)
+
+    def build(self):
+        """What train() does before its loop (:911-931): G, D and the SpecSeg mask network."""
+        if self.G is None:
+            self.G = self.build_generator()
+        if self.D is None:
+            self.D = self.build_discriminator()
+        if self.SpecSeg is None:
+            self.SpecSeg = SpecSeg(self.image_size, self.image_size, 1, self.dtype, tensor_core=self.tensor_core)
+        return self
+
+    # -- preprocessing ------------------------------------------------------------------------------------------------
+    def custom_per_image_standardization(self, image):
+        """:1271-1309 on a YUV tensor is served by `yuv_standardize` on the RGB tensor (rgb->yuv and the divide are fused);
+        this entry keeps the reference name for callers that hold RGB (test.py:218)."""
+        yuv, scale = ops.yuv_standardize(image.contiguous())
+        self.stddev_arr.append(scale)
+        return yuv
+
+    def calculate_estimate_diffuse(self, i0, i45, i90, i135):
+        """utils.py:68-123: pseudo-diffuse = per-pixel, per-channel min over the four polarisation images."""
+        return ops.pseudo_diffuse_min4(i0.contiguous(), i45.contiguous(), i90.contiguous(), i135.contiguous())
+
+    def _y_plane(self, yuv, dtype):
+        """Y channel [B,S,S,1] of a yuv tensor, converted to `dtype` (:486-490)."""
+        B, S = yuv.shape[0], yuv.shape[1]
+        out = ops.new((B, S, S, 1), dtype)
+        ops.cast_into(yuv[..., 0:1], out)
+        return out
+
+    # -- the hot path ---------------------------------------------------------------------------------------------------
+    def train_step(self, orig0, orig45, orig90, orig135, origED):
+        """train_step (:467-875).  Five [B,S,S,3] fp32 CUDA tensors in [0,1]; returns None and publishes the reference's
+        attributes (gen_Y, gen_rgb, cyc_gen*_rgb, specular_candidate, the loss scalars ...)."""
+        self.build()
+        G, D = self.G.net, self.D.net
+        origs = [t.contiguous() for t in (orig0, orig45, orig90, orig135, origED)]
+        B, S = origs[0].shape[0], origs[0].shape[1]
+        assert S == self.image_size and all(tuple(t.shape) == (B, S, S, 3) and t.dtype == torch.float32 for t in origs)
+        dt, f32 = self.dtype, torch.float32
+        npix = B * S * S
+        T = float(self.TARGET_LABELS)
+        bits = list(self.drop_bits) if self.drop_bits is not None else [self._rng.random() < self.randomness for _ in range(5)]
+        self.last_drop_bits = bits
+        tab = self.table
+        tab.zero()
+
+        # ---- preprocessing (:480-506) and the mask (:492, outside the tape)
+        ds = [ops.yuv_standardize(o)[0] for o in origs]
+        avg = ops.avg_cbcr(ds)
+        mask = self.SpecSeg.net.predict(self._y_plane(ds[2], dt))
+        self.specular_candidate = _f32(mask)
+        g_attn = g_attn_saved = d_attn = d_attn_saved = None
+        if self.live_mask:
+            g_attn, g_attn_saved = G.attention(mask)
+            d_attn, d_attn_saved = D.attention(mask)
+
+        # ---- G(1) (:509-553)
+        gen_in = ops.new((B, S, S, 10), dt)
+        ops.assemble_input([None if bits[k] else ds[k] for k in range(5)], [3] * 5, 4, gen_in)
+        gen_Y_lp, tape1 = G.forward(gen_in, g_attn, save=True)
+        gen_Y = _f32(gen_Y_lp)
+        xA = ops.new((2 * B, S, S, 3), dt)                  # D batch A = [gen_rgb | origED], training=True (:559-563)
+        xB = ops.new((10 * B, S, S, 3), dt)                 # D batch B = [5 cyc_rgb | 5 orig], training=False (:627-642)
+        if dt == f32:
+            gen_rgb = xA[:B]
+            ops.yuv2rgb(gen_Y, avg, gen_rgb, None)
+            ops.cast_into(origs[4], xA[B:])
+        else:
+            gen_rgb = ops.new((B, S, S, 3), f32)
+            ops.yuv2rgb(gen_Y, avg, gen_rgb, xA[:B])
+            ops.cast_into(origs[4], xA[B:])
+
+        # ---- cyclic G passes, batched as 5B images: pass k = images [kB, (k+1)B) (:576-624)
+        cyc_in = ops.new((5 * B, S, S, 10), dt)
+        for k in range(5):
+            srcs, lds = [], []
+            for j in range(5):
+                if j == k:
+                    srcs.append(None); lds.append(0)
+                elif bits[j]:
+                    srcs.append(gen_Y); lds.append(1)
+                else:
+                    srcs.append(ds[j]); lds.append(3)
+            ops.assemble_input(srcs, lds, k, cyc_in[k * B:(k + 1) * B])
+        cyc_Y_lp, tape5 = G.forward(cyc_in, g_attn, save=True)
+        cyc_Y = _f32(cyc_Y_lp)
+        if dt == f32:
+            cyc_rgb = xB[:5 * B]
+            ops.yuv2rgb(cyc_Y, avg, cyc_rgb, None)
+        else:
+            cyc_rgb = ops.new((5 * B, S, S, 3), f32)
+            ops.yuv2rgb(cyc_Y, avg, cyc_rgb, xB[:5 * B])
+        for k in range(5):
+            ops.cast_into(origs[k], xB[(5 + k) * B:(6 + k) * B])
+
+        # ---- D passes
+        s32 = S // 32
+        if self.d_noise is not None:
+            noise, keep = ops.cast(self.d_noise.contiguous(), dt), ops.cast(self.d_keep.contiguous(), dt)
+        else:
+            noise = ops.rng_normal((2 * B, S, S, 3), self.noise_seed, (4 * self.step_count) << 32, 0.1, dt)
+            keep = ops.rng_keep((2 * B, s32, s32, D.blocks[-1].conv.cout), self.noise_seed, (4 * self.step_count + 2) << 32,
+                                1.0 - self.dropout_amnt, dt)
+        rfA_lp, clsA, tapeA = D.forward(xA, d_attn, noise, keep, save=True)
+        rfB_lp, clsB, tapeB = D.forward(xB, d_attn, None, None, save=True)
+        rfA, rfB = _f32(rfA_lp), _f32(rfB_lp)
+        nrf = B * s32 * s32
+
+        # ---- losses (:669-844): values into the table, seed gradients for the two backward sweeps
+        # D-loss seeds: total_D + total_Cls = (D1_cls + D3_cls)/6 + (D2_rf + D4_rf)/6 + 10.5 D4_cls (+ NST, no D dependence)
+        dD_rfA, dD_clsA = torch.zeros_like(rfA), torch.zeros_like(clsA)
+        dD_rfB, dD_clsB = torch.zeros_like(rfB), torch.zeros_like(clsB)
+        # G-loss seeds through D: total_G contains (D1_rf + D3_rf)/6
+        dG_rfA, dG_rfB = ops.new((B, s32, s32, 1), f32), ops.new((5 * B, s32, s32, 1), f32)
+        sixth = 1.0 / 6.0
+        LS.lsgan(rfA[:B], T, tab.slot("D1_rf"), 1.0, dG_rfA, sixth)                                   # :677
+        LS.lsgan(rfB[:5 * B], T, tab.slot("D3_rf"), 5.0, dG_rfB, 5.0 * sixth)                        # :669-674 (sum of 5 means)
+        # D2_rf = sqd(rf_tgt, T) + mean(rf_gen^2) (:721); it enters total_D twice (D2 + D4, :728,:837-840)
+        LS.lsgan(rfA[B:], T, tab.slot("D2_rf"), 1.0, dD_rfA[B:], 2.0 * sixth)
+        LS.lsgan(rfA[:B], 0.0, tab.slot("D2_rf"), 1.0, dD_rfA[:B], 2.0 * sixth)
+        LS.lsgan(rfB[5 * B:], T, tab.slot("D4_rf_only"), 5.0, dD_rfB[5 * B:], 5.0 * sixth)           # :723-727
+        LS.lsgan(rfB[:5 * B], 0.0, tab.slot("D4_rf_only"), 5.0, dD_rfB[:5 * B], 5.0 * sixth)
+        LS.softmax_ce(clsA[:B], [0, 0, 0, 0, T], tab.slot("D1_cls"), 1.0, dD_clsA[:B], sixth)         # :702
+        for k in range(5):
+            onehot = [1.0 if j == k else 0.0 for j in range(5)]
+            LS.softmax_ce(clsB[k * B:(k + 1) * B], onehot, tab.slot("D3_cls"), 1.0, dD_clsB[k * B:(k + 1) * B], sixth)      # :695-700
+            LS.softmax_ce(clsB[(5 + k) * B:(6 + k) * B], onehot, tab.slot("D4_cls"), 1.0, dD_clsB[(5 + k) * B:(6 + k) * B], 10.5)  # :709-714
+
+        # image-space terms of total_G = ... + 10 L1 + 10 ssim + 10 NST (:829-832)
+        d_gen_rgb = ops.new((B, S, S, 3), f32)
+        d_cyc_rgb = ops.new((5 * B, S, S, 3), f32)
+        LS.l1(gen_rgb, origs[4], tab.slot("L1_G1"), 1.0, d_gen_rgb, 10.0 / 5.0)                      # :744,:751
+        for k in range(5):
+            w = 10.0 * (10.0 if k == 4 else 0.2)
+            LS.l1(cyc_rgb[k * B:(k + 1) * B], origs[k], tab.slot("L1_c%d" % k), 1.0, d_cyc_rgb[k * B:(k + 1) * B], w)   # :745-751
+        d_cyc_Y = torch.zeros((5 * B, S, S, 1), dtype=f32, device=cyc_Y.device)
+        self.ssim_values = []
+        for k in range(5):
+            Yk, dYk = cyc_Y[k * B:(k + 1) * B], d_cyc_Y[k * B:(k + 1) * B]
+            if not bits[k]:                                                                            # :774-778
+                w = 10.0 * (10.0 if k == 4 else 1.0) / 5.0
+                self.ssim_values.append(LS.ssim_term(Yk, avg, ds[k], tab.slot("ssim%d" % k), 1.0, dYk, w))
+            LS.spec(Yk, avg, ds[k], self.specular_candidate, tab.slot("spec%d" % k), 1.0)            # :792-796 (value only)
+        Y4, dY4 = cyc_Y[4 * B:], d_cyc_Y[4 * B:]
+        LS.mse_ycc(Y4, avg, ds[0], tab.slot("content"), 1.0, dY4, 10.0)                               # :814 (vs ds1, as written)
+        LS.style(Y4, avg, ds[4], S, tab.slot("style"), 1.0, dY4, 10.0 * 100.0)                        # :817-826
+
+        # ---- backward: D weight gradients (:859), then the generator loss through D (dgrad only) and G (:868)
+        D.store.zero_grad()
+        G.store.zero_grad()
+        d_dattn = torch.zeros_like(d_attn) if self.live_mask else None
+        D.backward(tapeA, dD_rfA, dD_clsA, wgrad=True, need_dx=False, dattn=d_dattn, attn_nb=B)
+        D.backward(tapeB, dD_rfB, dD_clsB, wgrad=True, need_dx=False, dattn=d_dattn, attn_nb=B)
+        if self.live_mask:
+            D.attention_backward(d_attn_saved, d_dattn)
+        if self._reducer is not None:
+            self._reducer.reduce_async(D.store.grad)
+        dxA = D.backward(tapeA, dG_rfA, None, n=B, wgrad=False, need_dx=True)
+        dxB = D.backward(tapeB, dG_rfB, None, n=5 * B, wgrad=False, need_dx=True)
+        lpA, lpB = (None, None) if dt == f32 else (dxA, dxB)
+        if dt == f32:
+            ops.axpy(1.0, dxA, d_gen_rgb)
+            ops.axpy(1.0, dxB, d_cyc_rgb)
+        ops.yuv2rgb_bwd(d_cyc_rgb, lpB, d_cyc_Y, accumulate=True)
+        g_dattn = [torch.zeros_like(a) for a in g_attn] if self.live_mask else None
+        any_dropped = any(bits)
+        d_cyc_in = G.backward(tape5, ops.cast(d_cyc_Y, dt), g_dattn, attn_nb=B, need_dx=any_dropped)
+        d_gen_Y = ops.new((B, S, S, 1), f32)
+        ops.yuv2rgb_bwd(d_gen_rgb, lpA, d_gen_Y, accumulate=False)
+        if any_dropped:                                    # gen_Y feeds the dropped slots of the cyclic inputs (:576-580)
+            for k in range(5):
+                slots = [j for j in range(5) if j != k and bits[j]]
+                if slots:
+                    ops.assemble_bwd(d_cyc_in[k * B:(k + 1) * B], slots, d_gen_Y)
+        G.backward(tape1, ops.cast(d_gen_Y, dt), g_dattn, attn_nb=B, need_dx=False)
+        if self.live_mask:
+            G.attention_backward(g_attn_saved, g_dattn)
+        if self._reducer is not None:
+            self._reducer.reduce_async(G.store.grad)
+            self._reducer.wait()
+
+        # ---- clip_by_value(+-1) + Adam (:860-871); both optimisers use g_lr (:169-174)
+        gscale = 1.0 if self._reducer is None else 1.0 / self._reducer.world
+        D.store.adam_step(self.g_lr, self.beta1, self.beta2, 1e-7, 1.0, gscale)
+        G.store.adam_step(self.g_lr, self.beta1, self.beta2, 1e-7, 1.0, gscale)
+        self.step_count += 1
+
+        # ---- published tensors / scalars (reference attribute names)
+        self.gen_input, self.gen_Y, self.gen_rgb = gen_in, gen_Y, gen_rgb
+        self.gen_rgb_output = gen_rgb
+        self.averageCbCr = avg
+        self.ds_yuv = ds
+        self.cyc_Y = [cyc_Y[k * B:(k + 1) * B] for k in range(5)]
+        rgbs = [cyc_rgb[k * B:(k + 1) * B] for k in range(5)]
+        self.cyc_gen0_rgb, self.cyc_gen45_rgb, self.cyc_gen90_rgb, self.cyc_gen135_rgb, self.cyc_genED_rgb = rgbs
+        self.RealFake_gen_D1, self.label_gen_D1 = rfA[:B], clsA[:B]
+        self.RealFake_target_D2, self.label_target_D2 = rfA[B:], clsA[B:]
+        self.RealFake_cyc_D3 = [rfB[k * B:(k + 1) * B] for k in range(5)]
+        self.label_cyc_D3 = [clsB[k * B:(k + 1) * B] for k in range(5)]
+        self.RealFake_orig_D4 = [rfB[(5 + k) * B:(6 + k) * B] for k in range(5)]
+        (self.label_orig0_D4, self.label_orig45_D4, self.label_orig90_D4, self.label_orig135_D4,
+         self.label_origED_D4) = [clsB[(5 + k) * B:(6 + k) * B] for k in range(5)]
+        self._publish_losses(tab.read())
+        return None
+
+    def _publish_losses(self, v):
+        """Totals of :669-844 from the per-term table (one device->host copy per step)."""
+        L1 = (v["L1_c0"] + v["L1_c1"] + v["L1_c2"] + v["L1_c3"] + v["L1_G1"]) / 5.0 + v["L1_c4"] * 10.0
+        ssim = (v["ssim0"] + v["ssim1"] + v["ssim2"] + v["ssim3"] + v["ssim4"] * 10.0) / 5.0
+        spec = (v["spec0"] + v["spec1"] + v["spec2"] + v["spec3"]) / 5.0 + v["spec4"] * 5.0
+        nst = 100.0 * v["style"] + v["content"]
+        D4_rf = v["D4_rf_only"] + v["D2_rf"]
+        self.D1_RealFake_loss, self.D3_RealFake_cyc = v["D1_rf"], v["D3_rf"]
+        self.D1_classification_loss, self.D3_classification_loss = v["D1_cls"], v["D3_cls"]
+        self.D2_RealFake_target = v["D2_rf"]
+        self.D4_RealFake_cyc, self.D4_classification_loss = D4_rf, v["D4_cls"]
+        self.G_gan_loss = (v["D3_rf"] + v["D1_rf"]) / 6.0
+        self.G_clsf_loss = (v["D3_cls"] + v["D1_cls"]) / 6.0
+        self.L1_loss_Gen, self.ssim_cyc_loss, self.Spec_loss = L1, ssim, spec
+        self.content_loss, self.style_loss, self.total_NST_loss = v["content"], v["style"], nst
+        self.total_Generator_loss = (v["D1_rf"] + v["D3_rf"]) / 6.0 + 10.0 * L1 + 10.0 * ssim + 10.0 * nst
+        self.total_Discriminator_loss = ((v["D1_cls"] + v["D3_cls"]) / 6.0 + (v["D2_rf"] + D4_rf) / 6.0
+                                         + 0.5 * v["D4_cls"] + 10.0 * nst)
+        self.total_Classification_loss = 10.0 * (v["D4_cls"] + nst)
+
+    def inference_step(self, rgb, cyclic: bool = False):
+        """The per-image body of test.py:218-297: standardise -> SpecSeg mask -> G1 with only slot 0 populated and the ED
+        one-hot plane -> yuv->rgb with the image's own CbCr.  Returns gen_rgb [B,S,S,3] fp32 (and publishes gen_Y, mask)."""
+        self.build()
+        G = self.G.net
+        rgb = rgb.contiguous()
+        B, S = rgb.shape[0], rgb.shape[1]
+        dt = self.dtype
+        yuv = ops.yuv_standardize(rgb)[0]
+        mask = self.SpecSeg.net.predict(self._y_plane(yuv, dt))
+        self.specular_candidate = _f32(mask)
+        attn = G.attention(mask)[0] if self.live_mask else None
+        gin = ops.new((B, S, S, 10), dt)
+        ops.assemble_input([yuv, None, None, None, None], [3, 0, 0, 0, 0], 4, gin)                   # test.py:227-235
+        self.gen_Y = _f32(G.forward(gin, attn))
+        cbcr = ops.new((B, S, S, 2), torch.float32)
+        ops.cast_into(yuv[..., 1:3], cbcr)                                                             # test.py:224
+        self.gen_rgb = ops.new((B, S, S, 3), torch.float32)
+        ops.yuv2rgb(self.gen_Y, cbcr, self.gen_rgb, None)                                              # test.py:244-250
+        if cyclic:                                          # test.py:252-284 (Q11: the R channel stands in for Y)
+            R = ops.new((B, S, S, 1), torch.float32)
+            ops.cast_into(self.gen_rgb[..., 0:1], R)
+            cin = ops.new((5 * B, S, S, 10), dt)
+            for k in range(5):
+                srcs = [None if j == k else R for j in range(5)]
+                ops.assemble_input(srcs, [1] * 5, k, cin[k * B:(k + 1) * B])
+            cy = _f32(G.forward(cin, attn))
+            crgb = ops.new((5 * B, S, S, 3), torch.float32)
+            ops.yuv2rgb(cy, cbcr, crgb, None)
+            self.cyc_rgb = [crgb[k * B:(k + 1) * B] for k in range(5)]
+        return self.gen_rgb
+
+    # -- data parallel ----------------------------------------------------------------------------------------------------
+    def enable_data_parallel(self, process_group=None, bucket_mb: float = 25.0):
+        """Shard the batch over the ranks of `process_group` (NCCL): gradients are summed in buckets on a side stream,
+        overlapped with the rest of the backward; clip + Adam run on the average."""
+        from .parallel import GradReducer
+        self.build()
+        self._reducer = GradReducer(process_group, bucket_mb)
+        self._reducer.broadcast_params([self.G.net.store.flat, self.D.net.store.flat, self.SpecSeg.net.store.flat])
+        return self

@@ -230,6 +230,13 @@ def cast_into(src, dst):
     return dst
 
 
+def axpy(alpha, x, y):
+    """y += alpha * x (dense tensors of one dtype)."""
+    assert x.is_contiguous() and y.is_contiguous() and x.dtype == y.dtype and x.numel() == y.numel()
+    call("shm_axpy", float(alpha), _p(x), _p(y), x.numel(), dt(x), _stream())
+    return y
+
+
 def rng_normal(shape, seed, offset, sigma, dtype):
     out = new(shape, dtype)
     call("shm_rng_normal", _p(out), out.numel(), seed, offset, float(sigma), dt(out), _stream())
@@ -272,6 +279,8 @@ def pseudo_diffuse_min4(i0, i45, i90, i135):
     """calculate_estimate_diffuse (utils.py:102-106).  fp32 / bf16 / uint8."""
     code = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}[i0.dtype]
     out = torch.empty_like(i0)
+    if i0.numel() == 0:                      # empty input -> empty output (numpy semantics of the reference), no launch
+        return out
     call("shm_pseudo_diffuse_min4", _p(i0), _p(i45), _p(i90), _p(i135), _p(out), i0.numel(), code, _stream())
     return out
 

@@ -1,0 +1,162 @@
+"""GPU parity: convolution kernels (exact-fp32 SIMT path and tcgen05 bf16 path) through the C ABI vs the CPU oracle.
+
+Tolerances (BASELINE.json north_star): 1e-3 relative in fp32 mode, 2e-2 in bf16 mode; the fp32 kernels are held to 1e-4 here.
+"""
+import pytest
+import torch
+
+import oracle as O
+from _util import F64, bf16_round, dev, oracle_conv, randn, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+def _mk_conv(cin, cout, k, stride, transposed, act, bias, w, b):
+    from shmgan_b200 import ops
+    c = ops.Conv("t", k, k, cin, cout, stride=stride, transposed=transposed, act=act, bias=bias)
+    c.w = dev(w)
+    c.b = dev(b) if bias else None
+    c.dw = torch.zeros_like(c.w)
+    c.db = torch.zeros(cout, device="cuda") if bias else None
+    return c
+
+
+# (N, H, W, Cin, Cout, k, stride, transposed, act, bias)
+SIMT_CASES = [
+    (2, 16, 16, 10, 64, 3, 1, False, 1, True),      # enc1a class
+    (2, 16, 16, 3, 64, 3, 2, False, 1, False),      # d1 class: TF SAME pad (0, 1)
+    (1, 12, 20, 64, 1, 1, 1, False, 1, True),       # generator output 1x1 -> 1 channel
+    (2, 8, 8, 32, 16, 3, 2, True, 1, True),         # Conv2DTranspose k3 s2 (generator up path)
+    (2, 8, 8, 32, 16, 2, 2, True, 0, True),         # Conv2DTranspose k2 s2 (SpecSeg)
+    (1, 9, 7, 5, 7, 3, 1, False, 2, True),          # ragged / odd sizes
+    (2, 7, 9, 4, 6, 3, 2, False, 0, True),          # odd input, stride 2: pad (1, 1)
+    (1, 8, 8, 256, 1, 3, 1, False, 1, False),       # discriminator real/fake head class
+    (2, 16, 16, 64, 128, 3, 1, False, 1, True),
+    (1, 4, 4, 1, 32, 3, 1, False, 1, True),         # attention first conv: single input channel
+    (1, 16, 16, 16, 1, 1, 1, False, 3, True),       # SpecSeg sigmoid head
+]
+
+
+@pytest.mark.parametrize("case", SIMT_CASES)
+def test_conv_fp32_fwd_dgrad_wgrad(case):
+    N, H, W, Cin, Cout, k, s, tr, act, bias = case
+    x = randn((N, H, W, Cin), 1)
+    wshape = (k, k, Cout, Cin) if tr else (k, k, Cin, Cout)
+    w = randn(wshape, 2, 0.1)
+    b = randn((Cout,), 3, 0.1)
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    pre = oracle_conv(xr, wr, br if bias else None, s, tr, 0)
+    want = oracle_conv(x, w, b if bias else None, s, tr, act)
+    dy = randn(tuple(pre.shape), 4)
+    grads = torch.autograd.grad((pre * dy).sum(), [xr, wr] + ([br] if bias else []))
+
+    c = _mk_conv(Cin, Cout, k, s, tr, act, bias, w, b)
+    xd = dev(x)
+    y = c.fwd(xd, tc=False)
+    assert rel_err(y, want) < FP32_TOL
+    dyd = dev(dy)
+    dx = c.dgrad(dyd, xd.shape, tc=False)
+    assert rel_err(dx, grads[0]) < FP32_TOL
+    # wgrad accumulates on top of what is already there
+    c.dw.fill_(0.5)
+    c.wgrad(xd, dyd, tc=False)
+    assert rel_err(c.dw - 0.5, grads[1]) < FP32_TOL
+    if bias:
+        assert rel_err(c.db, grads[2]) < FP32_TOL
+
+
+def test_conv_fp32_channel_slices():
+    """x read from and y written into channel slices of wider NHWC buffers (concat never materialised)."""
+    N, H, W, Cin, Cout = 2, 8, 8, 16, 32
+    x, w, b = randn((N, H, W, Cin), 5), randn((3, 3, Cin, Cout), 6, 0.1), randn((Cout,), 7, 0.1)
+    want = oracle_conv(x, w, b, 1, False, 1)
+    c = _mk_conv(Cin, Cout, 3, 1, False, 1, True, w, b)
+    xbuf = torch.full((N, H, W, 2 * Cin), 7.0, device="cuda")
+    xbuf[..., Cin:] = dev(x)
+    ybuf = torch.full((N, H, W, 3 * Cout), -3.0, device="cuda")
+    c.fwd(xbuf[..., Cin:], ybuf[..., Cout:2 * Cout], tc=False)
+    torch.cuda.synchronize()
+    assert rel_err(ybuf[..., Cout:2 * Cout], want) < FP32_TOL
+    assert float((ybuf[..., :Cout] + 3.0).abs().max()) == 0.0 and float((ybuf[..., 2 * Cout:] + 3.0).abs().max()) == 0.0
+
+
+def test_conv_transpose_impulse_alignment():
+    """Conv2DTranspose(k3, s2, SAME): out[2i+k] += x[i] w[k], cropped at the END."""
+    x = torch.zeros(1, 4, 4, 1, dtype=F64)
+    x[0, 1, 2, 0] = 1.0
+    w = torch.arange(1, 10, dtype=F64).reshape(3, 3, 1, 1)
+    c = _mk_conv(1, 1, 3, 2, True, 0, False, w, None)
+    y = c.fwd(dev(x), tc=False).cpu()[0, :, :, 0]
+    want = torch.zeros(8, 8)
+    want[2:5, 4:7] = w[:, :, 0, 0].float()
+    assert torch.equal(y, want)
+
+
+def test_conv_bad_args_fail_loudly():
+    from shmgan_b200 import _lib as L
+    import ctypes as C
+    d = L.ConvDesc(1, 8, 8, 4, 4, 5, 5, 1, 0, 0, 4, 4, 0, 0)      # 5x5 kernel: unsupported
+    with pytest.raises(L.ShmError):
+        L.call("shm_conv2d_fwd", C.byref(d), None, None, None, None, None)
+
+
+# ---- tcgen05 path --------------------------------------------------------------------------------
+# (N, H, W, Cin, Cout, k, stride, transposed, act, bias)
+TC_CASES = [
+    (2, 16, 16, 64, 64, 3, 1, False, 1, True),      # box 16x8x1
+    (2, 8, 8, 128, 128, 3, 1, False, 1, True),      # box 8x8x2 (two images per tile)
+    (8, 4, 4, 64, 128, 3, 1, False, 1, True),       # box 4x4x8
+    (1, 16, 16, 512, 512, 1, 1, False, 1, True),    # bottleneck 1x1
+    (2, 32, 32, 64, 128, 3, 2, False, 1, False),    # discriminator block, stride 2
+    (2, 8, 8, 128, 64, 3, 2, True, 1, True),        # Conv2DTranspose up path
+    (1, 4, 128, 64, 64, 3, 1, False, 1, True),      # box 128x1
+    (1, 2, 256, 64, 64, 3, 1, False, 0, True),      # two tiles per row
+    (2, 16, 16, 128, 64, 3, 1, False, 1, True),     # dec-a class (Cin = 2 * Cout)
+    (1, 16, 16, 256, 256, 3, 1, False, 2, True),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tc_fwd_dgrad_wgrad(case):
+    from shmgan_b200 import ops
+    import ctypes as C
+    N, H, W, Cin, Cout, k, s, tr, act, bias = case
+    x = bf16_round(randn((N, H, W, Cin), 11))
+    wshape = (k, k, Cout, Cin) if tr else (k, k, Cin, Cout)
+    w = bf16_round(randn(wshape, 12, 0.05))
+    b = randn((Cout,), 13, 0.1).float().to(F64)
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    pre = oracle_conv(xr, wr, b if bias else None, s, tr, 0)
+    want = oracle_conv(x, w, b if bias else None, s, tr, act)
+    dy = bf16_round(randn(tuple(pre.shape), 14))
+    gx, gw = torch.autograd.grad((pre * dy).sum(), [xr, wr])
+
+    c = _mk_conv(Cin, Cout, k, s, tr, act, bias, w, b)
+    xd = dev(x, torch.bfloat16)
+    d = c.desc(N, H, W, Cin, Cout, ops.BF16)
+    assert c.tc_ok(d), "case must be servable by the tensor-core path"
+    y = c.fwd(xd, tc=True, version=1)
+    assert y.dtype == torch.bfloat16
+    assert rel_err(y, want) < BF16_TOL
+    dyd = dev(dy, torch.bfloat16)
+    dx = c.dgrad(dyd, xd.shape, tc=True, version=1)
+    assert rel_err(dx, gx) < BF16_TOL
+    c.wgrad(xd, dyd, tc=True)
+    assert rel_err(c.dw, gw) < BF16_TOL
+
+
+def test_conv_tc_matches_simt_bf16_inputs():
+    """Same bf16 inputs through both kernel families: the tcgen05 result differs from the fp32-accumulating SIMT kernel only
+    by the bf16 output rounding."""
+    N, H, W, Cin, Cout = 2, 16, 16, 64, 64
+    x = bf16_round(randn((N, H, W, Cin), 21))
+    w = bf16_round(randn((3, 3, Cin, Cout), 22, 0.05))
+    b = randn((Cout,), 23, 0.1)
+    c = _mk_conv(Cin, Cout, 3, 1, False, 1, True, w, b)
+    xd = dev(x, torch.bfloat16)
+    y_tc = c.fwd(xd, tc=True, version=1).float()
+    y_simt = c.fwd(xd, tc=False).float()
+    assert rel_err(y_tc, y_simt) < 1e-2

@@ -1,0 +1,278 @@
+"""GPU parity: bandwidth / reduction kernels (instance norm, pooling, preprocessing, losses, Adam) vs the CPU oracle."""
+import math
+
+import pytest
+import torch
+
+import oracle as O
+from _util import F64, bf16_round, dev, rand, randn, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+# ---- instance norm ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (1, 8, 12, 8), (3, 4, 4, 512), (2, 32, 32, 16)])
+def test_inorm_fwd_pool_add(shape):
+    from shmgan_b200 import ops
+    N, H, W, C = shape
+    x = randn(shape, 1) * 2 + 0.5
+    gamma, beta = 1 + 0.1 * randn((C,), 2), 0.02 * randn((C,), 3)
+    add = randn((1, H, W, C), 4)
+    want = O.instance_norm(x, gamma, beta)
+    xd = dev(x)
+    sums = ops.inorm_stats(xd)
+    ref_s = torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1)
+    assert rel_err(sums, ref_s) < 1e-6
+    y, _ = ops.inorm_apply(xd, sums, dev(gamma), dev(beta))
+    assert rel_err(y, want) < TOL
+    # fused: + broadcast add, written into the upper half of a concat buffer, + AvgPool2 of the un-added value
+    cat = torch.zeros((N, H, W, 2 * C), device="cuda")
+    _, pooled = ops.inorm_apply(xd, sums, dev(gamma), dev(beta), add=dev(add), out=cat[..., C:], pooled=True)
+    assert rel_err(cat[..., C:], want + add) < TOL
+    assert rel_err(pooled, O.avg_pool2(want)) < TOL
+    assert float(cat[..., :C].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("act", [1, 0])
+def test_inorm_bwd(act):
+    from shmgan_b200 import ops
+    N, H, W, C = 2, 8, 8, 16
+    pre = randn((N, H, W, C), 5).requires_grad_()
+    gamma, beta = 1 + 0.1 * randn((C,), 6), 0.02 * randn((C,), 7)
+    z = O.leaky_relu(pre) if act == 1 else pre
+    y = O.instance_norm(z, gamma, beta)
+    dyA, dyP = randn((N, H, W, C), 8), randn((N, H // 2, W // 2, C), 9)
+    loss = (y * dyA).sum() + (O.avg_pool2(y) * dyP).sum()
+    want, = torch.autograd.grad(loss, pre)
+    zd = dev(z)
+    sums = ops.inorm_stats(zd)
+    got = ops.inorm_bwd(zd, sums, dev(gamma), dev(dyA), dev(dyP), act=act)
+    assert rel_err(got, want) < TOL
+    want_a, = torch.autograd.grad((O.instance_norm(O.leaky_relu(pre) if act == 1 else pre, gamma, beta) * dyA).sum(), pre)
+    assert rel_err(ops.inorm_bwd(zd, sums, dev(gamma), dev(dyA), None, act=act), want_a) < TOL
+
+
+def test_bn_eval_maxpool_actbwd_groupsum():
+    from shmgan_b200 import ops
+    N, H, W, C = 2, 8, 8, 16
+    x = randn((N, H, W, C), 10)
+    g, b, m, v = 1 + 0.2 * rand((C,), 11), randn((C,), 12, 0.1), randn((C,), 13, 0.1), 0.5 + rand((C,), 14)
+    want = (x - m) * torch.rsqrt(v + O.BN_EPS) * g + b
+    cat = torch.zeros((N, H, W, 2 * C), device="cuda")
+    _, pooled = ops.bn_eval(dev(x), dev(g), dev(b), dev(m), dev(v), out=cat[..., C:], pooled=True)
+    assert rel_err(cat[..., C:], want) < TOL
+    assert rel_err(pooled, O.max_pool(want, 2)) < TOL
+    mask = rand((N, 32, 32, 1), 15)
+    assert torch.equal(ops.maxpool(dev(mask), 16).cpu(), O.max_pool(mask.float(), 16))
+    assert torch.equal(ops.maxpool(dev(mask), 2).cpu(), O.max_pool(mask.float(), 2))
+    y = randn((N, H, W, C), 16)
+    dy = randn((N, H, W, C), 17)
+    assert rel_err(ops.act_bwd(dev(dy), dev(y), 1), dy * torch.where(y > 0, 1.0, 0.2)) < 1e-6
+    assert rel_err(ops.act_bwd(dev(dy), dev(y), 2), dy * (y > 0)) < 1e-6
+    src = randn((6, 4, 4, 8), 18)
+    dst = torch.ones((2, 4, 4, 8), device="cuda")
+    ops.group_sum(dev(src), 2, dst, accumulate=True)
+    assert rel_err(dst, 1 + src.reshape(3, 2, 4, 4, 8).sum(0)) < 1e-6
+    a, bb = randn((2, 4, 4, 3), 19), randn((2, 4, 4, 3), 20)
+    assert rel_err(ops.add(dev(a), dev(bb)), a + bb) < 1e-6
+
+
+def test_dense_head():
+    from shmgan_b200 import ops
+    B, K, J = 3, 4 * 4 * 64, 5
+    x, w, dout = randn((B, 4, 4, 64), 21), randn((K, J), 22, 0.02), randn((B, J), 23)
+    want = x.reshape(B, -1) @ w
+    assert rel_err(ops.dense_fwd(dev(x), dev(w)), want) < TOL
+    assert rel_err(ops.dense_dgrad(dev(dout), dev(w), dev(x)), (dout @ w.T).reshape(x.shape)) < TOL
+    dw = torch.full((K, J), 0.25, device="cuda")
+    ops.dense_wgrad(dev(x), dev(dout), dw)
+    assert rel_err(dw - 0.25, x.reshape(B, -1).T @ dout) < TOL
+
+
+# ---- polarimetric preprocessing ---------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [torch.uint8, torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [0, 1, 5, 4 * 37 * 53 * 3, 2 * 256 * 256 * 3])
+def test_pseudo_diffuse_min4_bit_exact(dtype, n):
+    """calculate_estimate_diffuse (utils.py:102-106): bit-exact in every dtype, ragged and empty sizes included."""
+    from shmgan_b200 import ops
+    g = torch.Generator().manual_seed(n + 1)
+    if dtype == torch.uint8:
+        imgs = [torch.randint(0, 256, (n,), generator=g, dtype=torch.uint8) for _ in range(4)]
+    else:
+        imgs = [torch.rand((n,), generator=g).to(dtype) for _ in range(4)]
+    want = O.pseudo_diffuse_min4(*imgs)
+    got = ops.pseudo_diffuse_min4(*[t.cuda() for t in imgs])
+    assert torch.equal(got.cpu(), want)
+
+
+def test_pseudo_diffuse_properties_full_size():
+    """Size-independent properties at cfg2 size (16 x 256 x 256 x 3): idempotence, permutation invariance, lower bound."""
+    from shmgan_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(0)
+    imgs = [torch.rand((16, 256, 256, 3), generator=g, device="cuda") for _ in range(4)]
+    ed = ops.pseudo_diffuse_min4(*imgs)
+    assert torch.equal(ops.pseudo_diffuse_min4(ed, ed, ed, ed), ed)
+    assert torch.equal(ops.pseudo_diffuse_min4(imgs[3], imgs[1], imgs[0], imgs[2]), ed)
+    for t in imgs:
+        assert bool((ed <= t).all())
+    assert torch.equal(ops.pseudo_diffuse_min4(ed, imgs[0], imgs[1], imgs[2]), ed)
+
+
+def test_yuv_standardize_avgcbcr_assemble_yuv2rgb():
+    from shmgan_b200 import ops
+    N, S = 3, 16
+    rgbs = [rand((N, S, S, 3), 30 + i) for i in range(5)]
+    ds = [O.per_image_standardization(O.rgb_to_yuv(r), True) for r in rgbs]
+    dd = []
+    for r, (want, scale) in zip(rgbs, ds):
+        yuv, sc = ops.yuv_standardize(dev(r))
+        assert rel_err(yuv, want) < TOL
+        assert rel_err(sc, scale.reshape(N)) < TOL
+        dd.append(yuv)
+    # constant image: std = 0 -> divisor clamps at 1/256 (ShmGANwithSSpecSeg.py:1299)
+    const = torch.zeros((1, S, S, 3), dtype=F64)
+    yuv, sc = ops.yuv_standardize(dev(const))
+    assert float(sc[0]) == pytest.approx(1.0 / 256.0) and float(yuv.abs().max()) == 0.0
+    avg = ops.avg_cbcr(dd)
+    want_avg = sum(d[0][..., 1:] for d in ds) / 5.0
+    assert rel_err(avg, want_avg) < TOL
+    # G1 input assembly (:509-531) with drop bits (1,0,1,0,0)
+    bits = [True, False, True, False, False]
+    Y = [d[0][..., 0:1] for d in ds]
+    want_in = O.assemble_g1_input(Y, bits)
+    out = torch.empty((N, S, S, 10), device="cuda")
+    ops.assemble_input([None if bits[k] else dd[k] for k in range(5)], [3] * 5, 4, out)
+    assert rel_err(out, want_in) < TOL
+    # cyclic inputs (:576-594)
+    genY = randn((N, S, S, 1), 40)
+    gd = dev(genY)
+    for k, want_c in enumerate(O.assemble_cyclic_inputs(Y, genY, bits)):
+        srcs, lds = [], []
+        for j in range(5):
+            if j == k:
+                srcs.append(None); lds.append(0)
+            elif bits[j]:
+                srcs.append(gd); lds.append(1)
+            else:
+                srcs.append(dd[j]); lds.append(3)
+        outb = torch.empty((N, S, S, 10), device="cuda", dtype=torch.bfloat16)
+        ops.assemble_input(srcs, lds, k, outb)
+        assert rel_err(outb, want_c) < 1e-2
+        ops.assemble_input(srcs, lds, k, out)
+        assert rel_err(out, want_c) < TOL
+    # yuv -> rgb with a batch-broadcast CbCr, and its backward
+    cb = want_avg
+    Yb = randn((2 * N, S, S, 1), 41)
+    want_rgb = O.yuv_to_rgb(torch.cat([Yb, cb.repeat(2, 1, 1, 1)], dim=3))
+    rgb = torch.empty((2 * N, S, S, 3), device="cuda")
+    lp = torch.empty((2 * N, S, S, 3), device="cuda", dtype=torch.bfloat16)
+    ops.yuv2rgb(dev(Yb), dev(cb), rgb, lp)
+    assert rel_err(rgb, want_rgb) < TOL and rel_err(lp, want_rgb) < 1e-2
+    drgb = randn((2 * N, S, S, 3), 42)
+    dY = torch.ones((2 * N, S, S, 1), device="cuda")
+    ops.yuv2rgb_bwd(dev(drgb), None, dY, accumulate=True)
+    assert rel_err(dY, 1 + drgb.sum(dim=3, keepdim=True)) < TOL
+    dgen = torch.zeros((N, S, S, 1), device="cuda")
+    din = randn((N, S, S, 10), 43)
+    ops.assemble_bwd(dev(din), [0, 2], dgen)
+    assert rel_err(dgen, din[..., 0:1] + din[..., 2:3]) < TOL
+
+
+# ---- losses -----------------------------------------------------------------------------------------
+def _slot():
+    return torch.zeros(1, device="cuda")
+
+
+def test_elementwise_losses_and_ce():
+    from shmgan_b200 import losses as LS, ops
+    import ctypes as C
+    a = randn((3, 8, 8, 1), 50).requires_grad_()
+    want = ((a - 0.9) ** 2).mean()
+    g, = torch.autograd.grad(want * 0.7, a)
+    s, ad = _slot(), dev(a)
+    da = torch.ones_like(ad)
+    LS.lsgan(ad, 0.9, C.c_void_p(s.data_ptr()), 2.0, da, 0.7, accumulate=True)
+    assert float(s) == pytest.approx(2.0 * float(want), rel=1e-5)
+    assert rel_err(da, 1 + g) < TOL
+    b = randn((3, 8, 8, 1), 51)
+    want = (a - b).abs().mean()
+    g, = torch.autograd.grad(want, a)
+    s = _slot()
+    LS.l1(ad, dev(b), C.c_void_p(s.data_ptr()), 1.0, da, 1.0, accumulate=False)
+    assert float(s) == pytest.approx(float(want), rel=1e-5) and rel_err(da, g) < TOL
+    logits = randn((4, 5), 52).requires_grad_()
+    lab = torch.tensor([[0, 0, 0, 0, 0.9]], dtype=F64)
+    want = O.softmax_ce(lab, logits).mean()
+    g, = torch.autograd.grad(want * 3.0, logits)
+    s = _slot()
+    dl = torch.zeros((4, 5), device="cuda")
+    LS.softmax_ce(dev(logits), lab[0].tolist(), C.c_void_p(s.data_ptr()), 1.0, dl, 3.0)
+    assert float(s) == pytest.approx(float(want), rel=1e-5) and rel_err(dl, g) < TOL
+
+
+def test_content_style_ssim_spec_losses():
+    from shmgan_b200 import losses as LS
+    import ctypes as C
+    N, S = 2, 32
+    Y = (randn((N, S, S, 1), 60) * 0.5 + 1.0).requires_grad_()
+    cbcr = randn((N, S, S, 2), 61) * 0.3
+    ref = randn((N, S, S, 3), 62) * 0.5 + 0.5
+    mask = rand((N, S, S, 1), 63)
+    img = torch.cat([Y, cbcr], dim=3)
+    Yd, cd, rd = dev(Y), dev(cbcr), dev(ref)
+
+    want = ((img - ref) ** 2).mean()
+    g, = torch.autograd.grad(want * 10.0, Y, retain_graph=True)
+    s, dY = _slot(), torch.zeros((N, S, S, 1), device="cuda")
+    LS.mse_ycc(Yd, cd, rd, C.c_void_p(s.data_ptr()), 1.0, dY, 10.0)
+    assert float(s) == pytest.approx(float(want), rel=1e-5) and rel_err(dY, g) < TOL
+
+    factor = 1.0 / float(2 * 9 * S * S) ** 2
+    want = factor * ((O.gram_matrix(img) - O.gram_matrix(ref)) ** 2).mean()
+    g, = torch.autograd.grad(want * 1000.0, Y, retain_graph=True)
+    s, dY = _slot(), torch.zeros((N, S, S, 1), device="cuda")
+    LS.style(Yd, cd, rd, S, C.c_void_p(s.data_ptr()), 1.0, dY, 1000.0)
+    assert float(s) == pytest.approx(float(want), rel=1e-4) and rel_err(dY, g) < 1e-3
+
+    ss = O.ssim(O.rescale_01(img, True), O.rescale_01(ref, True), 5.0)
+    want = (-torch.log((1.0 + ss) / 2.0)).mean()
+    g, = torch.autograd.grad(want * 2.0, Y, retain_graph=True)
+    s, dY = _slot(), torch.zeros((N, S, S, 1), device="cuda")
+    got_ss = LS.ssim_term(Yd, cd, rd, C.c_void_p(s.data_ptr()), 1.0, dY, 2.0)
+    assert rel_err(got_ss, ss) < 1e-4
+    assert float(s) == pytest.approx(float(want), rel=1e-4)
+    assert rel_err(dY, g) < 2e-3
+
+    want = (((img * mask) - (ref * mask)) ** 2).mean()
+    s = _slot()
+    LS.spec(Yd, cd, rd, dev(mask), C.c_void_p(s.data_ptr()), 1.0)
+    assert float(s) == pytest.approx(float(want), rel=1e-5)
+
+
+def test_clip_adam_matches_keras_update():
+    from shmgan_b200 import _lib as L
+    import ctypes as C
+    n = 1003
+    p = {"w": randn((n,), 70)}
+    g = {"w": randn((n,), 71) * 2.0}            # some |g| > 1 so the clip is exercised
+    m = {"w": torch.zeros(n, dtype=F64)}
+    v = {"w": torch.zeros(n, dtype=F64)}
+    pd, md, vd = dev(p["w"]), dev(m["w"]), dev(v["w"])
+    for step in range(3):
+        gc = {"w": g["w"].clamp(-1, 1)}
+        p, m, v = O.keras_adam_update(p, gc, m, v, step, 2e-5, 0.5, 0.99, 1e-7)
+        t = step + 1
+        lr_t = O.keras_adam_lr(step) * math.sqrt(1 - 0.99 ** t) / (1 - 0.5 ** t)
+        L.call("shm_clip_adam", C.c_void_p(pd.data_ptr()), C.c_void_p(dev(g["w"]).data_ptr()), C.c_void_p(md.data_ptr()),
+               C.c_void_p(vd.data_ptr()), n, lr_t, 0.5, 0.99, 1e-7, 1.0, 1.0, torch.cuda.current_stream().cuda_stream)
+    assert rel_err(pd, p["w"]) < 1e-6 and rel_err(md, m["w"]) < 1e-5 and rel_err(vd, v["w"]) < 1e-5
+
+
+def test_rng_moments():
+    from shmgan_b200 import ops
+    x = ops.rng_normal((1 << 20,), 7, 0, 0.1, torch.float32)
+    assert abs(float(x.mean())) < 1e-3 and float(x.std()) == pytest.approx(0.1, rel=1e-2)
+    k = ops.rng_keep((1 << 20,), 7, 1 << 20, 0.8, torch.float32)
+    assert float(k.mean()) == pytest.approx(0.8, abs=2e-3)
+    assert torch.equal(ops.rng_normal((1000,), 7, 0, 0.1, torch.float32), x[:1000])
