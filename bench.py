@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json: train images/sec of one full G+D step at 256 x 256.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (libshmgan kernels on B200s)
+  python bench.py --impl reference --gpus N ...            the CPU arm: the oracle port of the reference's step on host cores
+
+One "image" = one polarimetric sample = the 5-tuple (I0, I45, I90, I135, ED) consumed by one train_step slot
+(6 generator passes, 12 discriminator passes, 1 SpecSeg pass, both backward sweeps, clip + Adam).
+A "step" = one train_step call on a batch of `--batch` samples per GPU (weak scaling: per-GPU work fixed as N grows).
+For N > 1 launch with torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train_images_per_sec_GD_step_256"
+UNIT = "images/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=16, help="samples per GPU per step")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-extras", action="store_true", help="skip the roofline / cpu_baseline / parity-mode / inference legs")
+    ap.add_argument("--ref-size", type=int, default=256, help="image side of the CPU arm's bounded sample (rate rescaled to 256 if smaller)")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p["bf16_tflops"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's train step on the host cores
+# ------------------------------------------------------------------------------------------------------------------------
+def cpu_train_step_fn(size, fs=64):
+    """Returns (fn, cores): fn() runs ONE sample (B=1) of the reference train step -- forward of all 6 G / 12 D / 1 SpecSeg
+    passes, both gradient sweeps, clip + Keras Adam -- in float32 with every host thread torch can use."""
+    import torch
+    import oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    f = torch.float32
+    Gp = O.init_params(O.generator_param_specs(fs, True), 42, f)
+    Dp = O.init_params(O.discriminator_param_specs(size, fs, True), 43, f)
+    Sp = O.init_params(O.specseg_param_specs(), 44, f)
+    g = torch.Generator().manual_seed(0)
+    pol = [torch.rand((1, size, size, 3), generator=g) for _ in range(4)]
+    origs = pol + [O.pseudo_diffuse_min4(*pol)]
+    state = {"G": Gp, "D": Dp, "step": 0,
+             "mG": {k: torch.zeros_like(v) for k, v in Gp.items()}, "vG": {k: torch.zeros_like(v) for k, v in Gp.items()},
+             "mD": {k: torch.zeros_like(v) for k, v in Dp.items()}, "vD": {k: torch.zeros_like(v) for k, v in Dp.items()}}
+
+    def fn():
+        with torch.no_grad():
+            Y90 = O.per_image_standardization(O.rgb_to_yuv(origs[2]), True)[0][..., 0:1]
+            mask = O.specseg_forward(Sp, Y90)
+        noise = [torch.randn((1, size, size, 3), generator=g) * 0.1 for _ in range(2)]
+        keep = [(torch.rand((1, size // 32, size // 32, fs * 16), generator=g) < 0.8).float() for _ in range(2)]
+        L, gG, gD = O.train_step_grads(state["G"], state["D"], origs, mask, [True, False, True, False, False], 0.9, noise, keep)
+        with torch.no_grad():
+            for key, grads, m, v in (("D", gD, "mD", "vD"), ("G", gG, "mG", "vG")):
+                P = {k: state[key][k] for k in grads}
+                P, mm, vv = O.keras_adam_update(P, grads, {k: state[m][k] for k in grads}, {k: state[v][k] for k in grads}, state["step"])
+                state[key].update(P); state[m].update(mm); state[v].update(vv)
+        state["step"] += 1
+        return float(L["total_Generator_loss"])
+    return fn, cores
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    fn, cores = cpu_train_step_fn(a.ref_size)
+    for _ in range(min(a.warmup, 1)):                      # one warm-up sample is enough on the CPU (no clocks / caches to settle)
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        fn()
+    dt = time.perf_counter() - t0
+    val = a.steps / dt * (a.ref_size / 256.0) ** 2          # FLOPs of the fully-convolutional step scale with the pixel count
+    sample = ("%d train steps of ONE sample (B=1) at %dx%d, float32, PyTorch-CPU oracle port (TensorFlow is not installable here), "
+              "%d host threads%s" % (a.steps, a.ref_size, a.ref_size, cores,
+                                     "; reported rate = measured rate x (size/256)^2 (work scales with the pixel count)" if a.ref_size != 256 else ""))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": min(a.warmup, 1), "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "G+D train step, 4 polarimetric images + pseudo-diffuse, 256x256 (configs[1]/[2] shape), one sample per step on the CPU"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from shmgan_b200 import _lib, model as M, ops
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (our arm) needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == a.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % a.gpus
+    B, S = a.batch, a.size
+    hbm, tf_burst, tf_sus, peak_src = peaks()
+
+    net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B), dtype=a.dtype).build()
+    if world > 1:
+        net.enable_data_parallel()
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    pol = [torch.rand((B, S, S, 3), generator=g, device="cuda") for _ in range(4)]
+    dev_in = pol + [net.calculate_estimate_diffuse(*pol)]
+    host_in = [t.cpu().pin_memory() for t in dev_in]
+    stage = [torch.empty_like(t) for t in dev_in]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def step_resident():
+        net.train_step(*dev_in)
+
+    loss_box = [0.0]
+
+    def step_e2e():
+        for s, h in zip(stage, host_in):
+            s.copy_(h, non_blocking=True)                   # pinned host -> device, every step
+        net.train_step(*stage)
+        loss_box[0] = net.total_Generator_loss              # already read back from the device by train_step (loss table D2H)
+
+    for _ in range(max(a.warmup, 3)):
+        step_resident()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    l0 = _lib.launches()
+    ms = timed(step_resident, a.steps)
+    launches = (_lib.launches() - l0) // a.steps
+    clk = clocks.stop() if rank == 0 else None
+    value = world * B * a.steps / (ms * 1e-3)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, a.steps)
+    e2e = {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT,
+           "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_in), "d2h_bytes_per_step": net.table.buf.numel() * 4}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if a.dtype == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "G+D train step (6 G + 12 D + 1 SpecSeg passes, both backward sweeps, clip+Adam), 4 polarimetric "
+                                   "images + pseudo-diffuse, batch %d per GPU at %dx%d, %s mode, live mask; configs[1] shape%s"
+                                   % (B, S, S, "bf16 tcgen05" if a.dtype == "bf16" else "fp32 parity",
+                                      "" if world == 1 else "; configs[2] data-parallel, global batch %d" % (B * world)),
+                       "batch_per_gpu": B, "global_batch": B * world, "image_size": S, "parallelism": "dp%d" % world,
+                       "l2": "inputs+activations of one step >> 126 MB L2 (no flush needed)"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "peaks": peak_src}
+
+    if rank == 0 and not a.no_extras:
+        # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions), CUDA events per launch
+        ops.PROF = []
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize()
+        rows = [(fam, kind, name, fl, nb, e0.elapsed_time(e1)) for fam, kind, name, fl, nb, e0, e1 in ops.PROF]
+        ops.PROF = None
+        tot_ms = sum(r[5] for r in rows) / 2
+        fam = {}
+        for f, kind, name, fl, nb, t in rows:
+            k = (f, kind)
+            c = fam.setdefault(k, [0, 0.0, 0.0, 0])
+            c[0] += fl; c[1] += t; c[2] += nb; c[3] += 1
+        tc_fl = sum(v[0] for k, v in fam.items() if k[0] == "tc") / 2
+        tc_ms = sum(v[1] for k, v in fam.items() if k[0] == "tc") / 2
+        tc_n = sum(v[3] for k, v in fam.items() if k[0] == "tc") // 2
+        if tc_ms > 0:
+            ach = tc_fl / (tc_ms * 1e-3) / 1e12
+            line["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel / wgrad_tc_kernel (tcgen05 implicit-GEMM conv fwd+dgrad+wgrad)",
+                                "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
+                                "launches_per_step": tc_n, "ms_per_step_in_kernel": tc_ms, "share_of_step": tc_ms / (ms / a.steps),
+                                "peak_kind": "bf16_tflops_sustained (%s)" % peak_src}
+        line["kernel_families"] = {"%s_%s" % k: {"ms_per_step": v[1] / 2, "tflops": (v[0] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None,
+                                                  "gbs_algorithmic": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else None,
+                                                  "launches": v[3] // 2} for k, v in sorted(fam.items())}
+        line["conv_ms_per_step"] = tot_ms
+        try:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            per = {}
+            for f, kind, name, fl, nb, t in rows:
+                c = per.setdefault("%s/%s/%s" % (f, kind, name), [0, 0.0, 0])
+                c[0] += fl; c[1] += t; c[2] += 1
+            with open(os.path.join(ROOT, "gpurun_out", "bench_conv_layers.json"), "w") as fh:
+                json.dump({k: {"launches_per_step": v[2] // 2, "ms_per_step": v[1] / 2, "tflops": v[0] / (v[1] * 1e-3) / 1e12 if v[1] > 0 else None}
+                           for k, v in sorted(per.items(), key=lambda kv: -kv[1][1])}, fh, indent=1)
+        except OSError:
+            pass
+
+        # ---- HBM-bound leg: the pseudo-diffuse min-of-4 kernel at the step's size (4 reads + 1 write)
+        n_bytes = 5 * dev_in[0].numel() * 4
+        big = [torch.rand((64, S, S, 3), device="cuda") for _ in range(4)]
+        for _ in range(3):
+            ops.pseudo_diffuse_min4(*big)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(20):
+            ops.pseudo_diffuse_min4(*big)
+        e1.record()
+        torch.cuda.synchronize()
+        pd_bytes = 5 * big[0].numel() * 4
+        gbs = pd_bytes * 20 / (e0.elapsed_time(e1) * 1e-3) / 1e9
+        line["roofline_hbm"] = {"bound": "hbm", "kernel": "min4_f32_kernel (pseudo-diffuse, 64x%dx%dx3 fp32 x 4 in + 1 out = %.0f MB > L2)" % (S, S, pd_bytes / 1e6),
+                                "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None}
+        del big
+
+        # ---- configs[1] literally: the fp32 parity mode on the same batch (2 steps)
+        if a.dtype == "bf16":
+            del net
+            torch.cuda.empty_cache()
+            net32 = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B), dtype="fp32").build()
+            net32.train_step(*dev_in)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                net32.train_step(*dev_in)
+            torch.cuda.synchronize()
+            line["parity_mode_fp32"] = {"value": 2 * B / (time.perf_counter() - t0), "unit": UNIT, "steps": 2,
+                                        "note": "configs[1]: exact-fp32 SIMT kernels, same batch"}
+            del net32
+            torch.cuda.empty_cache()
+
+        # ---- CPU baseline beside it: one sample of the same step through the oracle port on the host cores
+        fn, cores = cpu_train_step_fn(S)
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "1 train step of ONE sample (B=1) at %dx%d, float32, PyTorch-CPU oracle port of the reference step "
+                                          "(TensorFlow not installable), %d host threads, %.1f s" % (S, S, cores, dt)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

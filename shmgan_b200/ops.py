@@ -14,6 +14,21 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, BF16, F32, ConvDes
 IN_EPS = 1e-6       # ShmGANwithSSpecSeg.py:245
 BN_EPS = 1e-3       # Keras BatchNormalization default (SpecSeg.py:37)
 
+# When set to a list, every convolution launch is bracketed by CUDA events on the launching stream and appended as
+# (family, pass, layer, flops, bytes, ev0, ev1); bench.py uses it for the per-kernel roofline (never on in the timed value).
+PROF = None
+
+
+def _prof(family, kind, name, flops, nbytes, fn):
+    if PROF is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    PROF.append((family, kind, name, flops, nbytes, e0, e1))
+    return r
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -104,12 +119,25 @@ class Conv:
         if y is None:
             y = new((n, ho, wo, self.cout), x.dtype)
         d = self.desc(n, h, w, ld(x), ld(y), dt(x))
+        fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, x.element_size())
         if tc and self.tc_ok(d):
             self.refresh_tc(version)
-            call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b), _p(y), _stream())
+            _prof("tc", "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b), _p(y), _stream()))
         else:
-            call("shm_conv2d_fwd", C.byref(d), _p(x), _p(self.w), _p(self.b), _p(y), _stream())
+            _prof("simt", "fwd", self.name, fl, nb, lambda: call("shm_conv2d_fwd", C.byref(d), _p(x), _p(self.w), _p(self.b), _p(y), _stream()))
         return y
+
+    def flops(self, n, h, w):
+        """Algorithmic FLOPs (2 x MACs) of one pass over an [n,h,w,cin] input (same count for fwd, dgrad and wgrad)."""
+        if self.transposed:
+            return 2 * n * h * w * self.cin * self.cout * self.kh * self.kw
+        ho, wo = self.out_hw(h, w)
+        return 2 * n * ho * wo * self.cin * self.cout * self.kh * self.kw
+
+    def io_bytes(self, n, h, w, esize):
+        """Algorithmic HBM bytes of one pass: read the input once, write the output once (weights are negligible)."""
+        ho, wo = self.out_hw(h, w)
+        return esize * n * (h * w * self.cin + ho * wo * self.cout)
 
     def dgrad(self, dy: torch.Tensor, x_shape, dx: Optional[torch.Tensor] = None, tc: bool = True, version: int = 0):
         """dx from dy = dL/d(pre-activation)."""
@@ -117,23 +145,25 @@ class Conv:
         if dx is None:
             dx = new((n, h, w, self.cin), dy.dtype)
         d = self.desc(n, h, w, ld(dx), ld(dy), dt(dy), ACT_NONE)
+        fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, dy.element_size())
         if tc and self.tc_ok(d):
             self.refresh_tc(version)
-            call("shm_conv2d_tc_dgrad", C.byref(d), _p(dy), _p(self.w_tc_d), _p(dx), _stream())
+            _prof("tc", "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_dgrad", C.byref(d), _p(dy), _p(self.w_tc_d), _p(dx), _stream()))
         else:
-            call("shm_conv2d_dgrad", C.byref(d), _p(dy), _p(self.w), _p(dx), 0, _stream())
+            _prof("simt", "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_dgrad", C.byref(d), _p(dy), _p(self.w), _p(dx), 0, _stream()))
         return dx
 
     def wgrad(self, x: torch.Tensor, dy: torch.Tensor, tc: bool = True):
         """dw += , db += (gradients accumulate: weights are shared by several passes)."""
         n, h, w, _ = x.shape
         d = self.desc(n, h, w, ld(x), ld(dy), dt(x), ACT_NONE)
+        fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, x.element_size())
         if tc and self.tc_ok(d):
-            call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _stream())
+            _prof("tc", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _stream()))
             if self.has_bias:
                 call("shm_colsum", _p(dy), dy.shape[0] * dy.shape[1] * dy.shape[2], self.cout, ld(dy), dt(dy), _p(self.db), _stream())
         else:
-            call("shm_conv2d_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _p(self.db) if self.has_bias else None, _stream())
+            _prof("simt", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _p(self.db) if self.has_bias else None, _stream()))
 
 
 # ------------------------------------------------------------------------------------------------
