@@ -57,7 +57,9 @@ int shm_conv2d_wgrad(const shm_conv_desc* d, const void* x, const void* dy, floa
  * optimiser step as bf16 [tap][n][k] (K-major B operand): for_dgrad = 0 -> (n,k) = (Cout,Cin); 1 -> (Cin,Cout). */
 int64_t shm_conv2d_tc_weight_elems(const shm_conv_desc* d);
 int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad);   /* 1 if the shape tiles into 128-point TMA boxes */
-int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, void* w_tc, int for_dgrad, void* stream);
+/* cin_real (0 = d->Cin): the Keras kernel holds only cin_real < d->Cin input channels; the rest of the bf16 copy is zero (the layer
+ * then reads a zero-padded 64-channel input, see shm_pad_channels64) */
+int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc, int for_dgrad, void* stream);
 int shm_conv2d_tc_fwd  (const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, void* stream);
 int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const void* w_tc_dgrad, void* dx, void* stream);
 int shm_conv2d_tc_wgrad(const shm_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);   /* dw += (fp32 atomics) */
@@ -109,6 +111,13 @@ int shm_dense_fwd  (const void* x, const float* w, float* out, int B, int K, int
 int shm_dense_dgrad(const float* dout, const float* w, void* dx, int B, int K, int J, int dtype, void* stream);
 int shm_dense_wgrad(const void* x, const float* dout, float* dw, int B, int K, int J, int dtype, void* stream); /* dw += */
 
+/* 1x1 convolution to ONE output channel (generator output ShmGANwithSSpecSeg.py:326, SpecSeg head SpecSeg.py:88) as a bandwidth kernel.
+ * bf16 activations, C in {8,16,32,64,128,256}; w [C] fp32 (the Keras (1,1,C,1) kernel), bias [1] or NULL.
+ * bwd fuses the activation derivative (from the saved post-activation y): dx (may be NULL) = dpre * w, dw += x^T dpre, dbias += sum dpre */
+int shm_pw1_fwd(const void* x, int ldx, int C, const float* w, const float* bias, int act, void* y, int64_t npix, int dtype, void* stream);
+int shm_pw1_bwd(const void* x, int ldx, int C, const float* w, const void* dy, const void* y, int act, void* dx, int lddx,
+                float* dw, float* dbias, int64_t npix, int dtype, void* stream);
+
 /* ---- polarimetric preprocessing ---- */
 /* calculate_estimate_diffuse utils.py:102-106: per-element min of four images (n elements). dtype: 0 f32, 1 bf16, 2 u8 */
 int shm_pseudo_diffuse_min4(const void* i0, const void* i45, const void* i90, const void* i135, void* out, int64_t n, int dtype, void* stream);
@@ -121,13 +130,17 @@ int shm_yuv_standardize(const float* rgb, int N, int HW, const double* sums, flo
 int shm_avg_cbcr(const float* y0, const float* y1, const float* y2, const float* y3, const float* y4, float* out, int64_t npix, void* stream);
 /* generator input assembly :509-531 / :576-594 / test.py:227-235.  For slot j: src[j] (fp32, pixel stride src_ld[j]) or NULL = zeros.
  * out [npix,10] (dtype): 5 slots then the one-hot plane `onehot`. */
-int shm_assemble_input(const float* const src[5], const int32_t src_ld[5], int onehot, void* out, int64_t npix, int dtype, void* stream);
-/* backward of the cyclic assembly: dgen[npix] += sum over listed slots of din[npix,10][slot] */
-int shm_assemble_bwd(const void* din, int dtype, const int32_t slots[5], int nslots, float* dgen, int64_t npix, void* stream);
-/* yuv_to_rgb(concat(Y, CbCr)) :544,553,613-624.  Y (dtypeY, ld 1), cbcr fp32 [npix,2]; rgb out fp32 and optional copy (dtype_out) for D */
-int shm_yuv2rgb(const float* Y, const float* cbcr, int64_t npix_cbcr /* cbcr index = pixel %% npix_cbcr */, float* rgb, void* rgb_lp, int dtype_lp, int64_t npix, void* stream);
+int shm_assemble_input(const float* const src[5], const int32_t src_ld[5], int onehot, void* out, int ldo /* >= 10; channels 10..ldo-1 are zero-filled */, int64_t npix, int dtype, void* stream);
+/* dst (bf16, pixel stride 64) = src channels 0..C-1 (C <= 64) followed by zeros: the zero-padded input that lets the first layers
+ * (Cin = 10 / 3 / 1) run on the tensor-core kernels, whose reduction dimension moves in 64-channel TMA boxes */
+int shm_pad_channels64(const void* src, int src_dtype, int lds, int C, void* dst_bf16, int64_t npix, void* stream);
+/* backward of the cyclic assembly: dgen[npix] += sum over listed slots of din[npix,ldin][slot] */
+int shm_assemble_bwd(const void* din, int dtype, int ldin, const int32_t slots[5], int nslots, float* dgen, int64_t npix, void* stream);
+/* yuv_to_rgb(concat(Y, CbCr)) :544,553,613-624.  Y fp32 (ld 1), cbcr fp32 [npix,2]; rgb out fp32 and / or a copy in dtype_lp with pixel
+ * stride ld_lp (channels 3..ld_lp-1 zero-filled) for the discriminator */
+int shm_yuv2rgb(const float* Y, const float* cbcr, int64_t npix_cbcr /* cbcr index = pixel %% npix_cbcr */, float* rgb, void* rgb_lp, int dtype_lp, int ld_lp, int64_t npix, void* stream);
 /* dY (+)= sum_c (drgb_f32 + drgb_lp)[.,c]  (d rgb / dY = (1,1,1)); either gradient source may be NULL */
-int shm_yuv2rgb_bwd(const float* drgb_f32, const void* drgb_lp, int dtype_lp, float* dY, int64_t npix, int accumulate, void* stream);
+int shm_yuv2rgb_bwd(const float* drgb_f32, const void* drgb_lp, int dtype_lp, int ld_lp, float* dY, int64_t npix, int accumulate, void* stream);
 
 /* ---- losses (ShmGANwithSSpecSeg.py:669-844).  All accumulate `weight * loss` into loss_out[0] (fp32, device) and write gradients ---- */
 /* mean((a - target)^2) over n; da (+)= gscale * 2 (a-target)/n.  :669-679, :721-728 */

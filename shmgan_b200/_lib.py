@@ -34,7 +34,7 @@ _SIG = {
     "shm_conv2d_dgrad": [_D, _P, _P, _P, _I, _P],
     "shm_conv2d_wgrad": [_D, _P, _P, _P, _P, _P],
     "shm_conv2d_tc_supported": [_D, _I],
-    "shm_conv2d_tc_prep_weights": [_D, _P, _P, _I, _P],
+    "shm_conv2d_tc_prep_weights": [_D, _P, _I, _P, _I, _P],
     "shm_conv2d_tc_fwd": [_D, _P, _P, _P, _P, _P],
     "shm_conv2d_tc_dgrad": [_D, _P, _P, _P, _P],
     "shm_conv2d_tc_wgrad": [_D, _P, _P, _P, _P],
@@ -61,10 +61,13 @@ _SIG = {
     "shm_yuv_stats": [_P, _I, _I, _P, _P],
     "shm_yuv_standardize": [_P, _I, _I, _P, _P, _P, _P],
     "shm_avg_cbcr": [_P, _P, _P, _P, _P, _P, _L, _P],
-    "shm_assemble_input": [C.POINTER(_P), C.POINTER(C.c_int32), _I, _P, _L, _I, _P],
-    "shm_assemble_bwd": [_P, _I, C.POINTER(C.c_int32), _I, _P, _L, _P],
-    "shm_yuv2rgb": [_P, _P, _L, _P, _P, _I, _L, _P],
-    "shm_yuv2rgb_bwd": [_P, _P, _I, _P, _L, _I, _P],
+    "shm_assemble_input": [C.POINTER(_P), C.POINTER(C.c_int32), _I, _P, _I, _L, _I, _P],
+    "shm_pad_channels64": [_P, _I, _I, _I, _P, _L, _P],
+    "shm_assemble_bwd": [_P, _I, _I, C.POINTER(C.c_int32), _I, _P, _L, _P],
+    "shm_yuv2rgb": [_P, _P, _L, _P, _P, _I, _I, _L, _P],
+    "shm_yuv2rgb_bwd": [_P, _P, _I, _I, _P, _L, _I, _P],
+    "shm_pw1_fwd": [_P, _I, _I, _P, _P, _I, _P, _L, _I, _P],
+    "shm_pw1_bwd": [_P, _I, _I, _P, _P, _P, _I, _P, _I, _P, _P, _L, _I, _P],
     "shm_lsgan": [_P, _L, _F, _P, _F, _P, _F, _I, _P],
     "shm_softmax_ce": [_P, _I, C.POINTER(C.c_float), _P, _F, _P, _F, _I, _P],
     "shm_l1": [_P, _P, _L, _P, _F, _P, _F, _I, _P],

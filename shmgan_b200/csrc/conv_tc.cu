@@ -519,13 +519,15 @@ bool pick_box64(int N, int Qh, int Qw, int& BW, int& BH, int& BI) {
 }
 
 // weights -> bf16 [tap][n][k]
-__global__ void prep_w_kernel(const float* __restrict__ w, bf16* __restrict__ o, int K, int Nn, long long tap_elems, int w_ks, int w_ns, long long total) {
+__global__ void prep_w_kernel(const float* __restrict__ w, bf16* __restrict__ o, int K, int Nn, int k_real, int n_real, long long tap_elems,
+                              int w_ks, int w_ns, long long total) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i % K);
         const long long t2 = i / K;
         const int n = (int)(t2 % Nn);
         const long long tap = t2 / Nn;
-        o[i] = __float2bfloat16_rn(__ldg(w + tap * tap_elems + (long long)k * w_ks + (long long)n * w_ns));
+        const float v = (k < k_real && n < n_real) ? __ldg(w + tap * tap_elems + (long long)k * w_ks + (long long)n * w_ns) : 0.f;
+        o[i] = __float2bfloat16_rn(v);
     }
 }
 
@@ -546,22 +548,26 @@ extern "C" int64_t shm_conv2d_tc_weight_elems(const shm_conv_desc* d) {
     return (int64_t)d->kh * d->kw * d->Cin * d->Cout;
 }
 
-extern "C" int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, void* w_tc, int for_dgrad, void* stream) {
+extern "C" int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc, int for_dgrad, void* stream) {
     if (int rc = tc_check(d)) return rc;
     SHM_REQUIRE(w && w_tc, "shm_conv2d_tc_prep_weights: NULL buffer");
-    // GEMM reduction dim K / output dim Nn and the strides of (k, n) inside one Keras tap slice
-    int K, Nn, w_ks, w_ns;
+    if (cin_real <= 0) cin_real = d->Cin;
+    SHM_REQUIRE(cin_real <= d->Cin, "shm_conv2d_tc_prep_weights: cin_real > Cin");
+    SHM_REQUIRE(cin_real == d->Cin || !d->transposed, "shm_conv2d_tc_prep_weights: channel padding is for Conv2D only");
+    // GEMM reduction dim K / output dim Nn and the strides of (k, n) inside one Keras tap slice (cin_real x Cout elements)
+    int K, Nn, w_ks, w_ns, k_real, n_real;
     if (!d->transposed) {          // (kh,kw,Cin,Cout)
-        if (!for_dgrad) { K = d->Cin; Nn = d->Cout; w_ks = d->Cout; w_ns = 1; }
-        else            { K = d->Cout; Nn = d->Cin; w_ks = 1; w_ns = d->Cout; }
+        if (!for_dgrad) { K = d->Cin; Nn = d->Cout; w_ks = d->Cout; w_ns = 1; k_real = cin_real; n_real = d->Cout; }
+        else            { K = d->Cout; Nn = d->Cin; w_ks = 1; w_ns = d->Cout; k_real = d->Cout; n_real = cin_real; }
     } else {                       // (kh,kw,Cout,Cin)
         if (!for_dgrad) { K = d->Cin; Nn = d->Cout; w_ks = 1; w_ns = d->Cin; }
         else            { K = d->Cout; Nn = d->Cin; w_ks = d->Cin; w_ns = 1; }
+        k_real = K; n_real = Nn;
     }
     const long long total = (long long)d->kh * d->kw * d->Cin * d->Cout;
     long long g = cdiv64(total, 256);
     if (g > shm_num_sms() * 16) g = shm_num_sms() * 16;
-    prep_w_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_tc, K, Nn, (long long)d->Cin * d->Cout, w_ks, w_ns, total);
+    prep_w_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_tc, K, Nn, k_real, n_real, (long long)cin_real * d->Cout, w_ks, w_ns, total);
     SHM_CHECK_LAUNCH("prep_w_kernel");
     return SHM_OK;
 }

@@ -98,3 +98,131 @@ extern "C" int shm_dense_wgrad(const void* x, const float* dout, float* dw, int 
         return SHM_OK;
     })
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 1x1 convolution to ONE output channel (the generator's output layer, ShmGANwithSSpecSeg.py:326, and SpecSeg's sigmoid
+// head, SpecSeg.py:88): a per-pixel dot product over C channels -- pure HBM bandwidth (C*e bytes in, e bytes out per pixel),
+// so it is served by a coalesced 128-bit-vectorised kernel with sub-warp shuffle reductions instead of a GEMM tile that
+// would waste 63/64 of its columns.  bf16 activations, C in {8,16,32,64,128,256}.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& u, float v[8]) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); v[2 * j] = f.x; v[2 * j + 1] = f.y; }
+}
+
+// TPP threads per pixel, each owning 8 consecutive channels
+template <int TPP>
+__global__ void __launch_bounds__(256) pw1_fwd_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ w,
+                                                      const float* __restrict__ bias, int act, bf16* __restrict__ y, long long npix) {
+    const int part = threadIdx.x % TPP;
+    float wv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wv[j] = __ldg(w + part * 8 + j);
+    const float b = bias ? __ldg(bias) : 0.f;
+    const long long ppb = 256 / TPP;
+    // the trip count is uniform over the block (p0), so the full-mask shuffles below are always converged
+    for (long long p0 = (long long)blockIdx.x * ppb; p0 < npix; p0 += (long long)gridDim.x * ppb) {
+        const long long p = p0 + threadIdx.x / TPP;
+        const bool ok = p < npix;
+        float s = 0.f;
+        if (ok) {
+            float v[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * ldx + part * 8)), v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(v[j], wv[j], s);
+        }
+#pragma unroll
+        for (int o = TPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (ok && part == 0) y[p] = __float2bfloat16_rn(act_fwd(s + b, act));
+    }
+}
+
+// fused backward: dpre = dy * act'(y);  dx[p, c] = dpre * w[c];  dw[c] += sum_p x[p, c] dpre;  dbias += sum_p dpre
+template <int TPP>
+__global__ void __launch_bounds__(256) pw1_bwd_kernel(const bf16* __restrict__ x, int ldx, const float* __restrict__ w,
+        const bf16* __restrict__ dy, const bf16* __restrict__ y, int act, bf16* __restrict__ dx, int lddx,
+        float* __restrict__ dw, float* __restrict__ dbias, long long npix) {
+    __shared__ float sdw[TPP * 8 + 1];
+    for (int i = threadIdx.x; i < TPP * 8 + 1; i += 256) sdw[i] = 0.f;
+    __syncthreads();
+    const int part = threadIdx.x % TPP;
+    float wv[8], acc[8], accb = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { wv[j] = __ldg(w + part * 8 + j); acc[j] = 0.f; }
+    const long long ppb = 256 / TPP;
+    for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / TPP; p < npix; p += (long long)gridDim.x * ppb) {
+        const float g = __bfloat162float(dy[p]) * act_grad_from_post(__bfloat162float(y[p]), act);
+        float v[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * ldx + part * 8)), v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], g, acc[j]);
+        if (part == 0) accb += g;
+        if (dx) {
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(g * wv[2 * j], g * wv[2 * j + 1]);
+            *reinterpret_cast<uint4*>(dx + p * lddx + part * 8) = *reinterpret_cast<uint4*>(h);
+        }
+    }
+    // lanes sharing `part` (stride TPP inside the warp) hold partials of the same channels
+#pragma unroll
+    for (int o = 16; o >= TPP; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+        accb += __shfl_xor_sync(0xffffffffu, accb, o);
+    }
+    if ((threadIdx.x & 31) < TPP) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sdw[part * 8 + j], acc[j]);
+        if (part == 0) atomicAdd(&sdw[TPP * 8], accb);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < TPP * 8; i += 256) atomicAdd(dw + i, sdw[i]);
+    if (threadIdx.x == 0 && dbias) atomicAdd(dbias, sdw[TPP * 8]);
+}
+
+inline int pw1_grid(long long npix, int tpp) {
+    long long g = cdiv64(npix, 256 / tpp);
+    const long long cap = (long long)shm_num_sms() * 8;
+    return (int)(g > cap ? cap : (g < 1 ? 1 : g));
+}
+
+inline int pw1_check(const void* x, int ldx, int C, int dtype, const char* who) {
+    if (dtype != SHM_BF16) SHM_FAIL(SHM_EUNSUPPORTED, "%s: bf16 only (fp32 mode uses shm_conv2d_*)", who);
+    if (!(C == 8 || C == 16 || C == 32 || C == 64 || C == 128 || C == 256)) SHM_FAIL(SHM_EUNSUPPORTED, "%s: C=%d not in {8,...,256}", who, C);
+    if (ldx % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) SHM_FAIL(SHM_EINVAL, "%s: x must be 16-byte aligned with ld %% 8 == 0", who);
+    return SHM_OK;
+}
+
+#define PW1_DISPATCH(C, KERNEL, ...) \
+    switch ((C) / 8) { \
+        case 1:  KERNEL<1> __VA_ARGS__; break;  case 2:  KERNEL<2> __VA_ARGS__; break; \
+        case 4:  KERNEL<4> __VA_ARGS__; break;  case 8:  KERNEL<8> __VA_ARGS__; break; \
+        case 16: KERNEL<16> __VA_ARGS__; break; default: KERNEL<32> __VA_ARGS__; break; }
+
+}  // namespace
+
+extern "C" int shm_pw1_fwd(const void* x, int ldx, int C, const float* w, const float* bias, int act, void* y, int64_t npix, int dtype, void* stream) {
+    SHM_REQUIRE(x && w && y && npix > 0, "shm_pw1_fwd: bad args");
+    if (int rc = pw1_check(x, ldx, C, dtype, "shm_pw1_fwd")) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = pw1_grid(npix, C / 8);
+    PW1_DISPATCH(C, pw1_fwd_kernel, <<<g, 256, 0, st>>>((const bf16*)x, ldx, w, bias, act, (bf16*)y, npix))
+    SHM_CHECK_LAUNCH("pw1_fwd_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_pw1_bwd(const void* x, int ldx, int C, const float* w, const void* dy, const void* y, int act, void* dx, int lddx,
+                           float* dw, float* dbias, int64_t npix, int dtype, void* stream) {
+    SHM_REQUIRE(x && w && dy && y && dw && npix > 0, "shm_pw1_bwd: bad args");
+    if (int rc = pw1_check(x, ldx, C, dtype, "shm_pw1_bwd")) return rc;
+    SHM_REQUIRE(!dx || (lddx % 8 == 0 && (reinterpret_cast<uintptr_t>(dx) & 15) == 0), "shm_pw1_bwd: dx must be 16-byte aligned with ld %% 8 == 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = pw1_grid(npix, C / 8);
+    PW1_DISPATCH(C, pw1_bwd_kernel, <<<g, 256, 0, st>>>((const bf16*)x, ldx, w, (const bf16*)dy, (const bf16*)y, act, (bf16*)dx, lddx, dw, dbias, npix))
+    SHM_CHECK_LAUNCH("pw1_bwd_kernel");
+    return SHM_OK;
+}

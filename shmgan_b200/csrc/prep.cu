@@ -150,45 +150,101 @@ __global__ void avg_cbcr_kernel(const float* __restrict__ y0, const float* __res
 struct AsmSrc { const float* p[5]; int ld[5]; };
 
 template <typename T>
-__global__ void assemble_kernel(AsmSrc s, int onehot, T* __restrict__ out, long long npix) {
+__global__ void assemble_kernel(AsmSrc s, int onehot, T* __restrict__ out, long long npix, int ldo) {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
-        T* o = out + p * 10;
+        T* o = out + p * ldo;
 #pragma unroll
         for (int j = 0; j < 5; ++j) stf(o + j, s.p[j] ? __ldg(s.p[j] + p * s.ld[j]) : 0.f);
 #pragma unroll
         for (int j = 0; j < 5; ++j) stf(o + 5 + j, j == onehot ? 1.f : 0.f);
+        for (int j = 10; j < ldo; ++j) stf(o + j, 0.f);
+    }
+}
+
+// bf16 rows of 64 channels (the zero-padded tensor-core input): 8 threads per pixel, one 16-byte store each
+__global__ void assemble64_kernel(AsmSrc s, int onehot, uint4* __restrict__ out, long long npix) {
+    const long long total = npix * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i >> 3; const int part = (int)(i & 7);
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (part < 2) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = part * 8 + j;
+                v[j] = c < 5 ? (s.p[c] ? __ldg(s.p[c] + p * s.ld[c]) : 0.f) : (c < 10 ? (c - 5 == onehot ? 1.f : 0.f) : 0.f);
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+        out[i] = u;
+    }
+}
+
+// dst[p, 0..C) = src[p, 0..C), dst[p, C..64) = 0: the zero-padded input of a tensor-core first layer
+template <typename S>
+__global__ void pad64_kernel(const S* __restrict__ src, int lds, int C, uint4* __restrict__ out, long long npix) {
+    const long long total = npix * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i >> 3; const int part = (int)(i & 7);
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (part * 8 < C) {
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = part * 8 + j < C ? ldf(src + p * lds + part * 8 + j) : 0.f;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+        out[i] = u;
     }
 }
 
 struct Slots { int s[5]; int n; };
 template <typename T>
-__global__ void assemble_bwd_kernel(const T* __restrict__ din, Slots sl, float* __restrict__ dgen, long long npix) {
+__global__ void assemble_bwd_kernel(const T* __restrict__ din, int ldin, Slots sl, float* __restrict__ dgen, long long npix) {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
         float acc = 0.f;
-        for (int j = 0; j < sl.n; ++j) acc += ldf(din + p * 10 + sl.s[j]);
+        for (int j = 0; j < sl.n; ++j) acc += ldf(din + p * ldin + sl.s[j]);
         dgen[p] += acc;
     }
 }
 
 template <typename T>
 __global__ void yuv2rgb_kernel(const float* __restrict__ Y, const float* __restrict__ cbcr, long long npix_c, float* __restrict__ rgb,
-                               T* __restrict__ rgb_lp, long long npix) {
+                               T* __restrict__ rgb_lp, int ld_lp, long long npix) {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
         const float2 uv = __ldg(reinterpret_cast<const float2*>(cbcr) + (p % npix_c));
         float r, g, b;
         yuv2rgb(__ldg(Y + p), uv.x, uv.y, r, g, b);
         if (rgb) { rgb[p * 3] = r; rgb[p * 3 + 1] = g; rgb[p * 3 + 2] = b; }
-        if (rgb_lp) { stf(rgb_lp + p * 3, r); stf(rgb_lp + p * 3 + 1, g); stf(rgb_lp + p * 3 + 2, b); }
+        if (rgb_lp) {
+            T* o = rgb_lp + p * ld_lp;
+            if (sizeof(T) == 2 && ld_lp == 64) {          // zero-padded 64-channel bf16 row: 8 x 16-byte stores
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(r, g), h1 = __floats2bfloat162_rn(b, 0.f);
+                uint4 u = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1), 0u, 0u);
+                uint4* o4 = reinterpret_cast<uint4*>(o);
+                o4[0] = u;
+#pragma unroll
+                for (int j = 1; j < 8; ++j) o4[j] = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                stf(o, r); stf(o + 1, g); stf(o + 2, b);
+                for (int j = 3; j < ld_lp; ++j) stf(o + j, 0.f);
+            }
+        }
     }
 }
 
 template <typename T>
-__global__ void yuv2rgb_bwd_kernel(const float* __restrict__ da, const T* __restrict__ db, float* __restrict__ dY, long long npix, int accumulate) {
+__global__ void yuv2rgb_bwd_kernel(const float* __restrict__ da, const T* __restrict__ db, int ldb, float* __restrict__ dY, long long npix, int accumulate) {
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
         float acc = accumulate ? dY[p] : 0.f;
         // d/dY of (r,g,b) = (1,1,1): first row of the yuv->rgb kernel
         if (da) acc += (da[p * 3] + da[p * 3 + 1]) + da[p * 3 + 2];
-        if (db) acc += (ldf(db + p * 3) + ldf(db + p * 3 + 1)) + ldf(db + p * 3 + 2);
+        if (db) acc += (ldf(db + p * ldb) + ldf(db + p * ldb + 1)) + ldf(db + p * ldb + 2);
         dY[p] = acc;
     }
 }
@@ -261,44 +317,62 @@ extern "C" int shm_avg_cbcr(const float* y0, const float* y1, const float* y2, c
     return SHM_OK;
 }
 
-extern "C" int shm_assemble_input(const float* const src[5], const int32_t src_ld[5], int onehot, void* out, int64_t npix, int dtype, void* stream) {
-    SHM_REQUIRE(src && src_ld && out && npix > 0 && onehot >= 0 && onehot < 5, "shm_assemble_input: bad args");
+extern "C" int shm_assemble_input(const float* const src[5], const int32_t src_ld[5], int onehot, void* out, int ldo, int64_t npix, int dtype, void* stream) {
+    SHM_REQUIRE(src && src_ld && out && npix > 0 && onehot >= 0 && onehot < 5 && ldo >= 10, "shm_assemble_input: bad args");
     AsmSrc s;
     for (int j = 0; j < 5; ++j) { s.p[j] = src[j]; s.ld[j] = src_ld[j]; }
+    if (dtype == SHM_BF16 && ldo == 64 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        assemble64_kernel<<<flat_grid(npix * 8), 256, 0, (cudaStream_t)stream>>>(s, onehot, (uint4*)out, npix);
+        SHM_CHECK_LAUNCH("assemble64_kernel");
+        return SHM_OK;
+    }
     DISPATCH_DTYPE(dtype, T, {
-        assemble_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(s, onehot, (T*)out, npix);
+        assemble_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(s, onehot, (T*)out, npix, ldo);
         SHM_CHECK_LAUNCH("assemble_kernel");
         return SHM_OK;
     })
 }
 
-extern "C" int shm_assemble_bwd(const void* din, int dtype, const int32_t slots[5], int nslots, float* dgen, int64_t npix, void* stream) {
-    SHM_REQUIRE(din && dgen && npix > 0 && nslots >= 0 && nslots <= 5, "shm_assemble_bwd: bad args");
+extern "C" int shm_pad_channels64(const void* src, int src_dtype, int lds, int C, void* dst_bf16, int64_t npix, void* stream) {
+    SHM_REQUIRE(src && dst_bf16 && npix > 0 && C >= 1 && C <= 64 && lds >= C, "shm_pad_channels64: bad args (1 <= C <= 64)");
+    SHM_REQUIRE((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0, "shm_pad_channels64: dst must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == SHM_F32) pad64_kernel<float><<<flat_grid(npix * 8), 256, 0, st>>>((const float*)src, lds, C, (uint4*)dst_bf16, npix);
+    else if (src_dtype == SHM_BF16) pad64_kernel<bf16><<<flat_grid(npix * 8), 256, 0, st>>>((const bf16*)src, lds, C, (uint4*)dst_bf16, npix);
+    else SHM_FAIL(SHM_EINVAL, "shm_pad_channels64: bad dtype %d", src_dtype);
+    SHM_CHECK_LAUNCH("pad64_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_assemble_bwd(const void* din, int dtype, int ldin, const int32_t slots[5], int nslots, float* dgen, int64_t npix, void* stream) {
+    SHM_REQUIRE(din && dgen && npix > 0 && nslots >= 0 && nslots <= 5 && ldin >= 10, "shm_assemble_bwd: bad args");
     if (nslots == 0) return SHM_OK;
     Slots sl; sl.n = nslots;
     for (int j = 0; j < 5; ++j) sl.s[j] = j < nslots ? slots[j] : 0;
     for (int j = 0; j < nslots; ++j) SHM_REQUIRE(slots[j] >= 0 && slots[j] < 5, "shm_assemble_bwd: slot out of range");
     DISPATCH_DTYPE(dtype, T, {
-        assemble_bwd_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>((const T*)din, sl, dgen, npix);
+        assemble_bwd_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>((const T*)din, ldin, sl, dgen, npix);
         SHM_CHECK_LAUNCH("assemble_bwd_kernel");
         return SHM_OK;
     })
 }
 
-extern "C" int shm_yuv2rgb(const float* Y, const float* cbcr, int64_t npix_cbcr, float* rgb, void* rgb_lp, int dtype_lp, int64_t npix, void* stream) {
+extern "C" int shm_yuv2rgb(const float* Y, const float* cbcr, int64_t npix_cbcr, float* rgb, void* rgb_lp, int dtype_lp, int ld_lp, int64_t npix, void* stream) {
     SHM_REQUIRE(Y && cbcr && (rgb || rgb_lp) && npix > 0 && npix_cbcr > 0, "shm_yuv2rgb: bad args");
+    SHM_REQUIRE(!rgb_lp || ld_lp >= 3, "shm_yuv2rgb: ld_lp must be >= 3");
+    SHM_REQUIRE(!(rgb_lp && dtype_lp == SHM_BF16 && ld_lp == 64) || (reinterpret_cast<uintptr_t>(rgb_lp) & 15) == 0, "shm_yuv2rgb: padded output must be 16-byte aligned");
     SHM_REQUIRE(npix % npix_cbcr == 0, "shm_yuv2rgb: npix %% npix_cbcr != 0");
     DISPATCH_DTYPE(dtype_lp, T, {
-        yuv2rgb_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(Y, cbcr, npix_cbcr, rgb, (T*)rgb_lp, npix);
+        yuv2rgb_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(Y, cbcr, npix_cbcr, rgb, (T*)rgb_lp, ld_lp, npix);
         SHM_CHECK_LAUNCH("yuv2rgb_kernel");
         return SHM_OK;
     })
 }
 
-extern "C" int shm_yuv2rgb_bwd(const float* drgb_f32, const void* drgb_lp, int dtype_lp, float* dY, int64_t npix, int accumulate, void* stream) {
-    SHM_REQUIRE((drgb_f32 || drgb_lp) && dY && npix > 0, "shm_yuv2rgb_bwd: bad args");
+extern "C" int shm_yuv2rgb_bwd(const float* drgb_f32, const void* drgb_lp, int dtype_lp, int ld_lp, float* dY, int64_t npix, int accumulate, void* stream) {
+    SHM_REQUIRE((drgb_f32 || drgb_lp) && dY && npix > 0 && (!drgb_lp || ld_lp >= 3), "shm_yuv2rgb_bwd: bad args");
     DISPATCH_DTYPE(dtype_lp, T, {
-        yuv2rgb_bwd_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(drgb_f32, (const T*)drgb_lp, dY, npix, accumulate);
+        yuv2rgb_bwd_kernel<T><<<flat_grid(npix), 256, 0, (cudaStream_t)stream>>>(drgb_f32, (const T*)drgb_lp, ld_lp, dY, npix, accumulate);
         SHM_CHECK_LAUNCH("yuv2rgb_bwd_kernel");
         return SHM_OK;
     })

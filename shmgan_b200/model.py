@@ -222,23 +222,25 @@ class ShmGANwithSSpecSeg:
             d_attn, d_attn_saved = D.attention(mask)
 
         # ---- G(1) (:509-553)
-        gen_in = ops.new((B, S, S, 10), dt)
+        g_cin = min(G.in_channels(B, S, S), G.in_channels(5 * B, S, S))
+        gen_in = ops.new((B, S, S, g_cin), dt)              # 10 channels, or zero-padded to 64 for the tensor-core first layer
         ops.assemble_input([None if bits[k] else ds[k] for k in range(5)], [3] * 5, 4, gen_in)
         gen_Y_lp, tape1 = G.forward(gen_in, g_attn, save=True)
         gen_Y = _f32(gen_Y_lp)
-        xA = ops.new((2 * B, S, S, 3), dt)                  # D batch A = [gen_rgb | origED], training=True (:559-563)
-        xB = ops.new((10 * B, S, S, 3), dt)                 # D batch B = [5 cyc_rgb | 5 orig], training=False (:627-642)
+        d_cin = min(D.in_channels(2 * B, S, S), D.in_channels(10 * B, S, S), D.in_channels(B, S, S), D.in_channels(5 * B, S, S))
+        xA = ops.new((2 * B, S, S, d_cin), dt)              # D batch A = [gen_rgb | origED], training=True (:559-563)
+        xB = ops.new((10 * B, S, S, d_cin), dt)             # D batch B = [5 cyc_rgb | 5 orig], training=False (:627-642)
+        to_d = ops.pad64 if d_cin == 64 else (lambda src, out: ops.cast_into(src, out))
         if dt == f32:
             gen_rgb = xA[:B]
             ops.yuv2rgb(gen_Y, avg, gen_rgb, None)
-            ops.cast_into(origs[4], xA[B:])
         else:
             gen_rgb = ops.new((B, S, S, 3), f32)
             ops.yuv2rgb(gen_Y, avg, gen_rgb, xA[:B])
-            ops.cast_into(origs[4], xA[B:])
+        to_d(origs[4], out=xA[B:])
 
         # ---- cyclic G passes, batched as 5B images: pass k = images [kB, (k+1)B) (:576-624)
-        cyc_in = ops.new((5 * B, S, S, 10), dt)
+        cyc_in = ops.new((5 * B, S, S, g_cin), dt)
         for k in range(5):
             srcs, lds = [], []
             for j in range(5):
@@ -258,7 +260,7 @@ class ShmGANwithSSpecSeg:
             cyc_rgb = ops.new((5 * B, S, S, 3), f32)
             ops.yuv2rgb(cyc_Y, avg, cyc_rgb, xB[:5 * B])
         for k in range(5):
-            ops.cast_into(origs[k], xB[(5 + k) * B:(6 + k) * B])
+            to_d(origs[k], out=xB[(5 + k) * B:(6 + k) * B])
 
         # ---- D passes
         s32 = S // 32
@@ -320,6 +322,7 @@ class ShmGANwithSSpecSeg:
         D.backward(tapeB, dD_rfB, dD_clsB, wgrad=True, need_dx=False, dattn=d_dattn, attn_nb=B)
         if self.live_mask:
             D.attention_backward(d_attn_saved, d_dattn)
+        D.store.finalize_grads()
         if self._reducer is not None:
             self._reducer.reduce_async(D.store.grad)
         dxA = D.backward(tapeA, dG_rfA, None, n=B, wgrad=False, need_dx=True)
@@ -342,6 +345,7 @@ class ShmGANwithSSpecSeg:
         G.backward(tape1, ops.cast(d_gen_Y, dt), g_dattn, attn_nb=B, need_dx=False)
         if self.live_mask:
             G.attention_backward(g_attn_saved, g_dattn)
+        G.store.finalize_grads()
         if self._reducer is not None:
             self._reducer.reduce_async(G.store.grad)
             self._reducer.wait()
@@ -353,7 +357,7 @@ class ShmGANwithSSpecSeg:
         self.step_count += 1
 
         # ---- published tensors / scalars (reference attribute names)
-        self.gen_input, self.gen_Y, self.gen_rgb = gen_in, gen_Y, gen_rgb
+        self.gen_input, self.gen_Y, self.gen_rgb = gen_in[..., :10], gen_Y, gen_rgb
         self.gen_rgb_output = gen_rgb
         self.averageCbCr = avg
         self.ds_yuv = ds
@@ -402,7 +406,7 @@ class ShmGANwithSSpecSeg:
         mask = self.SpecSeg.net.predict(self._y_plane(yuv, dt))
         self.specular_candidate = _f32(mask)
         attn = G.attention(mask)[0] if self.live_mask else None
-        gin = ops.new((B, S, S, 10), dt)
+        gin = ops.new((B, S, S, G.in_channels(B, S, S)), dt)
         ops.assemble_input([yuv, None, None, None, None], [3, 0, 0, 0, 0], 4, gin)                   # test.py:227-235
         self.gen_Y = _f32(G.forward(gin, attn))
         cbcr = ops.new((B, S, S, 2), torch.float32)
@@ -412,7 +416,7 @@ class ShmGANwithSSpecSeg:
         if cyclic:                                          # test.py:252-284 (Q11: the R channel stands in for Y)
             R = ops.new((B, S, S, 1), torch.float32)
             ops.cast_into(self.gen_rgb[..., 0:1], R)
-            cin = ops.new((5 * B, S, S, 10), dt)
+            cin = ops.new((5 * B, S, S, G.in_channels(5 * B, S, S)), dt)
             for k in range(5):
                 srcs = [None if j == k else R for j in range(5)]
                 ops.assemble_input(srcs, [1] * 5, k, cin[k * B:(k + 1) * B])

@@ -120,6 +120,7 @@ class ParamStore:
                                       if _is_trainable(k))
         self.version = 0
         self.step = 0
+        self.padded_convs: List[Conv] = []
         self.init(seed)
 
     def init(self, seed):
@@ -163,6 +164,7 @@ class ParamStore:
         return OrderedDict((k, host[o:o + n].view(shape).clone()) for k, (o, n, shape) in self.offsets.items())
 
     def export_grads(self) -> Dict[str, torch.Tensor]:
+        self.finalize_grads()
         host = self.grad.cpu()
         return OrderedDict((k, host[o:o + n].view(shape).clone()) for k, (o, n, shape) in self.offsets.items() if _is_trainable(k))
 
@@ -172,14 +174,30 @@ class ParamStore:
         if conv.has_bias:
             conv.b = self.views[conv.name + ".b"]
             conv.db = self.gviews.get(conv.name + ".b")
+        if conv.cin_pad is not None and conv not in self.padded_convs:
+            self.padded_convs.append(conv)
+        return conv
+
+    def pad(self, conv: Conv):
+        conv.enable_pad()
+        self.padded_convs.append(conv)
         return conv
 
     def zero_grad(self):
         self.grad.zero_()
+        for c in self.padded_convs:
+            c.zero_pad_grad()
+
+    def finalize_grads(self):
+        """Copies the weight gradients of the zero-padded first layers from their 64-channel scratch into the flat buffer
+        (idempotent; call once the backward sweeps are done, before the all-reduce / clip / Adam)."""
+        for c in self.padded_convs:
+            c.fold_pad_grad()
 
     def adam_step(self, lr0=2e-5, beta1=0.5, beta2=0.99, eps=1e-7, clip=1.0, gscale=1.0,
                   decay_steps=10000.0, decay_rate=0.95):
         """clip_by_value(+-1) + Keras Adam with ExponentialDecay (ShmGANwithSSpecSeg.py:169-175, :860-871)."""
+        self.finalize_grads()
         t = self.step + 1
         lr = lr0 * decay_rate ** (self.step / decay_steps)
         lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
@@ -204,6 +222,9 @@ class _CLI:
 class Generator:
     def __init__(self, filter_size=64, live_mask=True, dtype=torch.float32, device="cuda", seed=42, tensor_core=True):
         self.N0, self.live_mask, self.dtype, self.tc = filter_size, live_mask, dtype, tensor_core
+        # tensor-core mode: the 10-channel input and the 1-channel mask are presented zero-padded to 64 channels
+        self.pad_in = bool(tensor_core and dtype == torch.bfloat16 and filter_size % 64 == 0)
+        self.cin_buf = 64 if self.pad_in else 10
         self.store = ParamStore(generator_specs(filter_size, live_mask), device, seed)
         s, N, cin = self.store, filter_size, 10
         self.enc, self.attn, self.dec, self.up = [], [], [], []
@@ -225,8 +246,17 @@ class Generator:
             self.dec.append((_CLI(s, f"dec{u}a", 2 * N, N), _CLI(s, f"dec{u}b", N, N)))
             cin = N
         self.out = s.bind(Conv("out", 1, 1, cin, 1))
+        if self.pad_in:
+            s.pad(self.enc[0][0].conv)
+            for ca, _ in self.attn:
+                s.pad(ca)
 
     # -- helpers -----------------------------------------------------------------------------------
+    def in_channels(self, n, h, w) -> int:
+        """Channel count of the input buffer forward() wants for an [n,h,w] batch: 64 (zero-padded, tensor-core first layer)
+        when that form can serve the shape, else the plain 10."""
+        return 64 if (self.pad_in and self.enc[0][0].conv.can_pad(n, h, w)) else 10
+
     def _conv(self, c: Conv, x, y=None):
         return c.fwd(x, y, self.tc, self.store.version)
 
@@ -238,10 +268,11 @@ class Generator:
             if lvl > 0:
                 pooled = ops.maxpool(pooled, 2)
             ca, cb = self.attn[lvl]
-            a1 = self._conv(ca, pooled)
+            pin = ops.pad64(pooled) if (self.pad_in and ca.can_pad(*pooled.shape[:3])) else pooled
+            a1 = self._conv(ca, pin)
             a2 = self._conv(cb, a1)
             feats.append(a2)
-            saved.append((pooled, a1, a2))
+            saved.append((pin, a1, a2))
         return feats, saved
 
     def attention_backward(self, saved, dattn: List[torch.Tensor]):
@@ -256,8 +287,11 @@ class Generator:
             ca.wgrad(pooled, d1, self.tc)
 
     def forward(self, x: torch.Tensor, attn: Optional[List[torch.Tensor]] = None, save: bool = False):
-        """x [B,S,S,10] (self.dtype) -> y [B,S,S,1].  attn: per-level features [Ba,...] broadcast as n % Ba."""
+        """x [B,S,S,10] (self.dtype; or already zero-padded to [B,S,S,64] in tensor-core mode) -> y [B,S,S,1].
+        attn: per-level features [Ba,...] broadcast as n % Ba."""
         B, S = x.shape[0], x.shape[1]
+        if x.shape[-1] == 10 and self.in_channels(B, S, x.shape[2]) == 64:
+            x = ops.pad64(x)
         tape = {"x": x, "enc": [], "dec": [], "bott": []} if save else None
         h, cats = x, []
         for lvl in range(4):
@@ -314,9 +348,12 @@ class Generator:
         Returns d(x) [B,S,S,10] if need_dx."""
         v = self.store.version
         h, y = tape["last"]
-        dpre = ops.act_bwd(dy, y, ACT_LRELU)
-        self.out.wgrad(h, dpre, self.tc)
-        dh = self.out.dgrad(dpre, h.shape, None, self.tc, v)
+        if self.tc and self.out.pw1_ok(h):
+            dh = self.out.pw1_bwd(h, dy, y)
+        else:
+            dpre = ops.act_bwd(dy, y, ACT_LRELU)
+            self.out.wgrad(h, dpre, self.tc)
+            dh = self.out.dgrad(dpre, h.shape, None, self.tc, v)
         dskips = [None] * 4
         for u in (3, 2, 1, 0):
             hin, cat, za, sa, ya, zb, sb = tape["dec"][u]
@@ -352,6 +389,8 @@ class Discriminator:
     def __init__(self, image_size, filter_size=64, live_mask=True, dtype=torch.float32, device="cuda", seed=43,
                  tensor_core=True, dropout=0.2):
         self.S, self.live_mask, self.dtype, self.tc, self.dropout = image_size, live_mask, dtype, tensor_core, dropout
+        self.pad_in = bool(tensor_core and dtype == torch.bfloat16 and filter_size % 64 == 0)
+        self.cin_buf = 64 if self.pad_in else 3
         self.store = ParamStore(discriminator_specs(image_size, filter_size, live_mask), device, seed)
         s, N, cin = self.store, filter_size, 3
         self.blocks = []
@@ -363,11 +402,20 @@ class Discriminator:
         self.head = s.bind(Conv("head", 3, 3, cin, 1, bias=False))
         self.dense_w = s.views["dense.w"]
         self.dense_dw = s.gviews["dense.w"]
+        if self.pad_in:
+            s.pad(self.blocks[0].conv)
+            if live_mask:
+                s.pad(self.attn[0])
+
+    def in_channels(self, n, h, w) -> int:
+        return 64 if (self.pad_in and self.blocks[0].conv.can_pad(n, h, w)) else 3
 
     def attention(self, mask):
         """MaxPool16(mask) -> 2 x [Conv3x3 + LeakyReLU] @512 (ShmGANwithSSpecSeg.py:358, :404-412)."""
         m = ops.cast(mask, self.dtype) if mask.dtype != self.dtype else mask
         pooled = ops.maxpool(m, 16)
+        if self.pad_in and self.attn[0].can_pad(*pooled.shape[:3]):
+            pooled = ops.pad64(pooled)
         a1 = self.attn[0].fwd(pooled, None, self.tc, self.store.version)
         a2 = self.attn[1].fwd(a1, None, self.tc, self.store.version)
         return a2, (pooled, a1, a2)
@@ -384,7 +432,14 @@ class Discriminator:
         """x [B,S,S,3] -> (rf [B,S/32,S/32,1], cls [B,5] fp32).  noise / keep: the GaussianNoise(0.1) / Dropout(0.2)
         draws of a training=True call (:352, :363); None = training=False."""
         v = self.store.version
-        h = x if noise is None else ops.add(x, noise)
+        if x.shape[-1] == 64 or self.in_channels(x.shape[0], x.shape[1], x.shape[2]) == 64:
+            # zero-padded 64-channel input; the noise is added into the first 3 channels (of a private copy unless the caller
+            # already handed over the padded buffer, which train_step does)
+            h = x if x.shape[-1] == 64 else ops.pad64(x)
+            if noise is not None:
+                ops.add_channels_(h, noise)
+        else:
+            h = x if noise is None else ops.add(x, noise)
         tape = {"layers": []} if save else None
         for i, bl in enumerate(self.blocks):
             z = bl.conv.fwd(h, None, self.tc, v)

@@ -81,6 +81,30 @@ class Conv:
         self.w = self.b = self.dw = self.db = None          # views set by ParamStore.bind
         self.w_tc = self.w_tc_d = None                      # bf16 [tap][n][k] copies for the tensor-core path
         self.tc_version = -1
+        self.cin_pad = None                                 # 64 when the layer reads a zero-padded input on the tensor cores
+        self.dw_pad = None                                  # fp32 [kh,kw,cin_pad,cout] weight-gradient scratch of the padded layer
+
+    def enable_pad(self):
+        """First layers (Cin = 10 / 3 / 1) in tensor-core mode: the input is presented zero-padded to 64 channels so that the
+        reduction dimension fills one 64-channel TMA box; the padded weight rows are zero, so the arithmetic is unchanged."""
+        assert not self.transposed and self.cin < 64 and self.cout % 64 == 0
+        self.cin_pad = 64
+        return self
+
+    def can_pad(self, n, h, w) -> bool:
+        """True when the zero-padded tensor-core form can serve an [n,h,w,*] input (the lattice must tile into 128-point boxes)."""
+        if self.cin_pad is None:
+            return False
+        d = self.desc(n, h, w, self.cin_pad, self.cout, BF16, cin=self.cin_pad)
+        return self.tc_ok(d)
+
+    def padded(self, channels: int) -> bool:
+        return self.cin_pad is not None and channels == self.cin_pad and self.cin != self.cin_pad
+
+    def pw1_ok(self, x) -> bool:
+        """1x1 conv to one channel on bf16 activations: served by the bandwidth kernel (shm_pw1_*)."""
+        return (self.kh == 1 and self.kw == 1 and self.cout == 1 and not self.transposed and x.dtype == torch.bfloat16
+                and self.cin in (8, 16, 32, 64, 128, 256) and ld(x) % 8 == 0 and x.data_ptr() % 16 == 0)
 
     def wshape(self):
         return (self.kh, self.kw, self.cout, self.cin) if self.transposed else (self.kh, self.kw, self.cin, self.cout)
@@ -90,8 +114,8 @@ class Conv:
             return h * self.stride, w * self.stride
         return -(-h // self.stride), -(-w // self.stride)
 
-    def desc(self, n, h, w, ldx, ldy, dtype, act=None) -> ConvDesc:
-        return ConvDesc(n, h, w, self.cin, self.cout, self.kh, self.kw, self.stride, int(self.transposed),
+    def desc(self, n, h, w, ldx, ldy, dtype, act=None, cin=None) -> ConvDesc:
+        return ConvDesc(n, h, w, self.cin if cin is None else cin, self.cout, self.kh, self.kw, self.stride, int(self.transposed),
                         self.act if act is None else act, ldx, ldy, dtype, 0)
 
     # -- tensor-core weights ---------------------------------------------------------------------
@@ -99,17 +123,18 @@ class Conv:
         """Re-lays the fp32 master weights out as bf16 [tap][n][k] for fwd and dgrad (once per optimiser step)."""
         if self.tc_version == version:
             return
-        d = self.desc(1, 16, 16, self.cin, self.cout, BF16)
+        cin = self.cin_pad or self.cin
+        d = self.desc(1, 16, 16, cin, self.cout, BF16, cin=cin)
         if self.w_tc is None:
-            n = self.kh * self.kw * self.cin * self.cout
+            n = self.kh * self.kw * cin * self.cout
             self.w_tc = new((n,), torch.bfloat16)
             self.w_tc_d = new((n,), torch.bfloat16)
-        call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), _p(self.w_tc), 0, _stream())
-        call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), _p(self.w_tc_d), 1, _stream())
+        call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), self.cin, _p(self.w_tc), 0, _stream())
+        call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), self.cin, _p(self.w_tc_d), 1, _stream())
         self.tc_version = version
 
     def tc_ok(self, d: ConvDesc) -> bool:
-        return (d.dtype == BF16 and self.cin % 64 == 0 and self.cout % 64 == 0
+        return (d.dtype == BF16 and d.Cin % 64 == 0 and self.cout % 64 == 0
                 and bool(call("shm_conv2d_tc_supported", C.byref(d), 0)))
 
     # -- forward / backward ------------------------------------------------------------------------
@@ -118,9 +143,15 @@ class Conv:
         ho, wo = self.out_hw(h, w)
         if y is None:
             y = new((n, ho, wo, self.cout), x.dtype)
-        d = self.desc(n, h, w, ld(x), ld(y), dt(x))
+        pad = self.padded(x.shape[-1])
+        d = self.desc(n, h, w, ld(x), ld(y), dt(x), cin=self.cin_pad if pad else None)
         fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, x.element_size())
-        if tc and self.tc_ok(d):
+        if pad and not (tc and self.tc_ok(d)):
+            raise L.ShmError("%s: zero-padded input needs the tensor-core path (shape %s)" % (self.name, tuple(x.shape)))
+        if tc and self.pw1_ok(x):
+            _prof("bw", "fwd", self.name, fl, nb, lambda: call("shm_pw1_fwd", _p(x), ld(x), self.cin, _p(self.w), _p(self.b), self.act, _p(y),
+                                                              n * h * w, dt(x), _stream()))
+        elif tc and self.tc_ok(d):
             self.refresh_tc(version)
             _prof("tc", "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b), _p(y), _stream()))
         else:
@@ -141,11 +172,14 @@ class Conv:
 
     def dgrad(self, dy: torch.Tensor, x_shape, dx: Optional[torch.Tensor] = None, tc: bool = True, version: int = 0):
         """dx from dy = dL/d(pre-activation)."""
-        n, h, w, _ = x_shape
+        n, h, w, cx = x_shape
+        pad = self.padded(cx)
         if dx is None:
-            dx = new((n, h, w, self.cin), dy.dtype)
-        d = self.desc(n, h, w, ld(dx), ld(dy), dt(dy), ACT_NONE)
+            dx = new((n, h, w, cx if pad else self.cin), dy.dtype)
+        d = self.desc(n, h, w, ld(dx), ld(dy), dt(dy), ACT_NONE, cin=self.cin_pad if pad else None)
         fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, dy.element_size())
+        if pad and not (tc and self.tc_ok(d)):
+            raise L.ShmError("%s: zero-padded dgrad needs the tensor-core path" % self.name)
         if tc and self.tc_ok(d):
             self.refresh_tc(version)
             _prof("tc", "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_dgrad", C.byref(d), _p(dy), _p(self.w_tc_d), _p(dx), _stream()))
@@ -155,15 +189,43 @@ class Conv:
 
     def wgrad(self, x: torch.Tensor, dy: torch.Tensor, tc: bool = True):
         """dw += , db += (gradients accumulate: weights are shared by several passes)."""
-        n, h, w, _ = x.shape
-        d = self.desc(n, h, w, ld(x), ld(dy), dt(x), ACT_NONE)
+        n, h, w, cx = x.shape
+        pad = self.padded(cx)
+        d = self.desc(n, h, w, ld(x), ld(dy), dt(x), ACT_NONE, cin=self.cin_pad if pad else None)
         fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, x.element_size())
+        if pad and not (tc and self.tc_ok(d)):
+            raise L.ShmError("%s: zero-padded wgrad needs the tensor-core path" % self.name)
+        dw = self.dw
+        if pad:
+            if self.dw_pad is None:
+                self.dw_pad = torch.zeros((self.kh, self.kw, self.cin_pad, self.cout), dtype=torch.float32, device=x.device)
+            dw = self.dw_pad
         if tc and self.tc_ok(d):
-            _prof("tc", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _stream()))
+            _prof("tc", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(dw), _stream()))
             if self.has_bias:
                 call("shm_colsum", _p(dy), dy.shape[0] * dy.shape[1] * dy.shape[2], self.cout, ld(dy), dt(dy), _p(self.db), _stream())
         else:
             _prof("simt", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _p(self.db) if self.has_bias else None, _stream()))
+
+    def pw1_bwd(self, x, dy, y, need_dx=True):
+        """Fused backward of the 1x1 -> 1 channel layer: activation derivative, dx, dw +=, db += in one pass."""
+        n, h, w, _ = x.shape
+        dx = new((n, h, w, self.cin), x.dtype) if need_dx else None
+        fl, nb = 2 * self.flops(n, h, w), 2 * self.io_bytes(n, h, w, x.element_size())
+        _prof("bw", "bwd", self.name, fl, nb, lambda: call("shm_pw1_bwd", _p(x), ld(x), self.cin, _p(self.w), _p(dy), _p(y), self.act, _p(dx), ld(dx),
+                                                          _p(self.dw), _p(self.db) if self.has_bias else None, n * h * w, dt(x), _stream()))
+        return dx
+
+    def zero_pad_grad(self):
+        if self.dw_pad is not None:
+            self.dw_pad.zero_()
+
+    def fold_pad_grad(self):
+        """dw[tap, :cin, :] = dw_pad[tap, :cin, :] (the padded rows are gradients of weights that do not exist)."""
+        if self.dw_pad is None:
+            return
+        taps, n = self.kh * self.kw, self.cin * self.cout
+        call("shm_cast2d", _p(self.dw_pad), F32, self.cin_pad * self.cout, _p(self.dw), F32, n, taps, n, _stream())
 
 
 # ------------------------------------------------------------------------------------------------
@@ -334,27 +396,48 @@ def avg_cbcr(ds: Sequence[torch.Tensor]):
 
 
 def assemble_input(srcs, src_lds, onehot, out):
-    """srcs: 5 fp32 tensors (or None = zeros) giving one value per pixel at stride src_lds[j]; out [N,H,W,10]."""
+    """srcs: 5 fp32 tensors (or None = zeros) giving one value per pixel at stride src_lds[j]; out [N,H,W,10] or the
+    zero-padded [N,H,W,64] tensor-core form."""
     arr_p = (C.c_void_p * 5)(*[None if s is None else s.data_ptr() for s in srcs])
     arr_l = (C.c_int32 * 5)(*src_lds)
-    npix = out.numel() // 10
-    call("shm_assemble_input", C.cast(arr_p, C.POINTER(C.c_void_p)), arr_l, onehot, _p(out), npix, dt(out), _stream())
+    ldo = out.shape[-1]
+    call("shm_assemble_input", C.cast(arr_p, C.POINTER(C.c_void_p)), arr_l, onehot, _p(out), ldo, out.numel() // ldo, dt(out), _stream())
     return out
 
 
 def assemble_bwd(din, slots, dgen):
     arr = (C.c_int32 * 5)(*(list(slots) + [0] * (5 - len(slots))))
-    call("shm_assemble_bwd", _p(din), dt(din), arr, len(slots), _p(dgen), din.numel() // 10, _stream())
+    ldin = din.shape[-1]
+    call("shm_assemble_bwd", _p(din), dt(din), ldin, arr, len(slots), _p(dgen), din.numel() // ldin, _stream())
+
+
+def pad64(src, out=None):
+    """[N,H,W,C] (C <= 64, fp32 or bf16, any pixel stride) -> dense bf16 [N,H,W,64] with channels C.. zero."""
+    n, h, w, c = src.shape
+    if out is None:
+        out = new((n, h, w, 64), torch.bfloat16)
+    assert out.is_contiguous() and out.shape[-1] == 64 and out.dtype == torch.bfloat16
+    call("shm_pad_channels64", _p(src), dt(src), ld(src), c, _p(out), n * h * w, _stream())
+    return out
+
+
+def add_channels_(a, b):
+    """a[..., :C] += b  in place (C = b's channel count; a may be wider, e.g. the zero-padded discriminator input)."""
+    c = b.shape[-1]
+    call("shm_add", _p(a), ld(a), _p(b), ld(b), _p(a), ld(a), b.numel() // c, c, dt(a), _stream())
+    return a
 
 
 def yuv2rgb(Y, cbcr, rgb=None, lp=None):
     """Y [N,H,W,1] fp32, cbcr [Nc,H,W,2] fp32 broadcast over N as n % Nc -> rgb [N,H,W,3] fp32 and / or a bf16 copy `lp`
     (the discriminator's input in bf16 mode).  Outputs must be dense."""
     n, h, w, _ = Y.shape
-    call("shm_yuv2rgb", _p(Y), _p(cbcr), cbcr.numel() // 2, _p(rgb), _p(lp), BF16 if lp is not None else F32, n * h * w, _stream())
+    call("shm_yuv2rgb", _p(Y), _p(cbcr), cbcr.numel() // 2, _p(rgb), _p(lp), BF16 if lp is not None else F32,
+         3 if lp is None else lp.shape[-1], n * h * w, _stream())
     return rgb, lp
 
 
 def yuv2rgb_bwd(drgb_f32, drgb_lp, dY, accumulate):
     code = dt(drgb_lp) if drgb_lp is not None else F32
-    call("shm_yuv2rgb_bwd", _p(drgb_f32), _p(drgb_lp), code, _p(dY), dY.numel(), int(accumulate), _stream())
+    call("shm_yuv2rgb_bwd", _p(drgb_f32), _p(drgb_lp), code, 3 if drgb_lp is None else drgb_lp.shape[-1], _p(dY), dY.numel(),
+         int(accumulate), _stream())

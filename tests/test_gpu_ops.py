@@ -276,3 +276,67 @@ def test_rng_moments():
     k = ops.rng_keep((1 << 20,), 7, 1 << 20, 0.8, torch.float32)
     assert float(k.mean()) == pytest.approx(0.8, abs=2e-3)
     assert torch.equal(ops.rng_normal((1000,), 7, 0, 0.1, torch.float32), x[:1000])
+
+
+# ---- tensor-core first-layer padding and the 1x1 -> 1 channel bandwidth kernels -------------------------
+def test_pad64_and_padded_forms():
+    from shmgan_b200 import ops
+    N, S = 2, 16
+    for C, seed in ((1, 80), (3, 81), (10, 82)):
+        x = randn((N, S, S, C), seed)
+        out = ops.pad64(dev(x))
+        assert out.shape == (N, S, S, 64) and out.dtype == torch.bfloat16
+        assert torch.equal(out[..., :C].float().cpu(), x.float().bfloat16().float())
+        assert float(out[..., C:].abs().max()) == 0.0
+    # padded generator-input assembly == plain assembly in the first 10 channels, zeros after
+    ds = [dev(randn((N, S, S, 3), 90 + i)) for i in range(5)]
+    plain = torch.empty((N, S, S, 10), device="cuda", dtype=torch.bfloat16)
+    padded = torch.full((N, S, S, 64), 9.0, device="cuda", dtype=torch.bfloat16)
+    srcs, lds = [ds[0], None, ds[2], ds[3], None], [3, 0, 3, 3, 0]
+    ops.assemble_input(srcs, lds, 1, plain)
+    ops.assemble_input(srcs, lds, 1, padded)
+    assert torch.equal(padded[..., :10], plain) and float(padded[..., 10:].abs().max()) == 0.0
+    # padded yuv->rgb copy and the strided backward
+    Y, cb = randn((N, S, S, 1), 95), randn((N, S, S, 2), 96)
+    rgb = torch.empty((N, S, S, 3), device="cuda")
+    lp = torch.full((N, S, S, 64), 9.0, device="cuda", dtype=torch.bfloat16)
+    ops.yuv2rgb(dev(Y), dev(cb), rgb, lp)
+    assert torch.equal(lp[..., :3], rgb.bfloat16()) and float(lp[..., 3:].abs().max()) == 0.0
+    d = bf16_round(randn((N, S, S, 64), 97))
+    dY = torch.zeros((N, S, S, 1), device="cuda")
+    ops.yuv2rgb_bwd(None, dev(d, torch.bfloat16), dY, accumulate=False)
+    assert rel_err(dY, d[..., :3].sum(dim=3, keepdim=True)) < 1e-6
+    din = bf16_round(randn((N, S, S, 64), 98))
+    dgen = torch.zeros((N, S, S, 1), device="cuda")
+    ops.assemble_bwd(dev(din, torch.bfloat16), [1, 4], dgen)
+    assert rel_err(dgen, din[..., 1:2] + din[..., 4:5]) < 1e-6
+
+
+@pytest.mark.parametrize("C,act", [(64, 1), (16, 3), (256, 1), (8, 0)])
+def test_pw1_kernels(C, act):
+    from shmgan_b200 import ops
+    from _util import oracle_conv
+    N, H, W = 2, 13, 11                                   # ragged pixel count: exercises the tail of the last block
+    x = bf16_round(randn((N, H, W, C), 100))
+    w = randn((1, 1, C, 1), 101, 0.1).float().to(F64)
+    b = randn((1,), 102, 0.1).float().to(F64)
+    xr, wr, br = x.clone().requires_grad_(), w.clone().requires_grad_(), b.clone().requires_grad_()
+    y = oracle_conv(xr, wr, br, 1, False, act)
+    c = ops.Conv("t", 1, 1, C, 1, act=act)
+    c.w, c.b = dev(w), dev(b)
+    c.dw, c.db = torch.full_like(c.w, 0.5), torch.zeros(1, device="cuda")
+    xd = dev(x, torch.bfloat16)
+    assert c.pw1_ok(xd)
+    yd = c.fwd(xd, tc=True)
+    assert rel_err(yd, y) < 1e-2
+    if act == 3:
+        return
+    # backward from the device's own (bf16-rounded) output so that the activation branch is identical
+    yq = yd.double().cpu()
+    dy = bf16_round(randn(tuple(y.shape), 103))
+    g = dy * torch.where(yq > 0, 1.0, 0.2) if act == 1 else dy
+    pre = oracle_conv(xr, wr, br, 1, False, 0)
+    gx, gw, gb = torch.autograd.grad((pre * g).sum(), [xr, wr, br])
+    dx = c.pw1_bwd(xd, dev(dy, torch.bfloat16), yd)
+    assert rel_err(dx, gx) < 1e-2
+    assert rel_err(c.dw - 0.5, gw) < 1e-3 and rel_err(c.db, gb) < 1e-3
