@@ -113,6 +113,48 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+
+// Epilogue of one 32-column chunk of an accumulator row: TMEM -> registers -> (+bias) -> activation -> bf16 -> 64 contiguous bytes.
+// The activation is selected ONCE per chunk (warp-uniform branch) and the bias arrives as 8 x float4: the first version
+// re-decided both per element (~1500 SASS instructions per chunk) and was the bottleneck of every small-K layer
+// (ncu source page of r01: 12.5 k cycles per 128 x 64 tile against 1.2 k tensor-core cycles).
+__device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* __restrict__ bias, int act, bf16* __restrict__ dst, bool ok) {
+    uint32_t r[32];
+    tmem_ld32(taddr, r);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = __ldg(b4 + j);
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+    }
+    if (act == SHM_ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+    } else if (act == SHM_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == SHM_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+    }
+    if (ok) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            uint4 u;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(dst + j) = u;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad kernel
 // ------------------------------------------------------------------------------------------------
@@ -240,28 +282,149 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32), r);
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(r[j]);
-                    if (p.bias) x += __ldg(p.bias + nt * BN + c * 32 + j);
-                    v[j] = act_fwd(x, p.act);
-                }
-                if (ok) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 u;
-                        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-                        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-                        *reinterpret_cast<uint4*>(dst + c * 32 + j) = u;
-                    }
+            for (int c = 0; c < BN / 32; ++c)
+                epi_chunk(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32),
+                          p.bias ? p.bias + nt * BN + c * 32 : nullptr, p.act, dst + c * 32, ok);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// halo kernel: stride-1 3x3 convolutions with few channels (Cin*Cout <= 8192: the full-resolution 64/128-channel layers).
+//
+// The generic kernel above fetches the A tile once PER TAP (9x) and the weight tile once per (tile, tap): for a 64->64 layer
+// that is 216 KB of L2->SM traffic per 128x64 output tile against 1152 tensor-core cycles, i.e. the kernel runs at the
+// ~10 TB/s TMA/L2 fabric limit and 16 % of the tensor peak (profiles/r01_conv_layers_first.json).  Here
+//   * the weights of ALL taps stay resident in shared memory for the life of the persistent CTA (<= 144 KB), and
+//   * ONE TMA box brings the (16+2) x (8+2)-pixel halo of a 16 x 8 output tile; the nine taps are nine smem matrix descriptors
+//     into that same halo tile: start address shifted by (dy * 10 + dx) rows of 128 B, 8-row groups SBO = 10 rows apart.
+//     tcgen05.mma applies the 128-byte swizzle to the final absolute address, so unaligned starts and SBO = 1280 address the
+//     TMA-written tile correctly (measured: profiles/r01_umma_shifted_descriptor_probe.txt).
+// L2->SM traffic drops to 23 KB per k-chunk per tile (9.4x less); the layer becomes shared-memory-operand / HBM bound.
+// ------------------------------------------------------------------------------------------------
+constexpr int HALO_W = 10, HALO_H = 18;                       // (8 + 2) x (16 + 2) pixels
+constexpr int HALO_BYTES = HALO_W * HALO_H * 128;             // 23040
+constexpr int HALO_STAGE = 23552;                             // rounded up to 1024
+struct HaloParams {
+    int tdy[9], tdx[9], wrow[9];     // tap offsets relative to the halo origin (0..2) and first weight row of the tap
+    int oy, ox;                      // halo origin relative to the tile origin (-1 for SAME 3x3)
+    int tiles_x, tiles_y, total_tiles;
+    int H, W, ldout, Nn;
+    const float* bias; int act;
+    bf16* out;
+};
+
+template <int KC, int BN>
+struct HaloCfg {
+    static constexpr int W_BYTES = 9 * KC * BN * 128;
+    static constexpr int STAGES = (W_BYTES <= 73728) ? 6 : 3;
+    static constexpr int SMEM = W_BYTES + STAGES * HALO_STAGE + 1024 + 256;
+    static constexpr int TMEM_COLS = 2 * BN;
+};
+
+template <int KC, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+    using Cfg = HaloCfg<KC, BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sW = smem;                                   // [9 taps][KC][BN rows x 128 B]
+    uint8_t* sA = smem + Cfg::W_BYTES;                    // [STAGES][HALO_STAGE]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::STAGES * HALO_STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + Cfg::STAGES;
+    uint64_t* tfull = bars + 2 * Cfg::STAGES;             // [2]
+    uint64_t* tempty = tfull + 2;                         // [2]
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // weights of every tap, once
+            mbar_expect_tx(wbar, Cfg::W_BYTES);
+            for (int t = 0; t < 9; ++t)
+                for (int kc = 0; kc < KC; ++kc)
+                    tma_load_2d(sW + (t * KC + kc) * (BN * 128), &tmB, wbar, kc * 64, p.wrow[t]);
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const int img = tile / per_img; const int r = tile - img * per_img;
+                const int y0 = (r / p.tiles_x) * 16 + p.oy, x0 = (r % p.tiles_x) * 8 + p.ox;
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&empty[stage], phase ^ 1);
+                    mbar_expect_tx(&full[stage], HALO_BYTES);
+                    tma_load_4d(sA + stage * HALO_STAGE, &tmA, &full[stage], kc * 64, x0, y0, img);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+            mbar_wait(wbar, 0);
+            int stage = 0; uint32_t phase = 0;
+            int local = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+                const int as = local & 1;
+                mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kc = 0; kc < KC; ++kc) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + stage * HALO_STAGE);
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(p.tdy[t] * HALO_W + p.tdx[t]) * 128u, 16, HALO_W * 128);
+                        const uint64_t bdesc = make_desc_sw128(smem_u32(sW + (t * KC + kc) * (BN * 128)), 16, 1024);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+                    }
+                    umma_commit(&empty[stage]);
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull[as]);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int ty = row >> 3, tx = row & 7;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            const int img = tile / per_img; const int r = tile - img * per_img;
+            const int oy = (r / p.tiles_x) * 16 + ty, ox = (r % p.tiles_x) * 8 + tx;
+            bf16* dst = p.out + ((long long)(img * p.H + oy) * p.W + ox) * p.ldout;
+            mbar_wait(&tfull[as], (local >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c)
+                epi_chunk(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32),
+                          p.bias ? p.bias + c * 32 : nullptr, p.act, dst + c * 32, true);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
@@ -375,6 +538,60 @@ int launch_tc(const Geometry& g, int N, const void* in, const void* w_tc, int wr
     }
     SHM_CHECK_LAUNCH("conv_tc_kernel");
     return SHM_OK;
+}
+
+
+// encode a 4-D activation map with an explicit box (halo kernel)
+int encode_act_box(CUtensorMap* tm, const void* base, int C, int W, int H, int N, int ld, int bx, int by) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+    cuuint32_t box[4] = {64, (cuuint32_t)bx, (cuuint32_t)by, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled(halo C=%d W=%d H=%d N=%d ld=%d) failed: %d", C, W, H, N, ld, (int)r);
+    return SHM_OK;
+}
+
+// stride-1 3x3 layers the halo kernel serves: K, Nn in {64, 128} with all nine weight tiles resident (K * Nn <= 8192)
+bool halo_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
+    return kh == 3 && kw == 3 && stride == 1 && H % 16 == 0 && W % 8 == 0 && (K == 64 || K == 128) && (Nn == 64 || Nn == 128) && K * Nn <= 8192;
+}
+
+template <int KC, int BN>
+int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<KC, BN>::SMEM); attr = true; }
+    int grid = shm_num_sms();
+    if (grid > p.total_tiles) grid = p.total_tiles;
+    conv_halo_kernel<KC, BN><<<grid, TC_THREADS, HaloCfg<KC, BN>::SMEM, st>>>(tmA, tmB, p);
+    SHM_CHECK_LAUNCH("conv_halo_kernel");
+    return SHM_OK;
+}
+
+// in: [N,H,W,K] (ld ldin), out: [N,H,W,Nn] (ld ldout); taps (tdy, tdx) in {-1,0,1} with weight rows twrow
+int launch_halo(int N, int H, int W, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
+                void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st) {
+    HaloParams p{};
+    int miny = 9, minx = 9;
+    for (int t = 0; t < 9; ++t) { if (tdy[t] < miny) miny = tdy[t]; if (tdx[t] < minx) minx = tdx[t]; }
+    for (int t = 0; t < 9; ++t) {
+        p.tdy[t] = tdy[t] - miny; p.tdx[t] = tdx[t] - minx; p.wrow[t] = twrow[t];
+        if (p.tdy[t] > 2 || p.tdx[t] > 2) SHM_FAIL(SHM_EUNSUPPORTED, "conv_halo: tap offsets exceed the 1-pixel halo");
+    }
+    p.oy = miny; p.ox = minx;
+    p.tiles_x = W / 8; p.tiles_y = H / 16; p.total_tiles = N * p.tiles_x * p.tiles_y;
+    p.H = H; p.W = W; p.ldout = ldout; p.Nn = Nn; p.bias = bias; p.act = act; p.out = (bf16*)out;
+    CUtensorMap tmA, tmB;
+    if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, HALO_H)) return rc;
+    if (int rc = encode_w(&tmB, w_tc, K, wrows_total, Nn)) return rc;
+    if (K == 64 && Nn == 64) return launch_halo_t<1, 64>(tmA, tmB, p, st);
+    if (K == 128 && Nn == 64) return launch_halo_t<2, 64>(tmA, tmB, p, st);
+    if (K == 64 && Nn == 128) return launch_halo_t<1, 128>(tmA, tmB, p, st);
+    SHM_FAIL(SHM_EUNSUPPORTED, "conv_halo: K=%d Nn=%d", K, Nn);
 }
 
 
@@ -587,6 +804,7 @@ extern "C" int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad) {
 extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, void* stream) {
     if (int rc = tc_check(d)) return rc;
     SHM_REQUIRE(x && w_tc && y, "shm_conv2d_tc_fwd: NULL buffer");
+    SHM_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "shm_conv2d_tc_fwd: bias must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int Ho, Wo; out_dims(d, Ho, Wo);
     const int s = d->stride;
@@ -597,6 +815,8 @@ extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const vo
         int nt = 0;
         for (int ky = 0; ky < d->kh; ++ky)
             for (int kx = 0; kx < d->kw; ++kx) { tdy[nt] = ky - pby; tdx[nt] = kx - pbx; twr[nt] = (ky * d->kw + kx) * d->Cout; ++nt; }
+        if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
+            return launch_halo(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st);
         Geometry g{d->H, d->W, d->ldx, d->Cin, Ho, Wo, s, Ho, Wo, d->ldy, d->Cout, 1};
         return launch_tc(g, d->N, x, w_tc, wrows, bias, d->act, y, tdy, tdx, twr, nt, 0, 0, st);
     }
@@ -650,6 +870,8 @@ extern "C" int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const
                 }
             }
             if (nt == 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: parity class without taps");
+            if (halo_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s))
+                return launch_halo(d->N, d->H, d->W, d->Cout, d->Cin, dy, d->ldy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, d->ldx, tdy, tdx, twr, st);
             Geometry g{Ho, Wo, d->ldy, d->Cout, cdiv(d->H - ry, s), cdiv(d->W - rx, s), 1, d->H, d->W, d->ldx, d->Cin, s};
             if (int rc = launch_tc(g, d->N, dy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, tdy, tdx, twr, nt, ry, rx, st)) return rc;
         }

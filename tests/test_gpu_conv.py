@@ -116,6 +116,9 @@ TC_CASES = [
     (1, 2, 256, 64, 64, 3, 1, False, 0, True),      # two tiles per row
     (2, 16, 16, 128, 64, 3, 1, False, 1, True),     # dec-a class (Cin = 2 * Cout)
     (1, 16, 16, 256, 256, 3, 1, False, 2, True),
+    (2, 32, 32, 64, 64, 3, 1, False, 1, True),      # halo kernel (resident weights, one halo tile for all 9 taps), 8 tiles/image
+    (1, 48, 16, 128, 64, 3, 1, False, 1, True),     # halo kernel, two k-chunks, non-square
+    (3, 16, 16, 64, 128, 3, 1, False, 0, True),     # halo kernel BN = 128 (its dgrad: two k-chunks, BN = 64)
 ]
 
 
@@ -146,6 +149,24 @@ def test_conv_tc_fwd_dgrad_wgrad(case):
     assert rel_err(dx, gx) < BF16_TOL
     c.wgrad(xd, dyd, tc=True)
     assert rel_err(c.dw, gw) < BF16_TOL
+
+
+def test_conv_tc_halo_channel_slices():
+    """Halo kernel reading a channel slice of a wider buffer (the concat input of a decoder block) and writing into one."""
+    from shmgan_b200 import ops
+    N, H, W, Cin, Cout = 2, 32, 16, 64, 64
+    x = bf16_round(randn((N, H, W, Cin), 31))
+    w = bf16_round(randn((3, 3, Cin, Cout), 32, 0.05))
+    b = randn((Cout,), 33, 0.1).float().to(F64)
+    want = oracle_conv(x, w, b, 1, False, 1)
+    c = _mk_conv(Cin, Cout, 3, 1, False, 1, True, w, b)
+    xbuf = torch.full((N, H, W, 2 * Cin), 7.0, device="cuda", dtype=torch.bfloat16)
+    xbuf[..., Cin:] = dev(x, torch.bfloat16)
+    ybuf = torch.full((N, H, W, 2 * Cout), -3.0, device="cuda", dtype=torch.bfloat16)
+    c.fwd(xbuf[..., Cin:], ybuf[..., :Cout], tc=True, version=1)
+    torch.cuda.synchronize()
+    assert rel_err(ybuf[..., :Cout], want) < BF16_TOL
+    assert float((ybuf[..., Cout:].float() + 3.0).abs().max()) == 0.0
 
 
 def test_conv_tc_matches_simt_bf16_inputs():
