@@ -82,11 +82,12 @@ int shm_inorm_bwd_stats(const void* x, int N, int H, int W, int C, int ldx, int 
                         const void* dyA, int ldA, const void* dyP, int ldP, double* bsums, void* stream);
 int shm_inorm_bwd_apply(const void* x, int N, int H, int W, int C, int ldx, int dtype, const double* sums,
                         const float* gamma, float eps, const void* dyA, int ldA, const void* dyP, int ldP,
-                        const double* bsums, int act, void* dx, int lddx, void* stream);
+                        const double* bsums, int act, void* dx, int lddx,
+                        float* dbias /* may be NULL: dbias[c] += sum over pixels of dx = the producing conv's bias gradient */, void* stream);
 
 /* ---- pointwise ---- */
-/* dpre = dy * act'(y_post)   (LeakyReLU/ReLU derivative from the saved post-activation value) */
-int shm_act_bwd(const void* dy, int lddy, const void* y, int ldy, void* dpre, int ldd, int64_t npix, int C, int act, int dtype, void* stream);
+/* dpre = dy * act'(y_post)   (LeakyReLU/ReLU derivative from the saved post-activation value); dbias (may be NULL) += column sums of dpre */
+int shm_act_bwd(const void* dy, int lddy, const void* y, int ldy, void* dpre, int ldd, int64_t npix, int C, int act, int dtype, float* dbias, void* stream);
 /* MaxPooling2D(k) ShmGANwithSSpecSeg.py:406 (k=2), :358 (k=16); SpecSeg.py:38 */
 int shm_maxpool(const void* x, int N, int H, int W, int C, int ldx, int k, void* y, int ldy, int dtype, void* stream);
 /* Keras BatchNormalization at predict time (SpecSeg.py:37): y = (x-mean)*rsqrt(var+eps)*gamma+beta; optional fused MaxPool2 */

@@ -723,6 +723,169 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (warp == 1) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
 }
 
+// ------------------------------------------------------------------------------------------------
+// halo wgrad kernel: stride-1 3x3 Conv2D weight gradients (every 3x3 layer of the generator).
+//
+//   dW[ky][kx][ci][co] += sum_q x[q + (ky-1, kx-1), ci] * dy[q, co]
+//
+// The generic kernel above re-reads the x tile once per tap and the dy tile once per (tap, ci-block): at 128 x 128 x 64 per stage
+// it needs 128 B/clk/SM from L2 and runs at 220-600 TFLOP/s.  Here one TMA box brings the (16+2) x (8+2)-pixel halo of a
+// 16 x 8-pixel tile ONCE, and every tap is a shifted MN-major smem descriptor into it (start + (ty*10+tx) rows, 8-point K groups
+// SBO = 10 rows apart), against ONE dy tile.  All the taps a CTA owns accumulate in TMEM over the CTA's whole pixel range
+// (split-K over pixels across CTAs), then one vectorised red.global.add epilogue.
+//   MODE 0 (Cin or Cout == 64):  unit = (64 ci, 64 co), M = 128 = TWO TAPS (the second tap is LBO = tap distance away in the
+//           same halo), N = 64, five accumulators (taps 01 23 45 67 8-) = 320 TMEM columns; 39 KB of operands per 40 MMAs.
+//   MODE 1 (Cin, Cout % 128 == 0): unit = (128 ci, 128 co, one filter row), M = 128 = two 64-channel halos, N = 128,
+//           three accumulators = 384 TMEM columns; 72 KB of operands per 24 MMAs (47 B/clk/SM instead of 128).
+// ------------------------------------------------------------------------------------------------
+struct WhParams {
+    int units, splits;                 // grid = units * splits
+    int cblocks, nblocks;              // MODE 0: Cin/64, Cout/64;  MODE 1: Cin/128, Cout/128
+    int tiles_x, tiles_y, total_tiles, tiles_per_split;
+    int Cin, Cout;
+    float* dW;
+};
+
+template <int MODE>
+struct WhCfg {
+    static constexpr int A_ROWS = MODE == 0 ? 18 : 16;
+    static constexpr int A_ONE = MODE == 0 ? HALO_STAGE : 16 * HALO_W * 128;       // 23552 / 20480 (both multiples of 1024)
+    static constexpr int A_BYTES_TX = (MODE == 0 ? 1 : 2) * A_ROWS * HALO_W * 128;  // bytes TMA actually writes
+    static constexpr int A_ST = (MODE == 0 ? 1 : 2) * A_ONE;
+    static constexpr int B_ST = (MODE == 0 ? 1 : 2) * 16384;
+    static constexpr int STAGE_BYTES = A_ST + B_ST;
+    static constexpr int STAGES = MODE == 0 ? 5 : 3;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int BN = MODE == 0 ? 64 : 128;
+    static constexpr int NACC = MODE == 0 ? 5 : 3;
+};
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WhParams p) {
+    using Cfg = WhCfg<MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::STAGES * Cfg::A_ST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + Cfg::STAGES;
+    uint64_t* tfull = bars + 2 * Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x % p.units, split = blockIdx.x / p.units;
+    // unit -> (ci block, co block, filter row)
+    const int nb = unit % p.nblocks;
+    const int cb = (unit / p.nblocks) % p.cblocks;
+    const int frow = unit / (p.nblocks * p.cblocks);            // MODE 1 only (0..2)
+    const int t0 = split * p.tiles_per_split;
+    int t1 = t0 + p.tiles_per_split; if (t1 > p.total_tiles) t1 = p.total_tiles;
+    const int per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX); prefetch_tmap(&tmDY);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t0; t < t1; ++t) {
+                const int img = t / per_img; const int r = t - img * per_img;
+                const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+                mbar_wait(&empty[stage], phase ^ 1);
+                mbar_expect_tx(&full[stage], Cfg::A_BYTES_TX + Cfg::B_ST);
+                uint8_t* a = sA + stage * Cfg::A_ST;
+                uint8_t* b = sB + stage * Cfg::B_ST;
+                if (MODE == 0) {
+                    tma_load_4d(a, &tmX, &full[stage], cb * 64, x0 - 1, y0 - 1, img);
+                    tma_load_4d(b, &tmDY, &full[stage], nb * 64, x0, y0, img);
+                } else {
+                    tma_load_4d(a, &tmX, &full[stage], cb * 128, x0 - 1, y0 - 1 + frow, img);
+                    tma_load_4d(a + Cfg::A_ONE, &tmX, &full[stage], cb * 128 + 64, x0 - 1, y0 - 1 + frow, img);
+                    tma_load_4d(b, &tmDY, &full[stage], nb * 128, x0, y0, img);
+                    tma_load_4d(b + 16384, &tmDY, &full[stage], nb * 128 + 64, x0, y0, img);
+                }
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && t1 > t0) {
+            constexpr uint32_t idesc = make_idesc(128, Cfg::BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA + stage * Cfg::A_ST);
+                const uint32_t b0 = smem_u32(sB + stage * Cfg::B_ST);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {          // 16 pixels = tile rows 2j, 2j+1 per MMA
+                    const uint64_t bdesc = make_desc_sw128(b0 + j * 2048, 16384, 1024);
+                    const uint32_t acc = (t > t0 || j > 0) ? 1u : 0u;
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int pr = 0; pr < 5; ++pr) {
+                            const int ta = 2 * pr, tb = pr < 4 ? 2 * pr + 1 : 8;
+                            const int offa = (ta / 3) * HALO_W + ta % 3, offb = (tb / 3) * HALO_W + tb % 3;
+                            const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(2 * j * HALO_W + offa) * 128u, (uint32_t)(offb - offa) * 128u, HALO_W * 128);
+                            umma_bf16(tmem_base + pr * 64, adesc, bdesc, idesc, acc);
+                        }
+                    } else {
+#pragma unroll
+                        for (int tx = 0; tx < 3; ++tx) {
+                            const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(2 * j * HALO_W + tx) * 128u, Cfg::A_ONE, HALO_W * 128);
+                            umma_bf16(tmem_base + tx * 128, adesc, bdesc, idesc, acc);
+                        }
+                    }
+                }
+                umma_commit(&empty[stage]);
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tfull);
+        }
+    } else if (t1 > t0) {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int a = 0; a < Cfg::NACC; ++a) {
+            int tap, ci;
+            bool ok = true;
+            if (MODE == 0) { tap = 2 * a + (row >> 6); ci = cb * 64 + (row & 63); ok = tap < 9; }
+            else { tap = frow * 3 + a; ci = cb * 128 + row; }
+            float* dst = p.dW + ((long long)tap * p.Cin + ci) * p.Cout + nb * Cfg::BN;
+#pragma unroll 1
+            for (int c = 0; c < Cfg::BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * Cfg::BN + c * 32), r);
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        red_add_v4(dst + c * 32 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 bool pick_box64(int N, int Qh, int Qw, int& BW, int& BH, int& BI) {
     BW = Qw >= 64 ? 64 : Qw;
     if (BW <= 0 || 64 % BW != 0 || Qw % BW != 0) return false;
@@ -746,6 +909,48 @@ __global__ void prep_w_kernel(const float* __restrict__ w, bf16* __restrict__ o,
         const float v = (k < k_real && n < n_real) ? __ldg(w + tap * tap_elems + (long long)k * w_ks + (long long)n * w_ns) : 0.f;
         o[i] = __float2bfloat16_rn(v);
     }
+}
+
+bool wgrad_halo_ok(const shm_conv_desc* d) {
+    return !d->transposed && d->stride == 1 && d->kh == 3 && d->kw == 3 && d->H % 16 == 0 && d->W % 8 == 0 &&
+           d->Cin % 64 == 0 && d->Cout % 64 == 0;
+}
+
+template <int MODE>
+int launch_wgrad_halo_t(const CUtensorMap& tmX, const CUtensorMap& tmDY, const WhParams& p, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(wgrad_halo_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, WhCfg<MODE>::SMEM); attr = true; }
+    wgrad_halo_kernel<MODE><<<p.units * p.splits, TC_THREADS, WhCfg<MODE>::SMEM, st>>>(tmX, tmDY, p);
+    SHM_CHECK_LAUNCH("wgrad_halo_kernel");
+    return SHM_OK;
+}
+
+int launch_wgrad_halo(const shm_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    WhParams p{};
+    const int mode = (d->Cin % 128 == 0 && d->Cout % 128 == 0) ? 1 : 0;
+    p.cblocks = d->Cin / (mode ? 128 : 64);
+    p.nblocks = d->Cout / (mode ? 128 : 64);
+    p.units = p.cblocks * p.nblocks * (mode ? 3 : 1);
+    p.tiles_x = d->W / 8; p.tiles_y = d->H / 16;
+    p.total_tiles = d->N * p.tiles_x * p.tiles_y;
+    p.Cin = d->Cin; p.Cout = d->Cout; p.dW = dw;
+    // split the pixel range so that the grid fills whole waves of SMs; the epilogue (TMEM -> red.add) costs about 6 tiles
+    const int sms = shm_num_sms();
+    long long best_cost = -1; int best_s = 1;
+    const int smax = p.total_tiles < 4 * sms ? p.total_tiles : 4 * sms;
+    for (int s = 1; s <= smax; ++s) {
+        const long long ctas = (long long)p.units * s;
+        if (ctas > 4LL * sms && s > 1) break;
+        const long long waves = (ctas + sms - 1) / sms;
+        const long long cost = waves * (cdiv(p.total_tiles, s) + 6);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s; }
+    }
+    p.tiles_per_split = cdiv(p.total_tiles, best_s);
+    p.splits = cdiv(p.total_tiles, p.tiles_per_split);
+    CUtensorMap tmX, tmDY;
+    if (int rc = encode_act_box(&tmX, x, d->Cin, d->W, d->H, d->N, d->ldx, HALO_W, mode ? 16 : 18)) return rc;
+    if (int rc = encode_act_box(&tmDY, dy, d->Cout, d->W, d->H, d->N, d->ldy, 8, 16)) return rc;
+    return mode ? launch_wgrad_halo_t<1>(tmX, tmDY, p, st) : launch_wgrad_halo_t<0>(tmX, tmDY, p, st);
 }
 
 int tc_check(const shm_conv_desc* d) {
@@ -914,6 +1119,7 @@ extern "C" int shm_conv2d_tc_wgrad(const shm_conv_desc* d, const void* x, const 
                 p.woff[t] = (long long)(ky * d->kw + kx) * d->Cin * d->Cout;
             }
     }
+    if (wgrad_halo_ok(d)) return launch_wgrad_halo(d, x, dy, dw, st);
     if (!pick_box64(d->N, p.Qh, p.Qw, p.BW, p.BH, p.BI)) SHM_FAIL(SHM_EUNSUPPORTED, "wgrad_tc: lattice %dx%d does not tile into 64-point boxes", p.Qh, p.Qw);
     p.tiles_x = p.Qw / p.BW; p.tiles_y = p.Qh / p.BH;
     p.cblocks = Ca / 64;

@@ -220,6 +220,339 @@ __global__ void __launch_bounds__(256) inorm_bwd_apply_kernel(const T* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// bf16 fast paths: 8 channels (one 16-byte access) per thread, 4 pixels in flight per thread.
+// The generic kernels above move 8 bytes per access with one load in flight and reach ~35 % of the HBM roofline
+// (profiles/r01_launches_halo.txt); these serve every instance-norm tensor of the bf16 training step
+// (C in {64..1024}: C/8 is a power of two <= 256, 16-byte aligned channel slices).
+// ---------------------------------------------------------------------------------------------
+struct f8 { float v[8]; };
+__device__ __forceinline__ f8 ld8(const bf16* p) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    f8 r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+        r.v[2 * i] = f.x; r.v[2 * i + 1] = f.y;
+    }
+    return r;
+}
+__device__ __forceinline__ void st8(bf16* p, const f8& a) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(a.v[2 * i], a.v[2 * i + 1]);
+        w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ f8 load_dy8(const bf16* dyA, int ldA, const bf16* dyP, int ldP, int W, int p) {
+    f8 d;
+    if (dyA) d = ld8(dyA + (long long)p * ldA);
+    else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = 0.f;
+    }
+    if (dyP) {
+        const int y = p / W, xx = p - y * W;
+        const f8 e = ld8(dyP + ((long long)(y >> 1) * (W >> 1) + (xx >> 1)) * ldP);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d.v[j] = fmaf(0.25f, e.v[j], d.v[j]);
+    }
+    return d;
+}
+
+// block reduction of NV partial columns per thread over the TY pixel lanes; calls sink(column c8*8 + j-th value index, total)
+template <int NV, typename Sink>
+__device__ __forceinline__ void reduce_lanes(const float* vals, int TX, float (*red)[NV + 1], Sink sink) {
+    const int TY = 256 / TX;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) red[threadIdx.x][j] = vals[j];
+    __syncthreads();
+    for (int e = threadIdx.x; e < TX * NV; e += 256) {
+        const int t = e / NV, j = e % NV;
+        float acc = 0.f;
+        for (int y = 0; y < TY; ++y) acc += red[y * TX + t][j];
+        sink(t, j, acc);
+    }
+}
+
+__global__ void __launch_bounds__(256) inorm_stats8_kernel(const bf16* __restrict__ x, int HW, int C, int ldx,
+                                                           double* __restrict__ sums, int ppb, int TX) {
+    __shared__ float red[256][17];
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int n = blockIdx.z;
+    const int pbeg = blockIdx.x * ppb, pend = min(pbeg + ppb, HW);
+    float a[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a[j] = 0.f;
+    const bf16* xb = x + (long long)n * HW * ldx + tx * 8;
+    int p = pbeg + ty;
+    for (; p + 3 * TY < pend; p += 4 * TY) {
+        f8 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ld8(xb + (long long)(p + u * TY) * ldx);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] += v[u].v[j]; a[8 + j] = fmaf(v[u].v[j], v[u].v[j], a[8 + j]); }
+    }
+    for (; p < pend; p += TY) {
+        const f8 v = ld8(xb + (long long)p * ldx);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] += v.v[j]; a[8 + j] = fmaf(v.v[j], v.v[j], a[8 + j]); }
+    }
+    reduce_lanes<16>(a, TX, red, [&](int t, int j, float acc) {
+        atomicAdd(&sums[((long long)n * C + t * 8 + (j & 7)) * 2 + (j >> 3)], (double)acc);
+    });
+}
+
+template <bool POOL>
+__global__ void __launch_bounds__(256) inorm_apply8_kernel(const bf16* __restrict__ x, int H, int W, int C, int ldx,
+        const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+        const bf16* __restrict__ add, int ldadd, int nadd, bf16* __restrict__ out, int ldo, bf16* __restrict__ pooled, int ldp,
+        int upb, int TX) {
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int n = blockIdx.z;
+    const int c0 = tx * 8;
+    const int HW = H * W;
+    float a[8], b[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float mean, rstd;
+        stat_ab(sums, n, C, c0 + j, HW, eps, mean, rstd);
+        a[j] = rstd * __ldg(gamma + c0 + j);
+        b[j] = __ldg(beta + c0 + j) - mean * a[j];
+    }
+    const bf16* xb = x + (long long)n * HW * ldx + c0;
+    bf16* ob = out ? out + (long long)n * HW * ldo + c0 : nullptr;
+    const bf16* ab = add ? add + (long long)(n % nadd) * HW * ldadd + c0 : nullptr;
+    if (POOL) {
+        const int Wq = W / 2, nunits = (H / 2) * Wq;
+        bf16* pb = pooled + (long long)n * nunits * ldp + c0;
+        const int ubeg = blockIdx.x * upb, uend = min(ubeg + upb, nunits);
+        for (int u = ubeg + ty; u < uend; u += TY) {
+            const int qy = u / Wq, qx = u - qy * Wq;
+            long long pp[4];
+            f8 v[4], r[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                pp[i] = (long long)(2 * qy + (i >> 1)) * W + 2 * qx + (i & 1);
+                v[i] = ld8(xb + pp[i] * ldx);
+                if (ab && ob) r[i] = ld8(ab + pp[i] * ldadd);
+            }
+            f8 acc;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                f8 y;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { y.v[j] = fmaf(v[i].v[j], a[j], b[j]); acc.v[j] += y.v[j]; }
+                if (ob) {
+                    if (ab) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) y.v[j] += r[i].v[j];
+                    }
+                    st8(ob + pp[i] * ldo, y);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc.v[j] *= 0.25f;
+            st8(pb + (long long)u * ldp, acc);
+        }
+    } else {
+        const int ubeg = blockIdx.x * upb, uend = min(ubeg + upb, HW);
+        int p = ubeg + ty;
+        for (; p + 3 * TY < uend; p += 4 * TY) {
+            f8 v[4], r[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                v[u] = ld8(xb + (long long)(p + u * TY) * ldx);
+                if (ab) r[u] = ld8(ab + (long long)(p + u * TY) * ldadd);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                f8 y;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { y.v[j] = fmaf(v[u].v[j], a[j], b[j]); if (ab) y.v[j] += r[u].v[j]; }
+                st8(ob + (long long)(p + u * TY) * ldo, y);
+            }
+        }
+        for (; p < uend; p += TY) {
+            const f8 v = ld8(xb + (long long)p * ldx);
+            f8 y;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) y.v[j] = fmaf(v.v[j], a[j], b[j]);
+            if (ab) {
+                const f8 r = ld8(ab + (long long)p * ldadd);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) y.v[j] += r.v[j];
+            }
+            st8(ob + (long long)p * ldo, y);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) inorm_bwd_stats8_kernel(const bf16* __restrict__ x, int H, int W, int C, int ldx,
+        const double* __restrict__ sums, float eps, const bf16* __restrict__ dyA, int ldA, const bf16* __restrict__ dyP, int ldP,
+        double* __restrict__ bsums, int ppb, int TX) {
+    __shared__ float red[256][17];
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int n = blockIdx.z;
+    const int HW = H * W;
+    const int c0 = tx * 8;
+    const int pbeg = blockIdx.x * ppb, pend = min(pbeg + ppb, HW);
+    float mean[8], rstd[8], a[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { stat_ab(sums, n, C, c0 + j, HW, eps, mean[j], rstd[j]); a[j] = 0.f; a[8 + j] = 0.f; }
+    const bf16* xb = x + (long long)n * HW * ldx + c0;
+    const bf16* da = dyA ? dyA + (long long)n * HW * ldA + c0 : nullptr;
+    const bf16* dp = dyP ? dyP + (long long)n * (HW / 4) * ldP + c0 : nullptr;
+    int p = pbeg + ty;
+    for (; p + 3 * TY < pend; p += 4 * TY) {
+        f8 v[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { v[u] = ld8(xb + (long long)(p + u * TY) * ldx); d[u] = load_dy8(da, ldA, dp, ldP, W, p + u * TY); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { a[j] += d[u].v[j]; a[8 + j] = fmaf(d[u].v[j], v[u].v[j] - mean[j], a[8 + j]); }
+    }
+    for (; p < pend; p += TY) {
+        const f8 v = ld8(xb + (long long)p * ldx);
+        const f8 d = load_dy8(da, ldA, dp, ldP, W, p);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] += d.v[j]; a[8 + j] = fmaf(d.v[j], v.v[j] - mean[j], a[8 + j]); }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[8 + j] *= rstd[j];          // sum dy * xhat
+    reduce_lanes<16>(a, TX, red, [&](int t, int j, float acc) {
+        atomicAdd(&bsums[((long long)n * C + t * 8 + (j & 7)) * 2 + (j >> 3)], (double)acc);
+    });
+}
+
+// dx = act'(x) * rstd*gamma*(dy - mean(dy) - xhat*mean(dy*xhat)); dbias[c] += sum over pixels of dx (the producing conv's bias
+// gradient, ShmGANwithSSpecSeg.py:244: the conv bias sits right behind this tensor) when dbias != NULL
+__global__ void __launch_bounds__(256) inorm_bwd_apply8_kernel(const bf16* __restrict__ x, int H, int W, int C, int ldx,
+        const double* __restrict__ sums, const float* __restrict__ gamma, float eps,
+        const bf16* __restrict__ dyA, int ldA, const bf16* __restrict__ dyP, int ldP, const double* __restrict__ bsums, int act,
+        bf16* __restrict__ dx, int lddx, float* __restrict__ dbias, int ppb, int TX) {
+    __shared__ float red[256][9];
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int n = blockIdx.z;
+    const int HW = H * W;
+    const int c0 = tx * 8;
+    // r = g * (k0 + k1 * d + k2 * v) with g = act'(v):  a*(d - m1 - (v-mean)*rstd*m2)
+    float k0[8], k1[8], k2[8], s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float mean, rstd;
+        stat_ab(sums, n, C, c0 + j, HW, eps, mean, rstd);
+        const float a = rstd * __ldg(gamma + c0 + j);
+        const float m1 = (float)(bsums[((long long)n * C + c0 + j) * 2 + 0] / HW);
+        const float m2 = (float)(bsums[((long long)n * C + c0 + j) * 2 + 1] / HW);
+        k1[j] = a; k2[j] = -a * rstd * m2; k0[j] = -a * m1 + a * rstd * m2 * mean;
+        s[j] = 0.f;
+    }
+    const float neg = act == SHM_ACT_LRELU ? 0.2f : (act == SHM_ACT_RELU ? 0.f : 1.f);
+    const bf16* xb = x + (long long)n * HW * ldx + c0;
+    const bf16* da = dyA ? dyA + (long long)n * HW * ldA + c0 : nullptr;
+    const bf16* dp = dyP ? dyP + (long long)n * (HW / 4) * ldP + c0 : nullptr;
+    bf16* ob = dx + (long long)n * HW * lddx + c0;
+    const int pbeg = blockIdx.x * ppb, pend = min(pbeg + ppb, HW);
+    int p = pbeg + ty;
+    for (; p + 3 * TY < pend; p += 4 * TY) {
+        f8 v[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { v[u] = ld8(xb + (long long)(p + u * TY) * ldx); d[u] = load_dy8(da, ldA, dp, ldP, W, p + u * TY); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            f8 r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float g = v[u].v[j] > 0.f ? 1.f : neg;
+                r.v[j] = g * fmaf(k2[j], v[u].v[j], fmaf(k1[j], d[u].v[j], k0[j]));
+                s[j] += r.v[j];
+            }
+            st8(ob + (long long)(p + u * TY) * lddx, r);
+        }
+    }
+    for (; p < pend; p += TY) {
+        const f8 v = ld8(xb + (long long)p * ldx);
+        const f8 d = load_dy8(da, ldA, dp, ldP, W, p);
+        f8 r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float g = v.v[j] > 0.f ? 1.f : neg;
+            r.v[j] = g * fmaf(k2[j], v.v[j], fmaf(k1[j], d.v[j], k0[j]));
+            s[j] += r.v[j];
+        }
+        st8(ob + (long long)p * lddx, r);
+    }
+    if (dbias != nullptr)
+        reduce_lanes<8>(s, TX, red, [&](int t, int j, float acc) { atomicAdd(dbias + t * 8 + j, acc); });
+}
+
+// dpre = dy * act'(y) with the bias gradient fused: dbias[c] += sum over pixels of dpre
+__global__ void __launch_bounds__(256) act_bwd8_kernel(const bf16* __restrict__ dy, int lddy, const bf16* __restrict__ y, int ldy,
+        bf16* __restrict__ dpre, int ldd, long long npix, int act, float* __restrict__ dbias, int ppb, int TX) {
+    __shared__ float red[256][9];
+    const int TY = 256 / TX;
+    const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+    const int c0 = tx * 8;
+    const float neg = act == SHM_ACT_LRELU ? 0.2f : (act == SHM_ACT_RELU ? 0.f : 1.f);
+    float s[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = 0.f;
+    const long long pbeg = (long long)blockIdx.x * ppb;
+    long long pend = pbeg + ppb; if (pend > npix) pend = npix;
+    long long p = pbeg + ty;
+    for (; p + 3 * TY < pend; p += 4 * TY) {
+        f8 v[4], d[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { v[u] = ld8(y + (p + u * TY) * ldy + c0); d[u] = ld8(dy + (p + u * TY) * lddy + c0); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            f8 r;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { r.v[j] = d[u].v[j] * (v[u].v[j] > 0.f ? 1.f : neg); s[j] += r.v[j]; }
+            st8(dpre + (p + u * TY) * ldd + c0, r);
+        }
+    }
+    for (; p < pend; p += TY) {
+        const f8 v = ld8(y + p * ldy + c0), d = ld8(dy + p * lddy + c0);
+        f8 r;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { r.v[j] = d.v[j] * (v.v[j] > 0.f ? 1.f : neg); s[j] += r.v[j]; }
+        st8(dpre + p * ldd + c0, r);
+    }
+    if (dbias != nullptr)
+        reduce_lanes<8>(s, TX, red, [&](int t, int j, float acc) { atomicAdd(dbias + t * 8 + j, acc); });
+}
+
+// the fast paths serve bf16 tensors whose channel count is 8 * 2^k <= 2048 with 16-byte aligned pixels
+inline bool fast8_ok(int dtype, int C) {
+    if (dtype != SHM_BF16 || C % 8 != 0) return false;
+    const int tx = C / 8;
+    return tx <= 256 && (tx & (tx - 1)) == 0;
+}
+inline bool al16(const void* p, int ld) { return p == nullptr || (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && ld % 8 == 0); }
+inline int ppb8(long long units, int TY, int N) {
+    long long want = (long long)shm_num_sms() * 8 / (N > 0 ? N : 1);
+    if (want < 1) want = 1;
+    long long upb = cdiv64(units, want);
+    const long long lo = (long long)TY * 8, hi = (long long)TY * 128;
+    if (upb < lo) upb = lo;
+    if (upb > hi) upb = hi;
+    return (int)upb;
+}
+
+// ---------------------------------------------------------------------------------------------
 // BatchNorm(eval) + optional MaxPool2 (SpecSeg.py:37-38)
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool POOL>
@@ -398,6 +731,12 @@ inline int units_per_block(long long units, int TY, int other_blocks) {
 extern "C" int shm_inorm_stats(const void* x, int N, int HW, int C, int ldx, int dtype, double* sums, void* stream) {
     SHM_REQUIRE(x && sums && N > 0 && HW > 0 && C > 0 && ldx >= C, "shm_inorm_stats: bad args");
     SHM_REQUIRE(C % 4 == 0, "shm_inorm_stats: C=%d must be a multiple of 4", C);
+    if (fast8_ok(dtype, C) && al16(x, ldx)) {
+        const int TX = C / 8, pp = ppb8(HW, 256 / TX, N);
+        inorm_stats8_kernel<<<dim3(cdiv(HW, pp), 1, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, HW, C, ldx, sums, pp, TX);
+        SHM_CHECK_LAUNCH("inorm_stats8_kernel");
+        return SHM_OK;
+    }
     const CG g = cgeom(C);
     const int ppb = units_per_block(HW, g.TY, g.tiles * N);
     dim3 grid(cdiv(HW, ppb), g.tiles, N);
@@ -419,6 +758,16 @@ extern "C" int shm_inorm_apply(const void* x, int N, int H, int W, int C, int ld
     SHM_REQUIRE(!add || out, "shm_inorm_apply: add without out");
     if (nadd <= 0) nadd = N;
     SHM_REQUIRE(N % nadd == 0, "shm_inorm_apply: N %% nadd != 0");
+    if (fast8_ok(dtype, C) && al16(x, ldx) && al16(add, ldadd) && al16(out, ldo) && al16(pooled, ldp)) {
+        const int TX = C / 8;
+        const long long un = pooled ? (long long)(H / 2) * (W / 2) : (long long)H * W;
+        const int pp = ppb8(un, 256 / TX, N);
+        dim3 grid8((unsigned)cdiv64(un, pp), 1, N);
+        if (pooled) inorm_apply8_kernel<true><<<grid8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, ldx, sums, gamma, beta, eps, (const bf16*)add, ldadd, nadd, (bf16*)out, ldo, (bf16*)pooled, ldp, pp, TX);
+        else        inorm_apply8_kernel<false><<<grid8, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, ldx, sums, gamma, beta, eps, (const bf16*)add, ldadd, nadd, (bf16*)out, ldo, nullptr, 0, pp, TX);
+        SHM_CHECK_LAUNCH("inorm_apply8_kernel");
+        return SHM_OK;
+    }
     const CG g = cgeom(C);
     const long long units = pooled ? (long long)(H / 2) * (W / 2) : (long long)H * W;
     const int upb = units_per_block(units, g.TY, g.tiles * N);
@@ -439,6 +788,12 @@ extern "C" int shm_inorm_bwd_stats(const void* x, int N, int H, int W, int C, in
     SHM_REQUIRE(x && sums && bsums && (dyA || dyP) && N > 0 && H > 0 && W > 0, "shm_inorm_bwd_stats: bad args");
     SHM_REQUIRE(C % 4 == 0, "shm_inorm_bwd_stats: C=%d must be a multiple of 4", C);
     SHM_REQUIRE(!dyP || (H % 2 == 0 && W % 2 == 0), "shm_inorm_bwd_stats: pooled gradient needs even H, W");
+    if (fast8_ok(dtype, C) && al16(x, ldx) && al16(dyA, ldA) && al16(dyP, ldP)) {
+        const int TX = C / 8, pp = ppb8((long long)H * W, 256 / TX, N);
+        inorm_bwd_stats8_kernel<<<dim3(cdiv(H * W, pp), 1, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, ldx, sums, eps, (const bf16*)dyA, ldA, (const bf16*)dyP, ldP, bsums, pp, TX);
+        SHM_CHECK_LAUNCH("inorm_bwd_stats8_kernel");
+        return SHM_OK;
+    }
     const CG g = cgeom(C);
     const int ppb = units_per_block((long long)H * W, g.TY, g.tiles * N);
     dim3 grid(cdiv(H * W, ppb), g.tiles, N);
@@ -452,10 +807,16 @@ extern "C" int shm_inorm_bwd_stats(const void* x, int N, int H, int W, int C, in
 
 extern "C" int shm_inorm_bwd_apply(const void* x, int N, int H, int W, int C, int ldx, int dtype, const double* sums,
                                    const float* gamma, float eps, const void* dyA, int ldA, const void* dyP, int ldP,
-                                   const double* bsums, int act, void* dx, int lddx, void* stream) {
+                                   const double* bsums, int act, void* dx, int lddx, float* dbias, void* stream) {
     SHM_REQUIRE(x && sums && gamma && bsums && dx && (dyA || dyP) && N > 0 && H > 0 && W > 0, "shm_inorm_bwd_apply: bad args");
     SHM_REQUIRE(C % 4 == 0, "shm_inorm_bwd_apply: C=%d must be a multiple of 4", C);
     SHM_REQUIRE(!dyP || (H % 2 == 0 && W % 2 == 0), "shm_inorm_bwd_apply: pooled gradient needs even H, W");
+    if (fast8_ok(dtype, C) && al16(x, ldx) && al16(dyA, ldA) && al16(dyP, ldP) && al16(dx, lddx) && act != SHM_ACT_SIGMOID) {
+        const int TX = C / 8, pp = ppb8((long long)H * W, 256 / TX, N);
+        inorm_bwd_apply8_kernel<<<dim3(cdiv(H * W, pp), 1, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, ldx, sums, gamma, eps, (const bf16*)dyA, ldA, (const bf16*)dyP, ldP, bsums, act, (bf16*)dx, lddx, dbias, pp, TX);
+        SHM_CHECK_LAUNCH("inorm_bwd_apply8_kernel");
+        return SHM_OK;
+    }
     const CG g = cgeom(C);
     const int ppb = units_per_block((long long)H * W, g.TY, g.tiles * N);
     dim3 grid(cdiv(H * W, ppb), g.tiles, N);
@@ -464,6 +825,7 @@ extern "C" int shm_inorm_bwd_apply(const void* x, int N, int H, int W, int C, in
         REQ_VEC(dyP, ldP, T, "shm_inorm_bwd_apply"); REQ_VEC(dx, lddx, T, "shm_inorm_bwd_apply");
         inorm_bwd_apply_kernel<T><<<grid, 256, 0, (cudaStream_t)stream>>>((const T*)x, H, W, C, ldx, sums, gamma, eps, (const T*)dyA, ldA, (const T*)dyP, ldP, bsums, act, (T*)dx, lddx, ppb, g.TX);
         SHM_CHECK_LAUNCH("inorm_bwd_apply_kernel");
+        if (dbias) return shm_colsum(dx, (int64_t)N * H * W, C, lddx, dtype, dbias, stream);
         return SHM_OK;
     })
 }
@@ -488,16 +850,23 @@ extern "C" int shm_bn_eval(const void* x, int N, int H, int W, int C, int ldx, i
 }
 
 extern "C" int shm_act_bwd(const void* dy, int lddy, const void* y, int ldy, void* dpre, int ldd, int64_t npix, int C, int act,
-                           int dtype, void* stream) {
+                           int dtype, float* dbias, void* stream) {
     SHM_REQUIRE(dy && y && dpre && npix >= 0 && C > 0, "shm_act_bwd: bad args");
     if (npix == 0) return SHM_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (fast8_ok(dtype, C) && al16(dy, lddy) && al16(y, ldy) && al16(dpre, ldd) && act != SHM_ACT_SIGMOID) {
+        const int TX = C / 8, pp = ppb8(npix, 256 / TX, 1);
+        act_bwd8_kernel<<<(unsigned)cdiv64(npix, pp), 256, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (bf16*)dpre, ldd, npix, act, dbias, pp, TX);
+        SHM_CHECK_LAUNCH("act_bwd8_kernel");
+        return SHM_OK;
+    }
     DISPATCH_DTYPE(dtype, T, {
         if (C % 4 == 0 && vec_ok(dy, lddy, sizeof(T)) && vec_ok(y, ldy, sizeof(T)) && vec_ok(dpre, ldd, sizeof(T)))
             act_bwd_vec_kernel<T><<<flat_grid(npix * (C / 4)), 256, 0, st>>>((const T*)dy, lddy, (const T*)y, ldy, (T*)dpre, ldd, npix, C / 4, act);
         else
             act_bwd_kernel<T><<<flat_grid(npix * C), 256, 0, st>>>((const T*)dy, lddy, (const T*)y, ldy, (T*)dpre, ldd, npix, C, act);
         SHM_CHECK_LAUNCH("act_bwd_kernel");
+        if (dbias) return shm_colsum(dpre, npix, C, ldd, dtype, dbias, stream);
         return SHM_OK;
     })
 }

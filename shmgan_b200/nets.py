@@ -280,11 +280,11 @@ class Generator:
         for lvl in range(4):
             pooled, a1, a2 = saved[lvl]
             ca, cb = self.attn[lvl]
-            d2 = ops.act_bwd(dattn[lvl], a2, ACT_LRELU)
-            cb.wgrad(a1, d2, self.tc)
+            d2 = ops.act_bwd(dattn[lvl], a2, ACT_LRELU, dbias=cb.db)
+            cb.wgrad(a1, d2, self.tc, bias_done=True)
             d1 = cb.dgrad(d2, a1.shape, None, self.tc, self.store.version)
-            d1 = ops.act_bwd(d1, a1, ACT_LRELU)
-            ca.wgrad(pooled, d1, self.tc)
+            d1 = ops.act_bwd(d1, a1, ACT_LRELU, dbias=ca.db)
+            ca.wgrad(pooled, d1, self.tc, bias_done=True)
 
     def forward(self, x: torch.Tensor, attn: Optional[List[torch.Tensor]] = None, save: bool = False):
         """x [B,S,S,10] (self.dtype; or already zero-padded to [B,S,S,64] in tensor-core mode) -> y [B,S,S,1].
@@ -336,8 +336,8 @@ class Generator:
         return y
 
     def _cli_bwd(self, blk: _CLI, x_in, z, sums, dyA=None, dyP=None, need_dx=True):
-        dpre = ops.inorm_bwd(z, sums, blk.gamma, dyA, dyP, ACT_LRELU)
-        blk.conv.wgrad(x_in, dpre, self.tc)
+        dpre = ops.inorm_bwd(z, sums, blk.gamma, dyA, dyP, ACT_LRELU, dbias=blk.conv.db if blk.conv.has_bias else None)
+        blk.conv.wgrad(x_in, dpre, self.tc, bias_done=True)
         if not need_dx:
             return None
         return blk.conv.dgrad(dpre, x_in.shape, None, self.tc, self.store.version)
@@ -361,8 +361,8 @@ class Generator:
             C = cat.shape[3] // 2
             dya = self._cli_bwd(b, ya, zb, sb, dyA=dh)
             dcat = self._cli_bwd(a, cat, za, sa, dyA=dya)
-            dup = ops.act_bwd(dcat[..., :C], cat[..., :C], ACT_LRELU)
-            self.up[u].wgrad(hin, dup, self.tc)
+            dup = ops.act_bwd(dcat[..., :C], cat[..., :C], ACT_LRELU, dbias=self.up[u].db)
+            self.up[u].wgrad(hin, dup, self.tc, bias_done=True)
             dh = self.up[u].dgrad(dup, hin.shape, None, self.tc, v)
             dskips[3 - u] = dcat[..., C:]
         for i in (1, 0):
@@ -422,11 +422,11 @@ class Discriminator:
 
     def attention_backward(self, saved, dattn):
         pooled, a1, a2 = saved
-        d2 = ops.act_bwd(dattn, a2, ACT_LRELU)
-        self.attn[1].wgrad(a1, d2, self.tc)
+        d2 = ops.act_bwd(dattn, a2, ACT_LRELU, dbias=self.attn[1].db)
+        self.attn[1].wgrad(a1, d2, self.tc, bias_done=True)
         d1 = self.attn[1].dgrad(d2, a1.shape, None, self.tc, self.store.version)
-        d1 = ops.act_bwd(d1, a1, ACT_LRELU)
-        self.attn[0].wgrad(pooled, d1, self.tc)
+        d1 = ops.act_bwd(d1, a1, ACT_LRELU, dbias=self.attn[0].db)
+        self.attn[0].wgrad(pooled, d1, self.tc, bias_done=True)
 
     def forward(self, x, attn=None, noise=None, keep=None, save=False):
         """x [B,S,S,3] -> (rf [B,S/32,S/32,1], cls [B,5] fp32).  noise / keep: the GaussianNoise(0.1) / Dropout(0.2)

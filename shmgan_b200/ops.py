@@ -187,8 +187,9 @@ class Conv:
             _prof("simt", "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_dgrad", C.byref(d), _p(dy), _p(self.w), _p(dx), 0, _stream()))
         return dx
 
-    def wgrad(self, x: torch.Tensor, dy: torch.Tensor, tc: bool = True):
-        """dw += , db += (gradients accumulate: weights are shared by several passes)."""
+    def wgrad(self, x: torch.Tensor, dy: torch.Tensor, tc: bool = True, bias_done: bool = False):
+        """dw += , db += (gradients accumulate: weights are shared by several passes).
+        bias_done: db was already accumulated by the kernel that produced dy (inorm_bwd / act_bwd with dbias=)."""
         n, h, w, cx = x.shape
         pad = self.padded(cx)
         d = self.desc(n, h, w, ld(x), ld(dy), dt(x), ACT_NONE, cin=self.cin_pad if pad else None)
@@ -202,10 +203,10 @@ class Conv:
             dw = self.dw_pad
         if tc and self.tc_ok(d):
             _prof("tc", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(dw), _stream()))
-            if self.has_bias:
+            if self.has_bias and not bias_done:
                 call("shm_colsum", _p(dy), dy.shape[0] * dy.shape[1] * dy.shape[2], self.cout, ld(dy), dt(dy), _p(self.db), _stream())
         else:
-            _prof("simt", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _p(self.db) if self.has_bias else None, _stream()))
+            _prof("simt", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_wgrad", C.byref(d), _p(x), _p(dy), _p(self.dw), _p(self.db) if (self.has_bias and not bias_done) else None, _stream()))
 
     def pw1_bwd(self, x, dy, y, need_dx=True):
         """Fused backward of the 1x1 -> 1 channel layer: activation derivative, dx, dw +=, db += in one pass."""
@@ -249,23 +250,25 @@ def inorm_apply(x, sums, gamma, beta, add=None, out=None, pooled=False, want_out
     return out, pl
 
 
-def inorm_bwd(x, sums, gamma, dyA=None, dyP=None, act=ACT_LRELU, dx=None):
-    """dL/d(pre-activation of the producing conv) from dL/dy, y = IN(x), x = post-activation conv output."""
+def inorm_bwd(x, sums, gamma, dyA=None, dyP=None, act=ACT_LRELU, dx=None, dbias=None):
+    """dL/d(pre-activation of the producing conv) from dL/dy, y = IN(x), x = post-activation conv output.
+    dbias (fp32 [C], optional) += column sums of the result: the producing conv's bias gradient, fused into the same pass."""
     n, h, w, c = x.shape
     bs = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
     call("shm_inorm_bwd_stats", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), IN_EPS, _p(dyA), ld(dyA), _p(dyP), ld(dyP), _p(bs), _stream())
     if dx is None:
         dx = new((n, h, w, c), x.dtype)
     call("shm_inorm_bwd_apply", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), _p(gamma), IN_EPS, _p(dyA), ld(dyA), _p(dyP), ld(dyP),
-         _p(bs), act, _p(dx), ld(dx), _stream())
+         _p(bs), act, _p(dx), ld(dx), _p(dbias), _stream())
     return dx
 
 
-def act_bwd(dy, y, act, out=None):
+def act_bwd(dy, y, act, out=None, dbias=None):
+    """dpre = dy * act'(y); dbias (fp32 [C], optional) += column sums of dpre (the conv's bias gradient, same pass)."""
     n, h, w, c = y.shape
     if out is None:
         out = new((n, h, w, c), y.dtype)
-    call("shm_act_bwd", _p(dy), ld(dy), _p(y), ld(y), _p(out), ld(out), n * h * w, c, act, dt(y), _stream())
+    call("shm_act_bwd", _p(dy), ld(dy), _p(y), ld(y), _p(out), ld(out), n * h * w, c, act, dt(y), _p(dbias), _stream())
     return out
 
 

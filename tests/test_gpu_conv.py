@@ -119,6 +119,9 @@ TC_CASES = [
     (2, 32, 32, 64, 64, 3, 1, False, 1, True),      # halo kernel (resident weights, one halo tile for all 9 taps), 8 tiles/image
     (1, 48, 16, 128, 64, 3, 1, False, 1, True),     # halo kernel, two k-chunks, non-square
     (3, 16, 16, 64, 128, 3, 1, False, 0, True),     # halo kernel BN = 128 (its dgrad: two k-chunks, BN = 64)
+    (2, 32, 16, 128, 128, 3, 1, False, 1, True),    # halo wgrad MODE 1 (128 ci x 128 co x filter row units)
+    (3, 16, 32, 256, 128, 3, 1, False, 1, True),    # halo wgrad MODE 1, two ci blocks, split over tiles
+    (5, 32, 32, 64, 64, 3, 1, False, 1, True),      # halo wgrad MODE 0, uneven split of 40 tiles
 ]
 
 
@@ -167,6 +170,26 @@ def test_conv_tc_halo_channel_slices():
     torch.cuda.synchronize()
     assert rel_err(ybuf[..., :Cout], want) < BF16_TOL
     assert float((ybuf[..., Cout:].float() + 3.0).abs().max()) == 0.0
+
+
+def test_conv_tc_halo_wgrad_channel_slices_and_accumulate():
+    """Halo wgrad reading x from a channel slice of a concat buffer and dy from a slice, accumulating on top of dw."""
+    N, H, W, Cin, Cout = 2, 32, 16, 128, 64
+    x = bf16_round(randn((N, H, W, Cin), 41))
+    w = bf16_round(randn((3, 3, Cin, Cout), 42, 0.05))
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    pre = oracle_conv(xr, wr, None, 1, False, 0)
+    dy = bf16_round(randn(tuple(pre.shape), 43))
+    gw, = torch.autograd.grad((pre * dy).sum(), [wr])
+    c = _mk_conv(Cin, Cout, 3, 1, False, 1, False, w, None)
+    xbuf = torch.full((N, H, W, Cin + 64), 7.0, device="cuda", dtype=torch.bfloat16)
+    xbuf[..., 64:] = dev(x, torch.bfloat16)
+    dybuf = torch.full((N, H, W, 2 * Cout), -3.0, device="cuda", dtype=torch.bfloat16)
+    dybuf[..., :Cout] = dev(dy, torch.bfloat16)
+    c.dw.fill_(0.25)
+    c.wgrad(xbuf[..., 64:], dybuf[..., :Cout], tc=True)
+    c.wgrad(xbuf[..., 64:], dybuf[..., :Cout], tc=True)
+    assert rel_err(c.dw - 0.25, 2.0 * gw) < BF16_TOL
 
 
 def test_conv_tc_matches_simt_bf16_inputs():

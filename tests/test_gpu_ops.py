@@ -53,6 +53,77 @@ def test_inorm_bwd(act):
     assert rel_err(ops.inorm_bwd(zd, sums, dev(gamma), dev(dyA), None, act=act), want_a) < TOL
 
 
+
+# ---- bf16 fast paths (8 channels per thread, 4 pixels in flight) --------------------------------------
+BF = torch.bfloat16
+
+
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (3, 8, 24, 128), (1, 32, 32, 8), (2, 4, 4, 1024), (2, 18, 10, 256)])
+def test_inorm_bf16_fast_fwd(shape):
+    """inorm_stats8 / inorm_apply8 (+pool, +broadcast add, concat-slice output) on bf16 tensors vs the oracle on the same
+    bf16-rounded inputs; the only error left is the bf16 rounding of the outputs (<= 2^-8 relative)."""
+    from shmgan_b200 import ops
+    N, H, W, C = shape
+    x = bf16_round(randn(shape, 1) * 2 + 0.5)
+    gamma, beta = 1 + 0.1 * randn((C,), 2), 0.02 * randn((C,), 3)
+    add = bf16_round(randn((1, H, W, C), 4))
+    want = O.instance_norm(x, gamma, beta)
+    # x lives in a channel slice of a wider buffer (pixel stride 2C)
+    xbuf = torch.full((N, H, W, 2 * C), 3.0, device="cuda", dtype=BF)
+    xbuf[..., :C] = dev(x, BF)
+    xd = xbuf[..., :C]
+    sums = ops.inorm_stats(xd)
+    ref_s = torch.stack([x.sum(dim=(1, 2)), (x * x).sum(dim=(1, 2))], dim=-1)
+    assert rel_err(sums, ref_s) < 1e-5
+    y, _ = ops.inorm_apply(xd, sums, dev(gamma), dev(beta))
+    assert rel_err(y, want) < 8e-3
+    cat = torch.zeros((N, H, W, 2 * C), device="cuda", dtype=BF)
+    _, pooled = ops.inorm_apply(xd, sums, dev(gamma), dev(beta), add=dev(add, BF), out=cat[..., C:], pooled=True)
+    assert rel_err(cat[..., C:], want + add) < 8e-3
+    assert rel_err(pooled, O.avg_pool2(want)) < 8e-3
+    assert float(cat[..., :C].float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape,act", [((2, 16, 16, 64), 1), ((2, 8, 8, 128), 0), ((1, 24, 8, 512), 1), ((3, 6, 10, 8), 2)])
+def test_inorm_bf16_fast_bwd_with_bias_grad(shape, act):
+    from shmgan_b200 import ops
+    N, H, W, C = shape
+    pre = randn(shape, 5)
+    zv = O.leaky_relu(pre) if act == 1 else (torch.relu(pre) if act == 2 else pre)
+    z = bf16_round(zv).requires_grad_()
+    gamma = 1 + 0.1 * randn((C,), 6)
+    beta = 0.02 * randn((C,), 7)
+    y = O.instance_norm(z, gamma, beta)
+    dyA, dyP = bf16_round(randn(shape, 8)), bf16_round(randn((N, H // 2, W // 2, C), 9))
+    loss = (y * dyA).sum() + (O.avg_pool2(y) * dyP).sum()
+    dz, = torch.autograd.grad(loss, z)
+    slope = {1: torch.where(z > 0, 1.0, 0.2), 2: (z > 0).to(F64), 0: torch.ones_like(z)}[act]
+    want = (dz * slope).detach()
+    zd = dev(z.detach(), BF)
+    sums = ops.inorm_stats(zd)
+    db = torch.full((C,), 0.5, device="cuda")
+    dxbuf = torch.full((N, H, W, 2 * C), -1.0, device="cuda", dtype=BF)
+    got = ops.inorm_bwd(zd, sums, dev(gamma), dev(dyA, BF), dev(dyP, BF), act=act, dx=dxbuf[..., C:], dbias=db)
+    assert rel_err(got, want) < 1e-2
+    # the column sums cancel (exactly, without an activation): compare on the scale of the summed magnitudes
+    scale = float(want.abs().sum(dim=(0, 1, 2)).max())
+    assert float(((db - 0.5).double().cpu() - want.sum(dim=(0, 1, 2))).abs().max()) < 2e-3 * scale
+    assert float((dxbuf[..., :C].float() + 1.0).abs().max()) == 0.0
+
+
+def test_act_bwd_bf16_fast_with_bias_grad():
+    from shmgan_b200 import ops
+    N, H, W, C = 3, 10, 6, 64
+    y, dy = bf16_round(randn((N, H, W, C), 16)), bf16_round(randn((N, H, W, C), 17))
+    want = dy * torch.where(y > 0, 1.0, 0.2)
+    db = torch.zeros((C,), device="cuda")
+    ybuf = torch.zeros((N, H, W, 2 * C), device="cuda", dtype=BF)
+    ybuf[..., :C] = dev(y, BF)
+    got = ops.act_bwd(dev(dy, BF), ybuf[..., :C], 1, dbias=db)
+    assert rel_err(got, want) < 8e-3
+    assert rel_err(db, want.sum(dim=(0, 1, 2))) < 5e-3
+
+
 def test_bn_eval_maxpool_actbwd_groupsum():
     from shmgan_b200 import ops
     N, H, W, C = 2, 8, 8, 16
