@@ -60,6 +60,11 @@ int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad);   /* 1 if th
 /* cin_real (0 = d->Cin): the Keras kernel holds only cin_real < d->Cin input channels; the rest of the bf16 copy is zero (the layer
  * then reads a zero-padded 64-channel input, see shm_pad_channels64) */
 int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc, int for_dgrad, void* stream);
+/* forward-layout weights of a layer run in a zero-padded device geometry (d->Cin, d->Cout) >= the Keras kernel's (cin_real, cout_real):
+ * device input channel k holds real channel (k / seg_pad) * seg_real + k %% seg_pad when k %% seg_pad < seg_real, zero otherwise
+ * (one segment = zero-padded input; two = concat of two zero-padded halves, SpecSeg.py:65-83 at 16/32 channels) */
+int shm_conv2d_tc_prep_weights_padded(const shm_conv_desc* d, const float* w, int cin_real, int seg_real, int seg_pad, int cout_real,
+                                      void* w_tc, void* stream);
 int shm_conv2d_tc_fwd  (const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, void* stream);
 int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const void* w_tc_dgrad, void* dx, void* stream);
 int shm_conv2d_tc_wgrad(const shm_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);   /* dw += (fp32 atomics) */
@@ -118,6 +123,13 @@ int shm_dense_wgrad(const void* x, const float* dout, float* dw, int B, int K, i
 int shm_pw1_fwd(const void* x, int ldx, int C, const float* w, const float* bias, int act, void* y, int64_t npix, int dtype, void* stream);
 int shm_pw1_bwd(const void* x, int ldx, int C, const float* w, const void* dy, const void* y, int act, void* dx, int lddx,
                 float* dw, float* dbias, int64_t npix, int dtype, void* stream);
+
+/* 3x3 stride-1 SAME convolution to ONE output channel (the discriminator's real/fake head ShmGANwithSSpecSeg.py:365-369) as
+ * warp-per-pixel dot products.  bf16 activations, C %% 8 == 0; w = the Keras (3,3,C,1) kernel (fp32 [9][C]); y / dpre are [N,H,W] bf16.
+ * dgrad / wgrad take dpre = dL/d(pre-activation) (see shm_act_bwd); dw += */
+int shm_c3to1_fwd(const void* x, int N, int H, int W, int C, int ldx, const float* w, const float* bias, int act, void* y, int dtype, void* stream);
+int shm_c3to1_dgrad(const void* dpre, int N, int H, int W, int C, const float* w, void* dx, int lddx, int dtype, void* stream);
+int shm_c3to1_wgrad(const void* x, int N, int H, int W, int C, int ldx, const void* dpre, float* dw, int dtype, void* stream);
 
 /* ---- polarimetric preprocessing ---- */
 /* calculate_estimate_diffuse utils.py:102-106: per-element min of four images (n elements). dtype: 0 f32, 1 bf16, 2 u8 */

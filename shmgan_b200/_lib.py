@@ -35,6 +35,7 @@ _SIG = {
     "shm_conv2d_wgrad": [_D, _P, _P, _P, _P, _P],
     "shm_conv2d_tc_supported": [_D, _I],
     "shm_conv2d_tc_prep_weights": [_D, _P, _I, _P, _I, _P],
+    "shm_conv2d_tc_prep_weights_padded": [_D, _P, _I, _I, _I, _I, _P, _P],
     "shm_conv2d_tc_fwd": [_D, _P, _P, _P, _P, _P],
     "shm_conv2d_tc_dgrad": [_D, _P, _P, _P, _P],
     "shm_conv2d_tc_wgrad": [_D, _P, _P, _P, _P],
@@ -68,6 +69,9 @@ _SIG = {
     "shm_yuv2rgb_bwd": [_P, _P, _I, _I, _P, _L, _I, _P],
     "shm_pw1_fwd": [_P, _I, _I, _P, _P, _I, _P, _L, _I, _P],
     "shm_pw1_bwd": [_P, _I, _I, _P, _P, _P, _I, _P, _I, _P, _P, _L, _I, _P],
+    "shm_c3to1_fwd": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P],
+    "shm_c3to1_dgrad": [_P, _I, _I, _I, _I, _P, _P, _I, _I, _P],
+    "shm_c3to1_wgrad": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "shm_lsgan": [_P, _L, _F, _P, _F, _P, _F, _I, _P],
     "shm_softmax_ce": [_P, _I, C.POINTER(C.c_float), _P, _F, _P, _F, _I, _P],
     "shm_l1": [_P, _P, _L, _P, _F, _P, _F, _I, _P],

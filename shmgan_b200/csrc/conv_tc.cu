@@ -898,15 +898,18 @@ bool pick_box64(int N, int Qh, int Qw, int& BW, int& BH, int& BI) {
     return true;
 }
 
-// weights -> bf16 [tap][n][k]
+// weights -> bf16 [tap][n][k].  The device reduction dimension may be wider than the Keras one: device channel k maps to source
+// channel (k / seg_pad) * seg_real + (k % seg_pad) when (k % seg_pad) < seg_real (zero otherwise), which covers a zero-padded
+// input (one segment) and a concat of two zero-padded halves (two segments, SpecSeg decoder).
 __global__ void prep_w_kernel(const float* __restrict__ w, bf16* __restrict__ o, int K, int Nn, int k_real, int n_real, long long tap_elems,
-                              int w_ks, int w_ns, long long total) {
+                              int w_ks, int w_ns, int seg_real, int seg_pad, long long total) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int k = (int)(i % K);
         const long long t2 = i / K;
         const int n = (int)(t2 % Nn);
         const long long tap = t2 / Nn;
-        const float v = (k < k_real && n < n_real) ? __ldg(w + tap * tap_elems + (long long)k * w_ks + (long long)n * w_ns) : 0.f;
+        const int kin = k % seg_pad, ks = (k / seg_pad) * seg_real + kin;
+        const float v = (kin < seg_real && ks < k_real && n < n_real) ? __ldg(w + tap * tap_elems + (long long)ks * w_ks + (long long)n * w_ns) : 0.f;
         o[i] = __float2bfloat16_rn(v);
     }
 }
@@ -989,7 +992,28 @@ extern "C" int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w
     const long long total = (long long)d->kh * d->kw * d->Cin * d->Cout;
     long long g = cdiv64(total, 256);
     if (g > shm_num_sms() * 16) g = shm_num_sms() * 16;
-    prep_w_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_tc, K, Nn, k_real, n_real, (long long)cin_real * d->Cout, w_ks, w_ns, total);
+    prep_w_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_tc, K, Nn, k_real, n_real, (long long)cin_real * d->Cout, w_ks, w_ns, K, K, total);
+    SHM_CHECK_LAUNCH("prep_w_kernel");
+    return SHM_OK;
+}
+
+// forward-layout weights of a layer whose device geometry (d->Cin, d->Cout) is a zero-padded version of the Keras kernel
+// (cin_real, cout_real): input channels in segments of seg_pad device channels holding seg_real real ones each.
+extern "C" int shm_conv2d_tc_prep_weights_padded(const shm_conv_desc* d, const float* w, int cin_real, int seg_real, int seg_pad,
+                                                 int cout_real, void* w_tc, void* stream) {
+    if (int rc = tc_check(d)) return rc;
+    SHM_REQUIRE(w && w_tc, "shm_conv2d_tc_prep_weights_padded: NULL buffer");
+    SHM_REQUIRE(cin_real > 0 && cout_real > 0 && cout_real <= d->Cout && seg_real > 0 && seg_pad >= seg_real && d->Cin % seg_pad == 0 &&
+                (d->Cin / seg_pad) * seg_real >= cin_real, "shm_conv2d_tc_prep_weights_padded: inconsistent padding geometry");
+    const int K = d->Cin, Nn = d->Cout;
+    int w_ks, w_ns;
+    if (!d->transposed) { w_ks = cout_real; w_ns = 1; }      // (kh,kw,cin,cout)
+    else { w_ks = 1; w_ns = cin_real; }                      // (kh,kw,cout,cin)
+    const long long total = (long long)d->kh * d->kw * K * Nn;
+    long long g = cdiv64(total, 256);
+    if (g > shm_num_sms() * 16) g = shm_num_sms() * 16;
+    prep_w_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_tc, K, Nn, cin_real, cout_real, (long long)cin_real * cout_real, w_ks, w_ns,
+                                                            seg_real, seg_pad, total);
     SHM_CHECK_LAUNCH("prep_w_kernel");
     return SHM_OK;
 }

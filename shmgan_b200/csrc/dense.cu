@@ -226,3 +226,142 @@ extern "C" int shm_pw1_bwd(const void* x, int ldx, int C, const float* w, const 
     SHM_CHECK_LAUNCH("pw1_bwd_kernel");
     return SHM_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 3x3 stride-1 SAME convolution to ONE output channel (the discriminator's real/fake head, ShmGANwithSSpecSeg.py:365-369:
+// Conv2D(1, 3, use_bias=False) + LeakyReLU on the [B, S/32, S/32, 1024] feature map).  K = 9*C = 9216 but N = 1: a GEMM tile
+// would waste 127/128 of its columns and the exact-fp32 SIMT kernel took 1.6 ms per step on it; as a warp-per-pixel dot
+// product it is a ~25 MB read.  bf16 activations, C % 8 == 0; w = the Keras (3,3,C,1) kernel as fp32 [9][C].
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) c3to1_fwd_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int ldx,
+        const float* __restrict__ w, const float* __restrict__ bias, int act, bf16* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const long long total = (long long)N * H * W;
+    const float b = bias ? __ldg(bias) : 0.f;
+    for (long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); pix < total; pix += nwarps) {
+        const int n = (int)(pix / (H * W)); const int r = (int)(pix - (long long)n * H * W);
+        const int oy = r / W, ox = r - oy * W;
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int iy = oy + t / 3 - 1, ix = ox + t % 3 - 1;
+            if (iy < 0 || iy >= H || ix < 0 || ix >= W) continue;          // warp-uniform
+            const bf16* xp = x + ((long long)(n * H + iy) * W + ix) * ldx;
+            const float* wp = w + t * C;
+            for (int g = lane; g < C / 8; g += 32) {
+                float v[8];
+                unpack8(__ldg(reinterpret_cast<const uint4*>(xp + g * 8)), v);
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(wp + g * 8)), w1 = __ldg(reinterpret_cast<const float4*>(wp + g * 8 + 4));
+                s = fmaf(v[0], w0.x, s); s = fmaf(v[1], w0.y, s); s = fmaf(v[2], w0.z, s); s = fmaf(v[3], w0.w, s);
+                s = fmaf(v[4], w1.x, s); s = fmaf(v[5], w1.y, s); s = fmaf(v[6], w1.z, s); s = fmaf(v[7], w1.w, s);
+            }
+        }
+        s = warp_sum(s);
+        if (lane == 0) y[pix] = __float2bfloat16_rn(act_fwd(s + b, act));
+    }
+}
+
+// dx[n,iy,ix,c] = sum_t dpre[n, iy-(ty-1), ix-(tx-1)] * w[t][c]
+__global__ void __launch_bounds__(256) c3to1_dgrad_kernel(const bf16* __restrict__ dpre, int N, int H, int W, int C,
+        const float* __restrict__ w, bf16* __restrict__ dx, int lddx) {
+    const int G = C / 8;
+    const long long total = (long long)N * H * W * G;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % G); const long long pix = i / G;
+        const int n = (int)(pix / (H * W)); const int r = (int)(pix - (long long)n * H * W);
+        const int iy = r / W, ix = r - iy * W;
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int oy = iy - (t / 3 - 1), ox = ix - (t % 3 - 1);
+            if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;
+            const float d = __bfloat162float(dpre[(long long)(n * H + oy) * W + ox]);
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + t * C + g * 8)), w1 = __ldg(reinterpret_cast<const float4*>(w + t * C + g * 8 + 4));
+            a[0] = fmaf(d, w0.x, a[0]); a[1] = fmaf(d, w0.y, a[1]); a[2] = fmaf(d, w0.z, a[2]); a[3] = fmaf(d, w0.w, a[3]);
+            a[4] = fmaf(d, w1.x, a[4]); a[5] = fmaf(d, w1.y, a[5]); a[6] = fmaf(d, w1.z, a[6]); a[7] = fmaf(d, w1.w, a[7]);
+        }
+        __nv_bfloat162 h[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(a[2 * j], a[2 * j + 1]);
+        *reinterpret_cast<uint4*>(dx + pix * lddx + g * 8) = *reinterpret_cast<uint4*>(h);
+    }
+}
+
+// dw[t][c] += sum over pixels of x[n, oy+ty-1, ox+tx-1, c] * dpre[n, oy, ox]; one block per chunk of input pixels of one image
+__global__ void __launch_bounds__(128) c3to1_wgrad_kernel(const bf16* __restrict__ x, int N, int H, int W, int C, int ldx,
+        const bf16* __restrict__ dpre, float* __restrict__ dw, int chunks_per_img, int ppc) {
+    const int n = blockIdx.x / chunks_per_img, ch = blockIdx.x - n * chunks_per_img;
+    const int pbeg = ch * ppc, pend = min(pbeg + ppc, H * W);
+    for (int g = threadIdx.x; g < C / 8; g += blockDim.x) {
+        float acc[9][8];
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+        for (int p = pbeg; p < pend; ++p) {
+            const int iy = p / W, ix = p - iy * W;
+            float v[8];
+            unpack8(__ldg(reinterpret_cast<const uint4*>(x + ((long long)n * H * W + p) * ldx + g * 8)), v);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int oy = iy - (t / 3 - 1), ox = ix - (t % 3 - 1);
+                if (oy < 0 || oy >= H || ox < 0 || ox >= W) continue;      // block-uniform
+                const float d = __bfloat162float(dpre[(long long)(n * H + oy) * W + ox]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[t][j] = fmaf(v[j], d, acc[t][j]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < 9; ++t)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(dw + t * C + g * 8 + j, acc[t][j]);
+    }
+}
+
+inline int c3to1_check(const void* x, int C, int ldx, int dtype, const char* who) {
+    if (dtype != SHM_BF16) SHM_FAIL(SHM_EUNSUPPORTED, "%s: bf16 only (fp32 mode uses shm_conv2d_*)", who);
+    if (C % 8 != 0 || ldx % 8 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) != 0) SHM_FAIL(SHM_EINVAL, "%s: needs C %% 8 == 0, ld %% 8 == 0 and 16-byte alignment", who);
+    return SHM_OK;
+}
+
+}  // namespace
+
+extern "C" int shm_c3to1_fwd(const void* x, int N, int H, int W, int C, int ldx, const float* w, const float* bias, int act, void* y, int dtype, void* stream) {
+    SHM_REQUIRE(x && w && y && N > 0 && H > 0 && W > 0 && C > 0, "shm_c3to1_fwd: bad args");
+    if (int rc = c3to1_check(x, C, ldx, dtype, "shm_c3to1_fwd")) return rc;
+    SHM_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "shm_c3to1_fwd: w must be 16-byte aligned");
+    long long g = cdiv64((long long)N * H * W, 8);
+    if (g > shm_num_sms() * 8) g = shm_num_sms() * 8;
+    c3to1_fwd_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, N, H, W, C, ldx, w, bias, act, (bf16*)y);
+    SHM_CHECK_LAUNCH("c3to1_fwd_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_c3to1_dgrad(const void* dpre, int N, int H, int W, int C, const float* w, void* dx, int lddx, int dtype, void* stream) {
+    SHM_REQUIRE(dpre && w && dx && N > 0 && H > 0 && W > 0 && C > 0, "shm_c3to1_dgrad: bad args");
+    if (int rc = c3to1_check(dx, C, lddx, dtype, "shm_c3to1_dgrad")) return rc;
+    SHM_REQUIRE((reinterpret_cast<uintptr_t>(w) & 15) == 0, "shm_c3to1_dgrad: w must be 16-byte aligned");
+    long long g = cdiv64((long long)N * H * W * (C / 8), 256);
+    if (g > shm_num_sms() * 16) g = shm_num_sms() * 16;
+    c3to1_dgrad_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>((const bf16*)dpre, N, H, W, C, w, (bf16*)dx, lddx);
+    SHM_CHECK_LAUNCH("c3to1_dgrad_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_c3to1_wgrad(const void* x, int N, int H, int W, int C, int ldx, const void* dpre, float* dw, int dtype, void* stream) {
+    SHM_REQUIRE(x && dpre && dw && N > 0 && H > 0 && W > 0 && C > 0, "shm_c3to1_wgrad: bad args");
+    if (int rc = c3to1_check(x, C, ldx, dtype, "shm_c3to1_wgrad")) return rc;
+    // ~2 waves of blocks; at least 16 pixels per block so that the 72 atomics per thread amortise
+    int chunks = cdiv(shm_num_sms() * 2, N);
+    int ppc = cdiv(H * W, chunks < 1 ? 1 : chunks);
+    if (ppc < 16) ppc = 16;
+    chunks = cdiv(H * W, ppc);
+    c3to1_wgrad_kernel<<<N * chunks, 128, 0, (cudaStream_t)stream>>>((const bf16*)x, N, H, W, C, ldx, (const bf16*)dpre, dw, chunks, ppc);
+    SHM_CHECK_LAUNCH("c3to1_wgrad_kernel");
+    return SHM_OK;
+}

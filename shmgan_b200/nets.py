@@ -491,7 +491,11 @@ class Discriminator:
 # SpecSeg (predict only)
 # ------------------------------------------------------------------------------------------------
 class SpecSegNet:
-    """SpecSeg U-Net (SpecSeg.py:27-98) at predict time: Dropout inactive, BatchNorm on moving statistics."""
+    """SpecSeg U-Net (SpecSeg.py:27-98) at predict time: Dropout inactive, BatchNorm on moving statistics.
+
+    In tensor-core mode the 16- and 32-channel levels (encoder levels 1-2, decoder levels 8-9) run in a zero-padded 64-channel
+    geometry (ops.PaddedConv): activations are [.., 64] with zeros beyond the real channels, the two decoder concat buffers are
+    [.., 128] = [up padded to 64 | skip padded to 64], so every layer of the mask network is a tcgen05 kernel."""
 
     def __init__(self, dtype=torch.float32, device="cuda", seed=44, tensor_core=True):
         self.dtype, self.tc = dtype, tensor_core
@@ -506,9 +510,40 @@ class SpecSegNet:
                              s.bind(Conv(f"c{i}a", 3, 3, 2 * c, c, act=ACT_RELU)), s.bind(Conv(f"c{i}b", 3, 3, c, c, act=ACT_RELU))))
             cin = c
         self.out = s.bind(Conv("out", 1, 1, 16, 1, act=ACT_SIGMOID))
+        # zero-padded twins of the < 64-channel layers (same parameter views)
+        self.padded = None
+        if tensor_core and dtype == torch.bfloat16:
+            P = ops.PaddedConv
+            self.padded = {
+                "c1a": s.bind(P("c1a", 3, 3, 1, 16, 1, 1)), "c1b": s.bind(P("c1b", 3, 3, 16, 16, 16, 1)),
+                "c2a": s.bind(P("c2a", 3, 3, 16, 32, 16, 1)), "c2b": s.bind(P("c2b", 3, 3, 32, 32, 32, 1)),
+                "c3a": s.bind(P("c3a", 3, 3, 32, 64, 32, 1)),
+                "u8": s.bind(P("u8", 2, 2, 64, 32, 64, 1, stride=2, transposed=True, act=ACT_NONE)),
+                "c8a": s.bind(P("c8a", 3, 3, 64, 32, 32, 2)), "c8b": s.bind(P("c8b", 3, 3, 32, 32, 32, 1)),
+                "u9": s.bind(P("u9", 2, 2, 32, 16, 32, 1, stride=2, transposed=True, act=ACT_NONE)),
+                "c9a": s.bind(P("c9a", 3, 3, 32, 16, 16, 2)), "c9b": s.bind(P("c9b", 3, 3, 16, 16, 16, 1)),
+            }
+        self._zbuf = {}
+
+    def _zeros(self, key, shape):
+        """Zero-initialised scratch whose padding channels are never written (cached per shape across calls)."""
+        t = self._zbuf.get(key)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.zeros(shape, dtype=self.dtype, device=self.store.flat.device)
+            self._zbuf[key] = t
+        return t
+
+    def _padded_ok(self, B, H, W) -> bool:
+        if self.padded is None or H % 64 != 0 or W % 64 != 0:
+            return False
+        p = self.padded
+        return (p["c1a"].servable(B, H, W) and p["c2a"].servable(B, H // 2, W // 2) and p["c3a"].servable(B, H // 4, W // 4)
+                and p["u8"].servable(B, H // 4, W // 4) and p["u9"].servable(B, H // 2, W // 2))
 
     def predict(self, x: torch.Tensor, verbose=0) -> torch.Tensor:
         """x [B,S,S,1] -> sigmoid probabilities [B,S,S,1] in the same dtype (SpecSeg.predict, ShmGANwithSSpecSeg.py:492)."""
+        if self._padded_ok(*x.shape[:3]):
+            return self._predict_padded(x)
         v = self.store.version
         sv = self.store.views
         B = x.shape[0]
@@ -530,3 +565,39 @@ class SpecSegNet:
             h = ca.fwd(cat, None, self.tc, v)
             h = cb.fwd(h, None, self.tc, v)
         return self.out.fwd(h, None, self.tc, v)
+
+    def _predict_padded(self, x: torch.Tensor) -> torch.Tensor:
+        v, sv, P = self.store.version, self.store.views, self.padded
+        B, H, W = x.shape[:3]
+        bn = lambda i: (sv[f"bn{i}.gamma"], sv[f"bn{i}.beta"], sv[f"bn{i}.mean"], sv[f"bn{i}.var"])
+        # level 1 (16 real channels) and level 2 (32): 64-wide tensors; skips land in the upper half of 128-wide concat buffers
+        cat9 = self._zeros("cat9", (B, H, W, 128))
+        cat8 = self._zeros("cat8", (B, H // 2, W // 2, 128))
+        p1 = self._zeros("p1", (B, H // 2, W // 2, 64))
+        p2 = self._zeros("p2", (B, H // 4, W // 4, 64))
+        h = P["c1b"].fwd(P["c1a"].fwd(ops.pad64(x), None, True, v), None, True, v)
+        ops.bn_eval(h[..., :16], *bn(1), out=cat9[..., 64:80], pooled=p1[..., :16])
+        h = P["c2b"].fwd(P["c2a"].fwd(p1, None, True, v), None, True, v)
+        ops.bn_eval(h[..., :32], *bn(2), out=cat8[..., 64:96], pooled=p2[..., :32])
+        h = P["c3a"].fwd(p2, None, True, v)
+        cats = []
+        for ca, cb, i in self.enc[2:]:
+            if i > 3:
+                h = ca.fwd(h, None, True, v)
+            h = cb.fwd(h, None, True, v)
+            c = cb.cout
+            if i < 5:
+                cat = ops.new((B, h.shape[1], h.shape[2], 2 * c), self.dtype)
+                _, h = ops.bn_eval(h, *bn(i), out=cat[..., c:], pooled=True)
+                cats.append(cat)
+            else:
+                h, _ = ops.bn_eval(h, *bn(i))
+        for (up, ca, cb), cat in zip(self.dec[:2], reversed(cats)):
+            c = up.cout
+            up.fwd(h, cat[..., :c], True, v)
+            h = cb.fwd(ca.fwd(cat, None, True, v), None, True, v)
+        P["u8"].fwd(h, cat8[..., :64], True, v)
+        h = P["c8b"].fwd(P["c8a"].fwd(cat8, None, True, v), None, True, v)
+        P["u9"].fwd(h, cat9[..., :64], True, v)
+        h = P["c9b"].fwd(P["c9a"].fwd(cat9, None, True, v), None, True, v)
+        return self.out.fwd(h[..., :16], None, True, v)

@@ -106,6 +106,12 @@ class Conv:
         return (self.kh == 1 and self.kw == 1 and self.cout == 1 and not self.transposed and x.dtype == torch.bfloat16
                 and self.cin in (8, 16, 32, 64, 128, 256) and ld(x) % 8 == 0 and x.data_ptr() % 16 == 0)
 
+    def c3to1_ok(self, x) -> bool:
+        """3x3 stride-1 conv to one channel on bf16 activations (the discriminator's real/fake head): warp-per-pixel dot products."""
+        return (self.kh == 3 and self.kw == 3 and self.cout == 1 and self.stride == 1 and not self.transposed
+                and x.dtype == torch.bfloat16 and self.cin % 8 == 0 and x.shape[-1] == self.cin and ld(x) % 8 == 0
+                and x.data_ptr() % 16 == 0)
+
     def wshape(self):
         return (self.kh, self.kw, self.cout, self.cin) if self.transposed else (self.kh, self.kw, self.cin, self.cout)
 
@@ -148,7 +154,10 @@ class Conv:
         fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, x.element_size())
         if pad and not (tc and self.tc_ok(d)):
             raise L.ShmError("%s: zero-padded input needs the tensor-core path (shape %s)" % (self.name, tuple(x.shape)))
-        if tc and self.pw1_ok(x):
+        if tc and self.c3to1_ok(x):
+            _prof("bw", "fwd", self.name, fl, nb, lambda: call("shm_c3to1_fwd", _p(x), n, h, w, self.cin, ld(x), _p(self.w), _p(self.b), self.act,
+                                                              _p(y), dt(x), _stream()))
+        elif tc and self.pw1_ok(x):
             _prof("bw", "fwd", self.name, fl, nb, lambda: call("shm_pw1_fwd", _p(x), ld(x), self.cin, _p(self.w), _p(self.b), self.act, _p(y),
                                                               n * h * w, dt(x), _stream()))
         elif tc and self.tc_ok(d):
@@ -180,7 +189,9 @@ class Conv:
         fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, dy.element_size())
         if pad and not (tc and self.tc_ok(d)):
             raise L.ShmError("%s: zero-padded dgrad needs the tensor-core path" % self.name)
-        if tc and self.tc_ok(d):
+        if tc and self.c3to1_ok(dx):
+            _prof("bw", "dgrad", self.name, fl, nb, lambda: call("shm_c3to1_dgrad", _p(dy), n, h, w, self.cin, _p(self.w), _p(dx), ld(dx), dt(dy), _stream()))
+        elif tc and self.tc_ok(d):
             self.refresh_tc(version)
             _prof("tc", "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_dgrad", C.byref(d), _p(dy), _p(self.w_tc_d), _p(dx), _stream()))
         else:
@@ -201,7 +212,9 @@ class Conv:
             if self.dw_pad is None:
                 self.dw_pad = torch.zeros((self.kh, self.kw, self.cin_pad, self.cout), dtype=torch.float32, device=x.device)
             dw = self.dw_pad
-        if tc and self.tc_ok(d):
+        if tc and self.c3to1_ok(x) and not self.has_bias:
+            _prof("bw", "wgrad", self.name, fl, nb, lambda: call("shm_c3to1_wgrad", _p(x), n, h, w, self.cin, ld(x), _p(dy), _p(dw), dt(x), _stream()))
+        elif tc and self.tc_ok(d):
             _prof("tc", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(dw), _stream()))
             if self.has_bias and not bias_done:
                 call("shm_colsum", _p(dy), dy.shape[0] * dy.shape[1] * dy.shape[2], self.cout, ld(dy), dt(dy), _p(self.db), _stream())
@@ -227,6 +240,54 @@ class Conv:
             return
         taps, n = self.kh * self.kw, self.cin * self.cout
         call("shm_cast2d", _p(self.dw_pad), F32, self.cin_pad * self.cout, _p(self.dw), F32, n, taps, n, _stream())
+
+
+class PaddedConv(Conv):
+    """Inference-only layer whose channel counts are below the tensor-core granule (SpecSeg's 16/32-channel levels,
+    SpecSeg.py:34-44, :76-86): it runs in a zero-padded device geometry -- inputs live in 64-channel segments holding
+    `seg_real` real channels each, outputs are `cout_dev` wide with zero weights / bias beyond `cout` -- so that the 3x3 layers
+    go through the halo tcgen05 kernel instead of the exact-fp32 SIMT kernel (6.9 ms -> < 1 ms per step for the mask network).
+    The padded output channels are exactly zero after ReLU / LeakyReLU / no activation (zero weights, zero bias)."""
+
+    def __init__(self, name, kh, kw, cin, cout, seg_real, nseg, stride=1, transposed=False, act=ACT_RELU, bias=True):
+        super().__init__(name, kh, kw, cin, cout, stride=stride, transposed=transposed, act=act, bias=bias)
+        assert seg_real * nseg == cin and act != ACT_SIGMOID
+        self.seg_real, self.nseg = seg_real, nseg
+        self.cin_dev, self.cout_dev = 64 * nseg, max(64, cout)
+        self.b_dev = None
+
+    def refresh_tc(self, version: int):
+        if self.tc_version == version:
+            return
+        d = ConvDesc(1, 16, 16, self.cin_dev, self.cout_dev, self.kh, self.kw, self.stride, int(self.transposed), self.act,
+                     self.cin_dev, self.cout_dev, BF16, 0)
+        if self.w_tc is None:
+            self.w_tc = new((self.kh * self.kw * self.cin_dev * self.cout_dev,), torch.bfloat16)
+            self.b_dev = torch.zeros((self.cout_dev,), dtype=torch.float32, device=self.w.device)
+        call("shm_conv2d_tc_prep_weights_padded", C.byref(d), _p(self.w), self.cin, self.seg_real, 64, self.cout, _p(self.w_tc), _stream())
+        if self.has_bias:
+            call("shm_cast", _p(self.b), F32, _p(self.b_dev), F32, self.cout, _stream())
+        self.tc_version = version
+
+    def dev_desc(self, n, h, w, ldx, ldy):
+        return ConvDesc(n, h, w, self.cin_dev, self.cout_dev, self.kh, self.kw, self.stride, int(self.transposed), self.act, ldx, ldy, BF16, 0)
+
+    def servable(self, n, h, w) -> bool:
+        return bool(call("shm_conv2d_tc_supported", C.byref(self.dev_desc(n, h, w, self.cin_dev, self.cout_dev)), 0))
+
+    def fwd(self, x, y=None, tc=True, version=0):
+        """x [n,h,w,cin_dev] bf16 (zero-padded segments) -> y [n,ho,wo,cout_dev] bf16 (channels cout.. are zero)."""
+        n, h, w, cx = x.shape
+        assert tc and x.dtype == torch.bfloat16 and cx == self.cin_dev, (self.name, tuple(x.shape))
+        ho, wo = self.out_hw(h, w)
+        if y is None:
+            y = new((n, ho, wo, self.cout_dev), x.dtype)
+        assert y.shape[-1] == self.cout_dev
+        self.refresh_tc(version)
+        d = self.dev_desc(n, h, w, ld(x), ld(y))
+        fl, nb = self.flops(n, h, w), x.element_size() * n * (h * w * self.cin_dev + ho * wo * self.cout_dev)
+        _prof("tc", "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b_dev), _p(y), _stream()))
+        return y
 
 
 # ------------------------------------------------------------------------------------------------
@@ -280,10 +341,14 @@ def maxpool(x, k):
 
 
 def bn_eval(x, gamma, beta, mean, var, out=None, pooled=False):
+    """pooled: False | True (allocate) | a [n,h/2,w/2,c] tensor / channel-slice view to write MaxPool2 of the result into."""
     n, h, w, c = x.shape
     if out is None:
         out = new((n, h, w, c), x.dtype)
-    pl = new((n, h // 2, w // 2, c), x.dtype) if pooled else None
+    if torch.is_tensor(pooled):
+        pl = pooled
+    else:
+        pl = new((n, h // 2, w // 2, c), x.dtype) if pooled else None
     call("shm_bn_eval", _p(x), n, h, w, c, ld(x), dt(x), _p(gamma), _p(beta), _p(mean), _p(var), BN_EPS, _p(out), ld(out), _p(pl), ld(pl), _stream())
     return out, pl
 

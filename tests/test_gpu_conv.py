@@ -192,6 +192,30 @@ def test_conv_tc_halo_wgrad_channel_slices_and_accumulate():
     assert rel_err(c.dw - 0.25, 2.0 * gw) < BF16_TOL
 
 
+@pytest.mark.parametrize("shape", [(2, 8, 8, 1024), (3, 4, 6, 64), (1, 5, 3, 8)])
+def test_conv3x3_to_one_channel_bf16(shape):
+    """The discriminator's real/fake head (3x3, C -> 1, no bias, LeakyReLU) as warp-per-pixel dot products: fwd, dgrad, wgrad."""
+    N, H, W, C = shape
+    x = bf16_round(randn((N, H, W, C), 51))
+    w = randn((3, 3, C, 1), 52, 0.05).float().to(F64)
+    xr, wr = x.clone().requires_grad_(), w.clone().requires_grad_()
+    pre = oracle_conv(xr, wr, None, 1, False, 0)
+    want = oracle_conv(x, w, None, 1, False, 1)
+    dy = bf16_round(randn(tuple(pre.shape), 53))
+    gx, gw = torch.autograd.grad((pre * dy).sum(), [xr, wr])
+    c = _mk_conv(C, 1, 3, 1, False, 1, False, w, None)
+    xd = dev(x, torch.bfloat16)
+    assert c.c3to1_ok(xd)
+    y = c.fwd(xd, tc=True, version=1)
+    assert y.shape == (N, H, W, 1) and rel_err(y, want) < 8e-3
+    dyd = dev(dy, torch.bfloat16)
+    dx = c.dgrad(dyd, xd.shape, tc=True, version=1)
+    assert rel_err(dx, gx) < 8e-3
+    c.dw.fill_(0.5)
+    c.wgrad(xd, dyd, tc=True)
+    assert rel_err(c.dw - 0.5, gw) < 1e-4
+
+
 def test_conv_tc_matches_simt_bf16_inputs():
     """Same bf16 inputs through both kernel families: the tcgen05 result differs from the fp32-accumulating SIMT kernel only
     by the bf16 output rounding."""

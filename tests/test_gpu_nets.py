@@ -182,3 +182,32 @@ def test_specseg_predict(dtype, tol):
     agree = ((got.float().cpu() > 0.5) == (want > 0.5)).double().mean()
     near = ((want - 0.5).abs() < 1e-3).double().mean()
     assert float(agree) >= 0.999 - float(near)
+
+
+def test_specseg_padded_tensor_core_path():
+    """The 16/32-channel SpecSeg levels in the zero-padded 64-channel geometry (every layer on the tcgen05 kernels) vs the
+    oracle, and vs the mixed SIMT/tensor-core path on the same weights: same bf16 arithmetic, so the two device paths agree
+    to bf16 rounding and the binarised masks agree >= 99.9 %."""
+    from shmgan_b200 import nets
+    p = _params(O.specseg_param_specs(), 12)
+    for k in p:
+        if k.endswith(".var"):
+            p[k] = p[k].abs() + 0.5
+    x = bf16_round(rand((8, 128, 128, 1), 14))
+    want = O.specseg_forward(p, x)
+    net = nets.SpecSegNet(torch.bfloat16)
+    net.store.load(p)
+    xd = dev(x, torch.bfloat16)
+    assert net._padded_ok(8, 128, 128)
+    got = net.predict(xd)
+    assert rel_err(got, want) < 2e-2
+    agree = ((got.float().cpu() > 0.5) == (want > 0.5)).double().mean()
+    near = ((want - 0.5).abs() < 1e-3).double().mean()
+    assert float(agree) >= 0.999 - float(near)
+    padded, net.padded = net.padded, None               # same network through the unpadded (SIMT below 64 channels) path
+    ref = net.predict(xd)
+    net.padded = padded
+    assert rel_err(got, ref) < 2e-2
+    assert float(((got > 0.5) == (ref > 0.5)).double().mean()) >= 0.999
+    # the padding channels of the cached concat buffers were never written
+    assert float(net._zbuf["cat9"][..., 80:].float().abs().max()) == 0.0 and float(net._zbuf["cat9"][..., 16:64].float().abs().max()) == 0.0
