@@ -436,6 +436,149 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// big halo kernel: stride-1 3x3 convolutions with many channels (K * N > 8192: every 128..1024-channel generator layer,
+// forward and dgrad).  The generic kernel moves 32 KB of operands per four 128x128x16 MMAs (8 KB/MMA, 128 B/clk/SM from L2)
+// and tops out near 1050 TFLOP/s.  Here a CTA owns a 32 x 8-pixel tile (TWO 128-row accumulators) x 128 output channels:
+//   * per 64-channel k-chunk ONE TMA box brings the 34 x 10 halo (43.5 KB), and the nine taps x two M-tiles are shifted smem
+//     descriptors into it (as in conv_halo_kernel);
+//   * each 16 KB weight tile (tap, k-chunk) is streamed through its own ring and used by BOTH M-tiles (8 MMAs per tile);
+//   => 191 KB per 72 MMAs = 2.7 KB/MMA (3x less L2->SM traffic), accumulators double-buffered in all 512 TMEM columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int BIG_H = 34;                                      // (32 + 2) halo rows of HALO_W pixels
+constexpr int BIG_A_TX = BIG_H * HALO_W * 128;                 // 43520 bytes written by TMA
+constexpr int BIG_A_ST = 44032;                                // rounded up to 1024
+constexpr int BIG_B_ST = 128 * 128;                            // 128 output channels x 64 bf16
+constexpr int BIG_A_STAGES = 2, BIG_B_STAGES = 8;
+constexpr int BIG_SMEM = BIG_A_STAGES * BIG_A_ST + BIG_B_STAGES * BIG_B_ST + 1024 + 256;
+struct BigParams {
+    int ntaps; int tdy[9], tdx[9], wrow[9];   // tap offsets relative to the halo origin (0..2), first weight row of the tap
+    int oy, ox;                               // halo origin relative to the tile origin
+    int kchunks;
+    int tiles_x, tiles_y, m_tiles, n_tiles;
+    int H, W, ldout;
+    const float* bias; int act;
+    bf16* out;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_big_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const BigParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + BIG_A_STAGES * BIG_A_ST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + BIG_B_STAGES * BIG_B_ST);
+    uint64_t* fullA = bars;                              // [2]
+    uint64_t* emptyA = fullA + BIG_A_STAGES;             // [2]
+    uint64_t* fullB = emptyA + BIG_A_STAGES;             // [8]
+    uint64_t* emptyB = fullB + BIG_B_STAGES;             // [8]
+    uint64_t* tfull = emptyB + BIG_B_STAGES;             // [2]
+    uint64_t* tempty = tfull + 2;                        // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = p.m_tiles * p.n_tiles;
+    const int per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int i = 0; i < BIG_A_STAGES; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < BIG_B_STAGES; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x) {
+                const int nt = item % p.n_tiles, mt = item / p.n_tiles;
+                const int img = mt / per_img; const int r = mt - img * per_img;
+                const int y0 = (r / p.tiles_x) * 32 + p.oy, x0 = (r % p.tiles_x) * 8 + p.ox;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&emptyA[sa], pha ^ 1);
+                    mbar_expect_tx(&fullA[sa], BIG_A_TX);
+                    tma_load_4d(sA + sa * BIG_A_ST, &tmA, &fullA[sa], kc * 64, x0, y0, img);
+                    if (++sa == BIG_A_STAGES) { sa = 0; pha ^= 1; }
+                    for (int t = 0; t < p.ntaps; ++t) {
+                        mbar_wait(&emptyB[sb], phb ^ 1);
+                        mbar_expect_tx(&fullB[sb], BIG_B_ST);
+                        tma_load_2d(sB + sb * BIG_B_ST, &tmB, &fullB[sb], kc * 64, p.wrow[t] + nt * 128);
+                        if (++sb == BIG_B_STAGES) { sb = 0; phb ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
+            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+            int local = 0;
+            for (int item = blockIdx.x; item < total; item += gridDim.x, ++local) {
+                const int as = local & 1;
+                mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d0 = tmem_base + as * 256;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    mbar_wait(&fullA[sa], pha);
+                    tc_fence_after();
+                    const uint32_t a0 = smem_u32(sA + sa * BIG_A_ST);
+                    for (int t = 0; t < p.ntaps; ++t) {
+                        mbar_wait(&fullB[sb], phb);
+                        tc_fence_after();
+                        const uint64_t bdesc = make_desc_sw128(smem_u32(sB + sb * BIG_B_ST), 16, 1024);
+                        const uint32_t aoff = a0 + (uint32_t)(p.tdy[t] * HALO_W + p.tdx[t]) * 128u;
+#pragma unroll
+                        for (int half = 0; half < 2; ++half) {
+                            const uint64_t adesc = make_desc_sw128(aoff + (uint32_t)half * (16 * HALO_W * 128), 16, HALO_W * 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d0 + half * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+                        }
+                        umma_commit(&emptyB[sb]);
+                        if (++sb == BIG_B_STAGES) { sb = 0; phb ^= 1; }
+                    }
+                    umma_commit(&emptyA[sa]);
+                    if (++sa == BIG_A_STAGES) { sa = 0; pha ^= 1; }
+                }
+                umma_commit(&tfull[as]);
+            }
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int ty = row >> 3, tx = row & 7;
+        int local = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++local) {
+            const int as = local & 1;
+            const int nt = item % p.n_tiles, mt = item / p.n_tiles;
+            const int img = mt / per_img; const int r = mt - img * per_img;
+            const int oy = (r / p.tiles_x) * 32 + ty, ox = (r % p.tiles_x) * 8 + tx;
+            mbar_wait(&tfull[as], (local >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                bf16* dst = p.out + ((long long)(img * p.H + oy + half * 16) * p.W + ox) * p.ldout + nt * 128;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c)
+                    epi_chunk(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + half * 128 + c * 32),
+                              p.bias ? p.bias + nt * 128 + c * 32 : nullptr, p.act, dst + c * 32, true);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -559,6 +702,39 @@ int encode_act_box(CUtensorMap* tm, const void* base, int C, int W, int H, int N
 // stride-1 3x3 layers the halo kernel serves: K, Nn in {64, 128} with all nine weight tiles resident (K * Nn <= 8192)
 bool halo_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
     return kh == 3 && kw == 3 && stride == 1 && H % 16 == 0 && W % 8 == 0 && (K == 64 || K == 128) && (Nn == 64 || Nn == 128) && K * Nn <= 8192;
+}
+
+// stride-1 3x3 layers the big halo kernel serves
+bool big_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
+    return kh == 3 && kw == 3 && stride == 1 && H % 32 == 0 && W % 8 == 0 && K % 64 == 0 && Nn % 128 == 0;
+}
+
+int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
+               void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st) {
+    BigParams p{};
+    int miny = 9, minx = 9;
+    for (int t = 0; t < 9; ++t) { if (tdy[t] < miny) miny = tdy[t]; if (tdx[t] < minx) minx = tdx[t]; }
+    p.ntaps = 9;
+    for (int t = 0; t < 9; ++t) {
+        p.tdy[t] = tdy[t] - miny; p.tdx[t] = tdx[t] - minx; p.wrow[t] = twrow[t];
+        if (p.tdy[t] > 2 || p.tdx[t] > 2) SHM_FAIL(SHM_EUNSUPPORTED, "conv_big: tap offsets exceed the 1-pixel halo");
+    }
+    p.oy = miny; p.ox = minx;
+    p.kchunks = K / 64;
+    p.tiles_x = W / 8; p.tiles_y = H / 32;
+    p.m_tiles = N * p.tiles_x * p.tiles_y; p.n_tiles = Nn / 128;
+    p.H = H; p.W = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
+    CUtensorMap tmA, tmB;
+    if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, BIG_H)) return rc;
+    if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 128)) return rc;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM); attr = true; }
+    const int total = p.m_tiles * p.n_tiles;
+    int grid = shm_num_sms();
+    if (grid > total) grid = total;
+    conv_big_kernel<<<grid, TC_THREADS, BIG_SMEM, st>>>(tmA, tmB, p);
+    SHM_CHECK_LAUNCH("conv_big_kernel");
+    return SHM_OK;
 }
 
 template <int KC, int BN>
@@ -1046,6 +1222,8 @@ extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const vo
             for (int kx = 0; kx < d->kw; ++kx) { tdy[nt] = ky - pby; tdx[nt] = kx - pbx; twr[nt] = (ky * d->kw + kx) * d->Cout; ++nt; }
         if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
             return launch_halo(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st);
+        if (big_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
+            return launch_big(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st);
         Geometry g{d->H, d->W, d->ldx, d->Cin, Ho, Wo, s, Ho, Wo, d->ldy, d->Cout, 1};
         return launch_tc(g, d->N, x, w_tc, wrows, bias, d->act, y, tdy, tdx, twr, nt, 0, 0, st);
     }
@@ -1101,6 +1279,8 @@ extern "C" int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const
             if (nt == 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: parity class without taps");
             if (halo_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s))
                 return launch_halo(d->N, d->H, d->W, d->Cout, d->Cin, dy, d->ldy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, d->ldx, tdy, tdx, twr, st);
+            if (big_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s))
+                return launch_big(d->N, d->H, d->W, d->Cout, d->Cin, dy, d->ldy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, d->ldx, tdy, tdx, twr, st);
             Geometry g{Ho, Wo, d->ldy, d->Cout, cdiv(d->H - ry, s), cdiv(d->W - rx, s), 1, d->H, d->W, d->ldx, d->Cin, s};
             if (int rc = launch_tc(g, d->N, dy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, tdy, tdx, twr, nt, ry, rx, st)) return rc;
         }

@@ -122,6 +122,10 @@ TC_CASES = [
     (2, 32, 16, 128, 128, 3, 1, False, 1, True),    # halo wgrad MODE 1 (128 ci x 128 co x filter row units)
     (3, 16, 32, 256, 128, 3, 1, False, 1, True),    # halo wgrad MODE 1, two ci blocks, split over tiles
     (5, 32, 32, 64, 64, 3, 1, False, 1, True),      # halo wgrad MODE 0, uneven split of 40 tiles
+    (2, 32, 32, 128, 128, 3, 1, False, 1, True),    # big halo kernel (32x8 tile = two accumulators per weight tile), fwd and dgrad
+    (1, 64, 16, 256, 128, 3, 1, False, 2, True),    # big halo kernel, four k-chunks (A ring wraps), dgrad has two n-tiles
+    (2, 32, 8, 64, 256, 3, 1, False, 0, True),      # big halo kernel fwd with two n-tiles, single k-chunk
+    (10, 64, 64, 128, 256, 3, 1, False, 1, True),   # big halo kernel, 320 work items: persistent loop, accumulator double buffering
 ]
 
 
