@@ -152,6 +152,11 @@ class ShmGANwithSSpecSeg:
         self.step_count = 0
         self.table = LS.LossTable()
         self._reducer = None
+        # the discriminator's weight-gradient sweep (12 passes of small, bandwidth-heavy layers) is independent of the generator-loss
+        # sweep (D dgrad-only -> G backward): it runs on a side stream so that its bandwidth kernels fill the gaps of the
+        # tensor-bound generator kernels; likewise D(xA) forward runs beside the cyclic generator forward
+        self.overlap = True
+        self._side = None
 
     # -- model builders (same names as the reference) --------------------------------------------------------------
     def build_generator(self):
@@ -239,6 +244,20 @@ class ShmGANwithSSpecSeg:
             ops.yuv2rgb(gen_Y, avg, gen_rgb, xA[:B])
         to_d(origs[4], out=xA[B:])
 
+        # ---- D on [gen_rgb | origED] (training=True, :559-563) on the side stream, beside the cyclic generator pass
+        s32 = S // 32
+        if self.d_noise is not None:
+            noise, keep = ops.cast(self.d_noise.contiguous(), dt), ops.cast(self.d_keep.contiguous(), dt)
+        else:
+            noise = ops.rng_normal((2 * B, S, S, 3), self.noise_seed, (4 * self.step_count) << 32, 0.1, dt)
+            keep = ops.rng_keep((2 * B, s32, s32, D.blocks[-1].conv.cout), self.noise_seed, (4 * self.step_count + 2) << 32,
+                                1.0 - self.dropout_amnt, dt)
+        side = self._side_stream()
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                rfA_lp, clsA, tapeA = D.forward(xA, d_attn, noise, keep, save=True)
+
         # ---- cyclic G passes, batched as 5B images: pass k = images [kB, (k+1)B) (:576-624)
         cyc_in = ops.new((5 * B, S, S, g_cin), dt)
         for k in range(5):
@@ -263,14 +282,10 @@ class ShmGANwithSSpecSeg:
             to_d(origs[k], out=xB[(5 + k) * B:(6 + k) * B])
 
         # ---- D passes
-        s32 = S // 32
-        if self.d_noise is not None:
-            noise, keep = ops.cast(self.d_noise.contiguous(), dt), ops.cast(self.d_keep.contiguous(), dt)
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)    # D(xA) ran beside the cyclic generator pass
         else:
-            noise = ops.rng_normal((2 * B, S, S, 3), self.noise_seed, (4 * self.step_count) << 32, 0.1, dt)
-            keep = ops.rng_keep((2 * B, s32, s32, D.blocks[-1].conv.cout), self.noise_seed, (4 * self.step_count + 2) << 32,
-                                1.0 - self.dropout_amnt, dt)
-        rfA_lp, clsA, tapeA = D.forward(xA, d_attn, noise, keep, save=True)
+            rfA_lp, clsA, tapeA = D.forward(xA, d_attn, noise, keep, save=True)
         rfB_lp, clsB, tapeB = D.forward(xB, d_attn, None, None, save=True)
         rfA, rfB = _f32(rfA_lp), _f32(rfB_lp)
         nrf = B * s32 * s32
@@ -318,13 +333,22 @@ class ShmGANwithSSpecSeg:
         D.store.zero_grad()
         G.store.zero_grad()
         d_dattn = torch.zeros_like(d_attn) if self.live_mask else None
-        D.backward(tapeA, dD_rfA, dD_clsA, wgrad=True, need_dx=False, dattn=d_dattn, attn_nb=B)
-        D.backward(tapeB, dD_rfB, dD_clsB, wgrad=True, need_dx=False, dattn=d_dattn, attn_nb=B)
-        if self.live_mask:
-            D.attention_backward(d_attn_saved, d_dattn)
-        D.store.finalize_grads()
-        if self._reducer is not None:
-            self._reducer.reduce_async(D.store.grad)
+
+        def d_weight_sweep():
+            D.backward(tapeA, dD_rfA, dD_clsA, wgrad=True, need_dx=False, dattn=d_dattn, attn_nb=B)
+            D.backward(tapeB, dD_rfB, dD_clsB, wgrad=True, need_dx=False, dattn=d_dattn, attn_nb=B)
+            if self.live_mask:
+                D.attention_backward(d_attn_saved, d_dattn)
+            D.store.finalize_grads()
+            if self._reducer is not None:
+                self._reducer.reduce_async(D.store.grad)
+
+        if side is not None:
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                d_weight_sweep()
+        else:
+            d_weight_sweep()
         dxA = D.backward(tapeA, dG_rfA, None, n=B, wgrad=False, need_dx=True)
         dxB = D.backward(tapeB, dG_rfB, None, n=5 * B, wgrad=False, need_dx=True)
         lpA, lpB = (None, None) if dt == f32 else (dxA, dxB)
@@ -346,6 +370,8 @@ class ShmGANwithSSpecSeg:
         if self.live_mask:
             G.attention_backward(g_attn_saved, g_dattn)
         G.store.finalize_grads()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         if self._reducer is not None:
             self._reducer.reduce_async(G.store.grad)
             self._reducer.wait()
@@ -373,6 +399,13 @@ class ShmGANwithSSpecSeg:
          self.label_origED_D4) = [clsB[(5 + k) * B:(6 + k) * B] for k in range(5)]
         self._publish_losses(tab.read())
         return None
+
+    def _side_stream(self):
+        if not self.overlap:
+            return None
+        if self._side is None:
+            self._side = torch.cuda.Stream()
+        return self._side
 
     def _publish_losses(self, v):
         """Totals of :669-844 from the per-term table (one device->host copy per step)."""
