@@ -288,6 +288,31 @@ def run_ours(a):
                                 "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "traffic": None}
         del big
 
+        # ---- inference img/s (BASELINE.json metric, configs[3] / configs[4] shapes): SpecSeg mask + generator forward + yuv->rgb
+        # (test.py:218-250) through inference_step; inputs resident, CUDA events, >= L2-sized tensors
+        inf = {}
+        for tag, (ib, isz) in {"b64_512": (64, 512), "b8_1024": (8, 1024), "b64_256": (64, 256)}.items():
+            try:
+                inet = M.ShmGANwithSSpecSeg(M.default_args(image_size=isz, batch_size=ib), dtype=a.dtype).build()
+                img = torch.rand((ib, isz, isz, 3), device="cuda")
+                for _ in range(2):
+                    inet.inference_step(img)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    inet.inference_step(img)
+                e1.record()
+                torch.cuda.synchronize()
+                t = e0.elapsed_time(e1) / 5
+                gf = 119.5 * (isz / 256.0) ** 2              # SpecSeg + G1 with the live mask branch, GFLOP per image
+                inf[tag] = {"images_per_s": ib / (t * 1e-3), "ms_per_batch": t, "batch": ib, "size": isz,
+                            "tflops": gf * ib / t / 1e3}
+                del inet, img
+                torch.cuda.empty_cache()
+            except Exception as ex:                          # report, do not hide
+                inf[tag] = {"error": str(ex)[:200]}
+        line["inference"] = inf
+
         # ---- configs[1] literally: the fp32 parity mode on the same batch (2 steps)
         if a.dtype == "bf16":
             del net

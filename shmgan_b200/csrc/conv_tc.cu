@@ -11,6 +11,7 @@
 // (ShmGANwithSSpecSeg.py:244-326, :365, :387, :410-411; tape.gradient :859,:868).
 #include "common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -63,6 +64,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* tm) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
 }
+// one lane of the (converged) warp: the tcgen05 issue loops run warp-uniformly and only the MMA / commit instructions are guarded by
+// this predicate -- guarding the whole loop with `lane == 0` made ptxas wrap every UTCHMMA in a per-lane ELECT / R2UR.BROADCAST /
+// BRA.U.ANY loop (~90 issue cycles per MMA against 32-64 tensor cycles: every kernel was issue-bound)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n"
+        ".reg .pred px;\n"
+        "elect.sync _|px, 0xffffffff;\n"
+        "@px mov.s32 %0, 1;\n"
+        "}\n" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -114,21 +128,39 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 }
 
 
-// Epilogue of one 32-column chunk of an accumulator row: TMEM -> registers -> (+bias) -> activation -> bf16 -> 64 contiguous bytes.
-// The activation is selected ONCE per chunk (warp-uniform branch) and the bias arrives as 8 x float4: the first version
-// re-decided both per element (~1500 SASS instructions per chunk) and was the bottleneck of every small-K layer
-// (ncu source page of r01: 12.5 k cycles per 128 x 64 tile against 1.2 k tensor-core cycles).
-__device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* __restrict__ bias, int act, bf16* __restrict__ dst, bool ok) {
-    uint32_t r[32];
-    tmem_ld32(taddr, r);
+// 32 lanes x 32 columns WITHOUT the wait: the registers are valid only after tmem_wait_ld32 on the same array
+__device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+}
+// waits for every outstanding tcgen05.ld of this thread; the array is an in/out operand so that no consumer of r is scheduled
+// above the wait
+__device__ __forceinline__ void tmem_wait_ld32(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+          "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+          "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+        :: "memory");
+}
+
+// bias (shared memory, broadcast reads) + activation + bf16 + 64 contiguous bytes for 32 accumulator columns in registers
+__device__ __forceinline__ void epi_store32(const uint32_t* r, const float* sbias, int act, bf16* __restrict__ dst, bool ok) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (bias != nullptr) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias);
+    if (sbias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 b = __ldg(b4 + j);
+            const float4 b = b4[j];
             v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
         }
     }
@@ -155,6 +187,29 @@ __device__ __forceinline__ void epi_chunk(uint32_t taddr, const float* __restric
     }
 }
 
+// Epilogue of one accumulator row of NC x 32 columns.  The TMEM load of chunk c+1 is in flight while chunk c is converted and
+// stored: the first version loaded, waited and processed chunk by chunk, and ncu's source page put 45 % of the epilogue
+// warps' samples on the first use of the tcgen05.ld result (the load competes with the MMAs for TMEM bandwidth), which made
+// every 64-channel layer epilogue-bound (3300 cycles per 128 x 64 tile against 1360 tensor cycles).
+template <int NC>
+__device__ __forceinline__ void epi_row(uint32_t taddr, const float* sbias, int act, bf16* __restrict__ dst, bool ok) {
+    uint32_t r[2][32];
+    tmem_ld32_nw(taddr, r[0]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        tmem_wait_ld32(r[c & 1]);
+        if (c + 1 < NC) tmem_ld32_nw(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+        epi_store32(r[c & 1], sbias ? sbias + c * 32 : nullptr, act, dst + c * 32, ok);
+    }
+}
+
+// copies the layer's bias vector into shared memory (all threads of the CTA; call before the first __syncthreads)
+__device__ __forceinline__ void stage_bias(float* sbias, const float* __restrict__ bias, int n) {
+    if (bias != nullptr)
+        for (int i = threadIdx.x; i < n; i += blockDim.x) sbias[i] = __ldg(bias + i);
+}
+constexpr int BIAS_SMEM = 4096;          // up to 1024 output channels
+
 // ------------------------------------------------------------------------------------------------
 // forward / dgrad kernel
 // ------------------------------------------------------------------------------------------------
@@ -179,7 +234,7 @@ struct TcCfg {
     static constexpr int B_BYTES = BN * 128;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int STAGES = (BN == 64) ? 8 : 6;
-    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + BIAS_SMEM;
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -197,10 +252,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull = bars + 2 * Cfg::STAGES;       // [2]
     uint64_t* tempty = tfull + 2;                   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* sbias = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int niter = p.ntaps * p.kchunks;
+    stage_bias(sbias, p.bias, p.Nn);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -215,8 +272,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===== TMA producer =====
-        if (lane == 0) {
+        // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
+        {
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
@@ -228,38 +285,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int cy = qy0 * p.IS + p.dy[t], cx = qx0 * p.IS + p.dx[t];
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(&empty[stage], phase ^ 1);
-                        mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                        tma_load_4d(sA + stage * A_BYTES, &tmA, &full[stage], kc * 64, cx, cy, img0);
-                        tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kc * 64, p.wrow[t] + nt * BN);
+                        if (elect_one_sync()) {
+                            mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                            tma_load_4d(sA + stage * A_BYTES, &tmA, &full[stage], kc * 64, cx, cy, img0);
+                            tma_load_2d(sB + stage * Cfg::B_BYTES, &tmB, &full[stage], kc * 64, p.wrow[t] + nt * BN);
+                        }
+                        __syncwarp();
                         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-            int stage = 0; uint32_t phase = 0;
-            int local = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-                const int as = local & 1;
-                mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+        // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
+        constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+        int stage = 0; uint32_t phase = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            for (int it = 0; it < niter; ++it) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int it = 0; it < niter; ++it) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
+                if (elect_one_sync()) {
                     const uint64_t adesc = make_desc_sw128(smem_u32(sA + stage * A_BYTES), 16, 1024);
                     const uint64_t bdesc = make_desc_sw128(smem_u32(sB + stage * Cfg::B_BYTES), 16, 1024);
 #pragma unroll
                     for (int k = 0; k < 4; ++k)      // 4 x (K = 16) per 64-channel chunk: +32 bytes inside the swizzle row
                         umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it | k) != 0);
                     umma_commit(&empty[stage]);
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[as]);
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one_sync()) umma_commit(&tfull[as]);
+            __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM -> registers -> bias + activation -> bf16 -> global =====
@@ -281,10 +343,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bf16* dst = p.out + ((long long)(img * p.Hout + oy) * p.Wout + ox) * p.ldout + nt * BN;
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c)
-                epi_chunk(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32),
-                          p.bias ? p.bias + nt * BN + c * 32 : nullptr, p.act, dst + c * 32, ok);
+            epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN), p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
@@ -325,7 +384,7 @@ template <int KC, int BN>
 struct HaloCfg {
     static constexpr int W_BYTES = 9 * KC * BN * 128;
     static constexpr int STAGES = (W_BYTES <= 73728) ? 6 : 3;
-    static constexpr int SMEM = W_BYTES + STAGES * HALO_STAGE + 1024 + 256;
+    static constexpr int SMEM = W_BYTES + STAGES * HALO_STAGE + 1024 + 256 + BIAS_SMEM;
     static constexpr int TMEM_COLS = 2 * BN;
 };
 
@@ -344,9 +403,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* tempty = tfull + 2;                         // [2]
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* sbias = reinterpret_cast<float*>(sA + Cfg::STAGES * HALO_STAGE + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_img = p.tiles_x * p.tiles_y;
+    stage_bias(sbias, p.bias, BN);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -362,39 +423,45 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             // weights of every tap, once
-            mbar_expect_tx(wbar, Cfg::W_BYTES);
-            for (int t = 0; t < 9; ++t)
-                for (int kc = 0; kc < KC; ++kc)
-                    tma_load_2d(sW + (t * KC + kc) * (BN * 128), &tmB, wbar, kc * 64, p.wrow[t]);
+            if (elect_one_sync()) {
+                mbar_expect_tx(wbar, Cfg::W_BYTES);
+                for (int t = 0; t < 9; ++t)
+                    for (int kc = 0; kc < KC; ++kc)
+                        tma_load_2d(sW + (t * KC + kc) * (BN * 128), &tmB, wbar, kc * 64, p.wrow[t]);
+            }
+            __syncwarp();
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int img = tile / per_img; const int r = tile - img * per_img;
                 const int y0 = (r / p.tiles_x) * 16 + p.oy, x0 = (r % p.tiles_x) * 8 + p.ox;
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1);
-                    mbar_expect_tx(&full[stage], HALO_BYTES);
-                    tma_load_4d(sA + stage * HALO_STAGE, &tmA, &full[stage], kc * 64, x0, y0, img);
+                    if (elect_one_sync()) {
+                        mbar_expect_tx(&full[stage], HALO_BYTES);
+                        tma_load_4d(sA + stage * HALO_STAGE, &tmA, &full[stage], kc * 64, x0, y0, img);
+                    }
+                    __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
-            mbar_wait(wbar, 0);
-            int stage = 0; uint32_t phase = 0;
-            int local = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
-                const int as = local & 1;
-                mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+        constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+        mbar_wait(wbar, 0);
+        int stage = 0; uint32_t phase = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * BN;
+            for (int kc = 0; kc < KC; ++kc) {
+                mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
-                for (int kc = 0; kc < KC; ++kc) {
-                    mbar_wait(&full[stage], phase);
-                    tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA + stage * HALO_STAGE);
+                const uint32_t a0 = smem_u32(sA + stage * HALO_STAGE);
+                if (elect_one_sync()) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
                         const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(p.tdy[t] * HALO_W + p.tdx[t]) * 128u, 16, HALO_W * 128);
@@ -404,10 +471,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
                     }
                     umma_commit(&empty[stage]);
-                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull[as]);
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
+            if (elect_one_sync()) umma_commit(&tfull[as]);
+            __syncwarp();
         }
     } else {
         const int quad = warp & 3;
@@ -421,10 +490,17 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             bf16* dst = p.out + ((long long)(img * p.H + oy) * p.W + ox) * p.ldout;
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c)
-                epi_chunk(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN + c * 32),
-                          p.bias ? p.bias + c * 32 : nullptr, p.act, dst + c * 32, true);
+            {
+                constexpr int NC = BN / 32;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+                uint32_t r[NC][32];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) tmem_ld32_nw(taddr + (uint32_t)(c * 32), r[c]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) tmem_wait_ld32(r[c]);
+#pragma unroll
+                for (int c = 0; c < NC; ++c) epi_store32(r[c], p.bias ? sbias + c * 32 : nullptr, p.act, dst + c * 32, true);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
@@ -436,53 +512,64 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// big halo kernel: stride-1 3x3 convolutions with many channels (K * N > 8192: every 128..1024-channel generator layer,
-// forward and dgrad).  The generic kernel moves 32 KB of operands per four 128x128x16 MMAs (8 KB/MMA, 128 B/clk/SM from L2)
-// and tops out near 1050 TFLOP/s.  Here a CTA owns a 32 x 8-pixel tile (TWO 128-row accumulators) x 128 output channels:
-//   * per 64-channel k-chunk ONE TMA box brings the 34 x 10 halo (43.5 KB), and the nine taps x two M-tiles are shifted smem
-//     descriptors into it (as in conv_halo_kernel);
-//   * each 16 KB weight tile (tap, k-chunk) is streamed through its own ring and used by BOTH M-tiles (8 MMAs per tile);
-//   => 191 KB per 72 MMAs = 2.7 KB/MMA (3x less L2->SM traffic), accumulators double-buffered in all 512 TMEM columns.
+// multi-accumulator halo kernel.  One TMA box per 64-channel k-chunk brings the halo of a tile of lattice points; every tap is
+// a shifted smem descriptor into it (as in conv_halo_kernel); each 64-channel weight tile (tap, k-chunk) is streamed through
+// its own ring and feeds one or two accumulators.  Two configurations:
+//   * "big": stride-1 3x3 convolutions with many channels (K * N > 8192: every 128..1024-channel generator layer, fwd and
+//     dgrad).  32 x 8-pixel tile = TWO 128-row accumulators per weight tile: 191 KB of operands per 72 MMAs (2.7 KB/MMA against
+//     the generic kernel's 8 KB/MMA) -> 1220-1410 TFLOP/s instead of 900-1100 (profiles/r01_conv_big_layers.txt).
+//   * "scatter": Conv2DTranspose(k, s=2) forward and the dgrad of a stride-2 Conv2D: the FOUR output-parity classes of a
+//     16 x 8 input tile are four accumulators fed from ONE halo tile (the generic path launched one kernel per class, each
+//     re-reading the input), written with output stride 2.
+// Accumulator sets are double-buffered in TMEM when two sets fit in the 512 columns.
 // ------------------------------------------------------------------------------------------------
 constexpr int BIG_H = 34;                                      // (32 + 2) halo rows of HALO_W pixels
-constexpr int BIG_A_TX = BIG_H * HALO_W * 128;                 // 43520 bytes written by TMA
-constexpr int BIG_A_ST = 44032;                                // rounded up to 1024
-constexpr int BIG_B_ST = 128 * 128;                            // 128 output channels x 64 bf16
-constexpr int BIG_A_STAGES = 2, BIG_B_STAGES = 8;
-constexpr int BIG_SMEM = BIG_A_STAGES * BIG_A_ST + BIG_B_STAGES * BIG_B_ST + 1024 + 256;
-struct BigParams {
-    int ntaps; int tdy[9], tdx[9], wrow[9];   // tap offsets relative to the halo origin (0..2), first weight row of the tap
-    int oy, ox;                               // halo origin relative to the tile origin
-    int kchunks;
-    int tiles_x, tiles_y, m_tiles, n_tiles;
-    int H, W, ldout;
+constexpr int BIG_A_ST = 44032;                                // 34 * 10 * 128 = 43520 rounded up to 1024
+constexpr int BIG_A_STAGES = 2;
+template <int BN>
+struct MultiCfg {
+    static constexpr int B_ST = BN * 128;
+    static constexpr int B_STAGES = 131072 / B_ST;             // 8 (BN = 128) or 16 (BN = 64)
+    static constexpr int SMEM = BIG_A_STAGES * BIG_A_ST + B_STAGES * B_ST + 1024 + 512 + BIAS_SMEM;
+};
+struct MultiParams {
+    int ntaps; int wrow[9]; int npairs[9]; int aoff[9][2]; int acc[9][2]; int first[9][2];
+    int nacc; int row_dy[4], py[4], px[4];
+    int OS, TH, a_bytes, hy, hx;              // output stride, tile height, bytes of the halo box, halo origin relative to the tile origin
+    int kchunks, tiles_x, tiles_y, m_tiles, n_tiles;
+    int Hout, Wout, ldout;
     const float* bias; int act;
     bf16* out;
 };
 
+template <int BN, int NBUF, int NPAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_big_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const BigParams p) {
+conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const MultiParams p) {
+    using Cfg = MultiCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
     uint8_t* sB = smem + BIG_A_STAGES * BIG_A_ST;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + BIG_B_STAGES * BIG_B_ST);
-    uint64_t* fullA = bars;                              // [2]
-    uint64_t* emptyA = fullA + BIG_A_STAGES;             // [2]
-    uint64_t* fullB = emptyA + BIG_A_STAGES;             // [8]
-    uint64_t* emptyB = fullB + BIG_B_STAGES;             // [8]
-    uint64_t* tfull = emptyB + BIG_B_STAGES;             // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + Cfg::B_STAGES * Cfg::B_ST);
+    uint64_t* fullA = bars;
+    uint64_t* emptyA = fullA + BIG_A_STAGES;
+    uint64_t* fullB = emptyA + BIG_A_STAGES;
+    uint64_t* emptyB = fullB + Cfg::B_STAGES;
+    uint64_t* tfull = emptyB + Cfg::B_STAGES;            // [2]
     uint64_t* tempty = tfull + 2;                        // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* sbias = reinterpret_cast<float*>(sB + Cfg::B_STAGES * Cfg::B_ST + 512);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = p.m_tiles * p.n_tiles;
     const int per_img = p.tiles_x * p.tiles_y;
+    const int set_cols = p.nacc * BN;
+    stage_bias(sbias, p.bias, p.n_tiles * BN);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
         for (int i = 0; i < BIG_A_STAGES; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
-        for (int i = 0; i < BIG_B_STAGES; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < Cfg::B_STAGES; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
         fence_barrier_init();
     }
@@ -493,60 +580,75 @@ conv_big_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
             for (int item = blockIdx.x; item < total; item += gridDim.x) {
                 const int nt = item % p.n_tiles, mt = item / p.n_tiles;
                 const int img = mt / per_img; const int r = mt - img * per_img;
-                const int y0 = (r / p.tiles_x) * 32 + p.oy, x0 = (r % p.tiles_x) * 8 + p.ox;
+                const int y0 = (r / p.tiles_x) * p.TH + p.hy, x0 = (r % p.tiles_x) * 8 + p.hx;
                 for (int kc = 0; kc < p.kchunks; ++kc) {
                     mbar_wait(&emptyA[sa], pha ^ 1);
-                    mbar_expect_tx(&fullA[sa], BIG_A_TX);
-                    tma_load_4d(sA + sa * BIG_A_ST, &tmA, &fullA[sa], kc * 64, x0, y0, img);
+                    if (elect_one_sync()) {
+                        mbar_expect_tx(&fullA[sa], p.a_bytes);
+                        tma_load_4d(sA + sa * BIG_A_ST, &tmA, &fullA[sa], kc * 64, x0, y0, img);
+                    }
+                    __syncwarp();
                     if (++sa == BIG_A_STAGES) { sa = 0; pha ^= 1; }
                     for (int t = 0; t < p.ntaps; ++t) {
                         mbar_wait(&emptyB[sb], phb ^ 1);
-                        mbar_expect_tx(&fullB[sb], BIG_B_ST);
-                        tma_load_2d(sB + sb * BIG_B_ST, &tmB, &fullB[sb], kc * 64, p.wrow[t] + nt * 128);
-                        if (++sb == BIG_B_STAGES) { sb = 0; phb ^= 1; }
+                        if (elect_one_sync()) {
+                            mbar_expect_tx(&fullB[sb], Cfg::B_ST);
+                            tma_load_2d(sB + sb * Cfg::B_ST, &tmB, &fullB[sb], kc * 64, p.wrow[t] + nt * BN);
+                        }
+                        __syncwarp();
+                        if (++sb == Cfg::B_STAGES) { sb = 0; phb ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, 128, 0, 0);
-            int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-            int local = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x, ++local) {
-                const int as = local & 1;
-                mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+        constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+        int local = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x, ++local) {
+            const int as = local % NBUF;
+            mbar_wait(&tempty[as], ((local / NBUF) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + as * set_cols;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&fullA[sa], pha);
                 tc_fence_after();
-                const uint32_t d0 = tmem_base + as * 256;
-                for (int kc = 0; kc < p.kchunks; ++kc) {
-                    mbar_wait(&fullA[sa], pha);
-                    tc_fence_after();
-                    const uint32_t a0 = smem_u32(sA + sa * BIG_A_ST);
-                    for (int t = 0; t < p.ntaps; ++t) {
+                const uint32_t a0 = smem_u32(sA + sa * BIG_A_ST);
+                // fully unrolled over the (at most nine) taps: the per-tap parameters become constant-bank operands
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    if (t < p.ntaps) {
                         mbar_wait(&fullB[sb], phb);
                         tc_fence_after();
-                        const uint64_t bdesc = make_desc_sw128(smem_u32(sB + sb * BIG_B_ST), 16, 1024);
-                        const uint32_t aoff = a0 + (uint32_t)(p.tdy[t] * HALO_W + p.tdx[t]) * 128u;
+                        if (elect_one_sync()) {
+                            const uint64_t bdesc = make_desc_sw128(smem_u32(sB + sb * Cfg::B_ST), 16, 1024);
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            const uint64_t adesc = make_desc_sw128(aoff + (uint32_t)half * (16 * HALO_W * 128), 16, HALO_W * 128);
+                            for (int j = 0; j < NPAIR; ++j) {
+                                const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)p.aoff[t][j] * 128u, 16, HALO_W * 128);
+                                const uint32_t keep = (kc == 0 && p.first[t][j]) ? 0u : 1u;
+                                const uint32_t dcol = d0 + p.acc[t][j] * BN;
+                                umma_bf16(dcol, adesc, bdesc, idesc, keep);
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(d0 + half * 128, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+                                for (int k = 1; k < 4; ++k)
+                                    umma_bf16(dcol, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+                            }
+                            umma_commit(&emptyB[sb]);
                         }
-                        umma_commit(&emptyB[sb]);
-                        if (++sb == BIG_B_STAGES) { sb = 0; phb ^= 1; }
+                        __syncwarp();
+                        if (++sb == Cfg::B_STAGES) { sb = 0; phb ^= 1; }
                     }
-                    umma_commit(&emptyA[sa]);
-                    if (++sa == BIG_A_STAGES) { sa = 0; pha ^= 1; }
                 }
-                umma_commit(&tfull[as]);
+                if (elect_one_sync()) umma_commit(&emptyA[sa]);
+                __syncwarp();
+                if (++sa == BIG_A_STAGES) { sa = 0; pha ^= 1; }
             }
+            if (elect_one_sync()) umma_commit(&tfull[as]);
+            __syncwarp();
         }
     } else {
         const int quad = warp & 3;
@@ -554,19 +656,19 @@ conv_big_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int ty = row >> 3, tx = row & 7;
         int local = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x, ++local) {
-            const int as = local & 1;
+            const int as = local % NBUF;
             const int nt = item % p.n_tiles, mt = item / p.n_tiles;
             const int img = mt / per_img; const int r = mt - img * per_img;
-            const int oy = (r / p.tiles_x) * 32 + ty, ox = (r % p.tiles_x) * 8 + tx;
-            mbar_wait(&tfull[as], (local >> 1) & 1);
+            const int qy = (r / p.tiles_x) * p.TH + ty, qx = (r % p.tiles_x) * 8 + tx;
+            mbar_wait(&tfull[as], (local / NBUF) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                bf16* dst = p.out + ((long long)(img * p.H + oy + half * 16) * p.W + ox) * p.ldout + nt * 128;
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c)
-                    epi_chunk(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 256 + half * 128 + c * 32),
-                              p.bias ? p.bias + nt * 128 + c * 32 : nullptr, p.act, dst + c * 32, true);
+            for (int a = 0; a < p.nacc; ++a) {
+                const int oy = (qy + p.row_dy[a]) * p.OS + p.py[a], ox = qx * p.OS + p.px[a];
+                const bool ok = oy < p.Hout && ox < p.Wout;
+                bf16* dst = p.out + ((long long)(img * p.Hout + oy) * p.Wout + ox) * p.ldout + nt * BN;
+                epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN), p.bias ? sbias + nt * BN : nullptr,
+                                 p.act, dst, ok);
             }
             tc_fence_before();
             __syncwarp();
@@ -704,37 +806,89 @@ bool halo_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
     return kh == 3 && kw == 3 && stride == 1 && H % 16 == 0 && W % 8 == 0 && (K == 64 || K == 128) && (Nn == 64 || Nn == 128) && K * Nn <= 8192;
 }
 
-// stride-1 3x3 layers the big halo kernel serves
+template <int BN, int NBUF, int NPAIR>
+int launch_multi_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const MultiParams& p, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_multi_kernel<BN, NBUF, NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, MultiCfg<BN>::SMEM); attr = true; }
+    const int total = p.m_tiles * p.n_tiles;
+    int grid = shm_num_sms();
+    if (grid > total) grid = total;
+    conv_multi_kernel<BN, NBUF, NPAIR><<<grid, TC_THREADS, MultiCfg<BN>::SMEM, st>>>(tmA, tmB, p);
+    SHM_CHECK_LAUNCH("conv_multi_kernel");
+    return SHM_OK;
+}
+
+// stride-1 3x3 layers the "big" configuration serves
 bool big_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
     return kh == 3 && kw == 3 && stride == 1 && H % 32 == 0 && W % 8 == 0 && K % 64 == 0 && Nn % 128 == 0;
 }
 
 int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
                void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st) {
-    BigParams p{};
+    MultiParams p{};
     int miny = 9, minx = 9;
     for (int t = 0; t < 9; ++t) { if (tdy[t] < miny) miny = tdy[t]; if (tdx[t] < minx) minx = tdx[t]; }
     p.ntaps = 9;
     for (int t = 0; t < 9; ++t) {
-        p.tdy[t] = tdy[t] - miny; p.tdx[t] = tdx[t] - minx; p.wrow[t] = twrow[t];
-        if (p.tdy[t] > 2 || p.tdx[t] > 2) SHM_FAIL(SHM_EUNSUPPORTED, "conv_big: tap offsets exceed the 1-pixel halo");
+        const int dy = tdy[t] - miny, dx = tdx[t] - minx;
+        if (dy > 2 || dx > 2) SHM_FAIL(SHM_EUNSUPPORTED, "conv_big: tap offsets exceed the 1-pixel halo");
+        p.wrow[t] = twrow[t]; p.npairs[t] = 2;
+        p.aoff[t][0] = dy * HALO_W + dx; p.aoff[t][1] = p.aoff[t][0] + 16 * HALO_W;
+        p.acc[t][0] = 0; p.acc[t][1] = 1;
+        p.first[t][0] = p.first[t][1] = (t == 0);
     }
-    p.oy = miny; p.ox = minx;
+    p.nacc = 2; p.row_dy[0] = 0; p.row_dy[1] = 16;
+    p.OS = 1; p.TH = 32; p.a_bytes = BIG_H * HALO_W * 128; p.hy = miny; p.hx = minx;
     p.kchunks = K / 64;
     p.tiles_x = W / 8; p.tiles_y = H / 32;
     p.m_tiles = N * p.tiles_x * p.tiles_y; p.n_tiles = Nn / 128;
-    p.H = H; p.W = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
+    p.Hout = H; p.Wout = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
     CUtensorMap tmA, tmB;
     if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, BIG_H)) return rc;
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 128)) return rc;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(conv_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG_SMEM); attr = true; }
-    const int total = p.m_tiles * p.n_tiles;
-    int grid = shm_num_sms();
-    if (grid > total) grid = total;
-    conv_big_kernel<<<grid, TC_THREADS, BIG_SMEM, st>>>(tmA, tmB, p);
-    SHM_CHECK_LAUNCH("conv_big_kernel");
-    return SHM_OK;
+    return launch_multi_t<128, 2, 2>(tmA, tmB, p, st);
+}
+
+// "scatter" configuration: out[(q + .) * 2 + r] classes of a stride-2 scatter (Conv2DTranspose fwd, strided-Conv2D dgrad).
+// Per class (ry, rx) the caller lists its taps as offsets (dy, dx) in {-1, 0} on the input lattice and their weight rows.
+bool scatter_ok(int Hq, int Wq, int K, int Nn) {
+    return Hq % 16 == 0 && Wq % 8 == 0 && K % 64 == 0 && Nn % 64 == 0;
+}
+
+struct ScatterTap { int ry, rx, dy, dx, wrow; };
+
+int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
+                   void* out, int Hout, int Wout, int ldout, const ScatterTap* taps, int ntaps, cudaStream_t st) {
+    MultiParams p{};
+    if (ntaps > 9) SHM_FAIL(SHM_EUNSUPPORTED, "conv_scatter: more than 9 taps");
+    bool seen[4] = {false, false, false, false};
+    p.ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) {
+        const ScatterTap& tp = taps[t];
+        if (tp.dy < -1 || tp.dy > 0 || tp.dx < -1 || tp.dx > 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_scatter: tap offset outside {-1, 0}");
+        const int a = tp.ry * 2 + tp.rx;
+        p.wrow[t] = tp.wrow; p.npairs[t] = 1;
+        p.aoff[t][0] = (tp.dy + 1) * HALO_W + (tp.dx + 1);
+        p.acc[t][0] = a; p.first[t][0] = seen[a] ? 0 : 1;
+        seen[a] = true;
+    }
+    for (int a = 0; a < 4; ++a) {
+        if (!seen[a]) SHM_FAIL(SHM_EUNSUPPORTED, "conv_scatter: parity class without taps");
+        p.row_dy[a] = 0; p.py[a] = a >> 1; p.px[a] = a & 1;
+    }
+    p.nacc = 4;
+    p.OS = 2; p.TH = 16; p.a_bytes = HALO_H * HALO_W * 128; p.hy = -1; p.hx = -1;
+    p.kchunks = K / 64;
+    p.tiles_x = Wq / 8; p.tiles_y = Hq / 16;
+    p.m_tiles = N * p.tiles_x * p.tiles_y;
+    p.Hout = Hout; p.Wout = Wout; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
+    const int BN = (Nn % 128 == 0) ? 128 : 64;
+    p.n_tiles = Nn / BN;
+    CUtensorMap tmA, tmB;
+    if (int rc = encode_act_box(&tmA, in, K, Wq, Hq, N, ldin, HALO_W, HALO_H)) return rc;
+    if (int rc = encode_w(&tmB, w_tc, K, wrows_total, BN)) return rc;
+    if (BN == 128) return launch_multi_t<128, 1, 1>(tmA, tmB, p, st);   // 4 x 128 columns: one accumulator set
+    return launch_multi_t<64, 2, 1>(tmA, tmB, p, st);                   // 4 x 64 columns, double-buffered
 }
 
 template <int KC, int BN>
@@ -835,7 +989,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             const int per_img = p.tiles_x * p.tiles_y;
             for (int kb = kb0; kb < kb1; ++kb) {
@@ -843,26 +997,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 if (p.BI > 1) { img0 = kb * p.BI; qy0 = 0; qx0 = 0; }
                 else { img0 = kb / per_img; const int r = kb - img0 * per_img; qy0 = (r / p.tiles_x) * p.BH; qx0 = (r % p.tiles_x) * p.BW; }
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
-                uint8_t* a = sA + stage * Cfg::A_ST;
-                uint8_t* b = sB + stage * Cfg::B_ST;
-                tma_load_4d(a, &tmA, &full[stage], cb0 * 64, qx0 * p.SA + p.dax[tap0], qy0 * p.SA + p.day[tap0], img0);
-                tma_load_4d(a + 8192, &tmA, &full[stage], cb1 * 64, qx0 * p.SA + p.dax[tap1], qy0 * p.SA + p.day[tap1], img0);
-                // the B operand is shifted by its own tap offset (zero for Conv2D where B = dy): both M-blocks of a tile must
-                // therefore share the B offset, which holds because offB != 0 only when cblocks >= 2 pairs blocks of ONE tap
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
+                    uint8_t* a = sA + stage * Cfg::A_ST;
+                    uint8_t* b = sB + stage * Cfg::B_ST;
+                    tma_load_4d(a, &tmA, &full[stage], cb0 * 64, qx0 * p.SA + p.dax[tap0], qy0 * p.SA + p.day[tap0], img0);
+                    tma_load_4d(a + 8192, &tmA, &full[stage], cb1 * 64, qx0 * p.SA + p.dax[tap1], qy0 * p.SA + p.day[tap1], img0);
+                    // the B operand is shifted by its own tap offset (zero for Conv2D where B = dy): both M-blocks of a tile must
+                    // therefore share the B offset, which holds because offB != 0 only when cblocks >= 2 pairs blocks of ONE tap
 #pragma unroll
-                for (int j = 0; j < BN / 64; ++j)
-                    tma_load_4d(b + j * 8192, &tmB, &full[stage], nt * BN + j * 64, qx0 * p.SB + p.dbx[tap0], qy0 * p.SB + p.dby[tap0], img0);
+                    for (int j = 0; j < BN / 64; ++j)
+                        tma_load_4d(b + j * 8192, &tmB, &full[stage], nt * BN + j * 64, qx0 * p.SB + p.dbx[tap0], qy0 * p.SB + p.dby[tap0], img0);
+                }
+                __syncwarp();
                 if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
-            int stage = 0; uint32_t phase = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                mbar_wait(&full[stage], phase);
-                tc_fence_after();
+        constexpr uint32_t idesc = make_idesc(128, BN, 1, 1);
+        int stage = 0; uint32_t phase = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            if (elect_one_sync()) {
                 // MN-major SW128: 64-channel atoms LBO = 8192 bytes apart, 8-point K groups SBO = 1024 bytes apart
                 const uint64_t adesc = make_desc_sw128(smem_u32(sA + stage * Cfg::A_ST), 8192, 1024);
                 const uint64_t bdesc = make_desc_sw128(smem_u32(sB + stage * Cfg::B_ST), 8192, 1024);
@@ -870,10 +1027,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 for (int k = 0; k < 4; ++k)      // 16 points per MMA = 2048 bytes
                     umma_bf16(tmem_base, adesc + (uint64_t)(k * 128), bdesc + (uint64_t)(k * 128), idesc, (kb > kb0) || (k > 0));
                 umma_commit(&empty[stage]);
-                if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(tfull);
+            __syncwarp();
+            if (++stage == WG_STAGES) { stage = 0; phase ^= 1; }
         }
+        if (elect_one_sync()) umma_commit(tfull);
+        __syncwarp();
     } else if (kb1 > kb0) {
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
@@ -977,60 +1136,67 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
+        {
             int stage = 0; uint32_t phase = 0;
             for (int t = t0; t < t1; ++t) {
                 const int img = t / per_img; const int r = t - img * per_img;
                 const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
                 mbar_wait(&empty[stage], phase ^ 1);
-                mbar_expect_tx(&full[stage], Cfg::A_BYTES_TX + Cfg::B_ST);
-                uint8_t* a = sA + stage * Cfg::A_ST;
-                uint8_t* b = sB + stage * Cfg::B_ST;
-                if (MODE == 0) {
-                    tma_load_4d(a, &tmX, &full[stage], cb * 64, x0 - 1, y0 - 1, img);
-                    tma_load_4d(b, &tmDY, &full[stage], nb * 64, x0, y0, img);
-                } else {
-                    tma_load_4d(a, &tmX, &full[stage], cb * 128, x0 - 1, y0 - 1 + frow, img);
-                    tma_load_4d(a + Cfg::A_ONE, &tmX, &full[stage], cb * 128 + 64, x0 - 1, y0 - 1 + frow, img);
-                    tma_load_4d(b, &tmDY, &full[stage], nb * 128, x0, y0, img);
-                    tma_load_4d(b + 16384, &tmDY, &full[stage], nb * 128 + 64, x0, y0, img);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full[stage], Cfg::A_BYTES_TX + Cfg::B_ST);
+                    uint8_t* a = sA + stage * Cfg::A_ST;
+                    uint8_t* b = sB + stage * Cfg::B_ST;
+                    if (MODE == 0) {
+                        tma_load_4d(a, &tmX, &full[stage], cb * 64, x0 - 1, y0 - 1, img);
+                        tma_load_4d(b, &tmDY, &full[stage], nb * 64, x0, y0, img);
+                    } else {
+                        tma_load_4d(a, &tmX, &full[stage], cb * 128, x0 - 1, y0 - 1 + frow, img);
+                        tma_load_4d(a + Cfg::A_ONE, &tmX, &full[stage], cb * 128 + 64, x0 - 1, y0 - 1 + frow, img);
+                        tma_load_4d(b, &tmDY, &full[stage], nb * 128, x0, y0, img);
+                        tma_load_4d(b + 16384, &tmDY, &full[stage], nb * 128 + 64, x0, y0, img);
+                    }
                 }
+                __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0 && t1 > t0) {
+        if (t1 > t0) {
             constexpr uint32_t idesc = make_idesc(128, Cfg::BN, 1, 1);
             int stage = 0; uint32_t phase = 0;
             for (int t = t0; t < t1; ++t) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
-                const uint32_t a0 = smem_u32(sA + stage * Cfg::A_ST);
-                const uint32_t b0 = smem_u32(sB + stage * Cfg::B_ST);
+                if (elect_one_sync()) {
+                    const uint32_t a0 = smem_u32(sA + stage * Cfg::A_ST);
+                    const uint32_t b0 = smem_u32(sB + stage * Cfg::B_ST);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {          // 16 pixels = tile rows 2j, 2j+1 per MMA
-                    const uint64_t bdesc = make_desc_sw128(b0 + j * 2048, 16384, 1024);
-                    const uint32_t acc = (t > t0 || j > 0) ? 1u : 0u;
-                    if (MODE == 0) {
+                    for (int j = 0; j < 8; ++j) {          // 16 pixels = tile rows 2j, 2j+1 per MMA
+                        const uint64_t bdesc = make_desc_sw128(b0 + j * 2048, 16384, 1024);
+                        const uint32_t acc = (t > t0 || j > 0) ? 1u : 0u;
+                        if (MODE == 0) {
 #pragma unroll
-                        for (int pr = 0; pr < 5; ++pr) {
-                            const int ta = 2 * pr, tb = pr < 4 ? 2 * pr + 1 : 8;
-                            const int offa = (ta / 3) * HALO_W + ta % 3, offb = (tb / 3) * HALO_W + tb % 3;
-                            const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(2 * j * HALO_W + offa) * 128u, (uint32_t)(offb - offa) * 128u, HALO_W * 128);
-                            umma_bf16(tmem_base + pr * 64, adesc, bdesc, idesc, acc);
-                        }
-                    } else {
+                            for (int pr = 0; pr < 5; ++pr) {
+                                const int ta = 2 * pr, tb = pr < 4 ? 2 * pr + 1 : 8;
+                                const int offa = (ta / 3) * HALO_W + ta % 3, offb = (tb / 3) * HALO_W + tb % 3;
+                                const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(2 * j * HALO_W + offa) * 128u, (uint32_t)(offb - offa) * 128u, HALO_W * 128);
+                                umma_bf16(tmem_base + pr * 64, adesc, bdesc, idesc, acc);
+                            }
+                        } else {
 #pragma unroll
-                        for (int tx = 0; tx < 3; ++tx) {
-                            const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(2 * j * HALO_W + tx) * 128u, Cfg::A_ONE, HALO_W * 128);
-                            umma_bf16(tmem_base + tx * 128, adesc, bdesc, idesc, acc);
+                            for (int tx = 0; tx < 3; ++tx) {
+                                const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(2 * j * HALO_W + tx) * 128u, Cfg::A_ONE, HALO_W * 128);
+                                umma_bf16(tmem_base + tx * 128, adesc, bdesc, idesc, acc);
+                            }
                         }
                     }
+                    umma_commit(&empty[stage]);
                 }
-                umma_commit(&empty[stage]);
+                __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(tfull);
+            if (elect_one_sync()) umma_commit(tfull);
+            __syncwarp();
         }
     } else if (t1 > t0) {
         const int quad = warp & 3;
@@ -1229,6 +1395,20 @@ extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const vo
     }
     // transposed: out[p] = sum_{o,k: s*o + k - pb = p} x[o] W[k];  p = s*q + r
     const int pby = same_pad_before(Ho, d->kh, s), pbx = same_pad_before(Wo, d->kw, s);
+    if (s == 2 && scatter_ok(d->H, d->W, d->Cin, d->Cout)) {
+        ScatterTap taps[9]; int n = 0; bool fits = true;
+        for (int ry = 0; ry < 2; ++ry) for (int rx = 0; rx < 2; ++rx)
+            for (int ky = 0; ky < d->kh; ++ky) {
+                if (((ry + pby - ky) % 2) != 0) continue;
+                for (int kx = 0; kx < d->kw; ++kx) {
+                    if (((rx + pbx - kx) % 2) != 0) continue;
+                    const int oy = (ry + pby - ky) / 2, ox = (rx + pbx - kx) / 2;
+                    if (oy < -1 || oy > 0 || ox < -1 || ox > 0) fits = false;
+                    taps[n++] = ScatterTap{ry, rx, oy, ox, (ky * d->kw + kx) * d->Cout};
+                }
+            }
+        if (fits) return launch_scatter(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, Ho, Wo, d->ldy, taps, n, st);
+    }
     for (int ry = 0; ry < s; ++ry)
         for (int rx = 0; rx < s; ++rx) {
             int nt = 0;
@@ -1266,6 +1446,20 @@ extern "C" int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const
     }
     // Conv2D dgrad: dx[p] = sum_{o,k: s*o + k - pb = p} dy[o] W[k]^T  (scatter by parity; one class when s == 1)
     const int pby = same_pad_before(d->H, d->kh, s), pbx = same_pad_before(d->W, d->kw, s);
+    if (s == 2 && d->H % 2 == 0 && d->W % 2 == 0 && scatter_ok(Ho, Wo, d->Cout, d->Cin)) {
+        ScatterTap taps[9]; int n = 0; bool fits = true;
+        for (int ry = 0; ry < 2; ++ry) for (int rx = 0; rx < 2; ++rx)
+            for (int ky = 0; ky < d->kh; ++ky) {
+                if (((ry + pby - ky) % 2) != 0) continue;
+                for (int kx = 0; kx < d->kw; ++kx) {
+                    if (((rx + pbx - kx) % 2) != 0) continue;
+                    const int oy = (ry + pby - ky) / 2, ox = (rx + pbx - kx) / 2;
+                    if (oy < -1 || oy > 0 || ox < -1 || ox > 0) fits = false;
+                    taps[n++] = ScatterTap{ry, rx, oy, ox, (ky * d->kw + kx) * d->Cin};
+                }
+            }
+        if (fits && n <= 9) return launch_scatter(d->N, Ho, Wo, d->Cout, d->Cin, dy, d->ldy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, d->H, d->W, d->ldx, taps, n, st);
+    }
     for (int ry = 0; ry < s; ++ry)
         for (int rx = 0; rx < s; ++rx) {
             int nt = 0;

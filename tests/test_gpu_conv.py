@@ -126,6 +126,12 @@ TC_CASES = [
     (1, 64, 16, 256, 128, 3, 1, False, 2, True),    # big halo kernel, four k-chunks (A ring wraps), dgrad has two n-tiles
     (2, 32, 8, 64, 256, 3, 1, False, 0, True),      # big halo kernel fwd with two n-tiles, single k-chunk
     (10, 64, 64, 128, 256, 3, 1, False, 1, True),   # big halo kernel, 320 work items: persistent loop, accumulator double buffering
+    (2, 16, 16, 128, 64, 3, 2, True, 1, True),      # scatter kernel: Conv2DTranspose fwd, four parity accumulators x 64 columns
+    (1, 32, 16, 256, 128, 3, 2, True, 1, True),     # scatter kernel, 4 x 128 columns (single accumulator set), four k-chunks
+    (3, 16, 8, 64, 128, 2, 2, True, 0, True),       # scatter kernel, k2 s2 transposed conv (SpecSeg up path)
+    (2, 64, 64, 128, 256, 3, 2, False, 1, False),   # stride-2 conv: dgrad through the scatter kernel (K = 256, N = 128)
+    (20, 32, 32, 128, 128, 3, 2, True, 1, True),    # scatter kernel, 160 work items on one accumulator set (persistent loop)
+    (40, 16, 16, 64, 64, 3, 2, True, 1, True),      # scatter kernel, 80 x ... double-buffered sets across many items
 ]
 
 
