@@ -27,6 +27,19 @@ __device__ __forceinline__ void stat_ab(const double* __restrict__ sums, int n, 
     rstd = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+// cheap variant for the bf16 fast paths: one 16-byte load, fp64 only for the cancellation-prone variance, float rsqrt.
+// (the exact version above costs ~100+ instructions per channel in fp64 division / sqrt sequences, which dominated the deep
+// levels where a thread owns 8 channels but only ~20 pixels)
+__device__ __forceinline__ void stat_ab_fast(const double* __restrict__ sums, int n, int C, int c, double inv_hw, float eps,
+                                             float& mean, float& rstd) {
+    const double2 sq = __ldg(reinterpret_cast<const double2*>(sums + ((long long)n * C + c) * 2));
+    const double m = sq.x * inv_hw;
+    double var = fma(-m, m, sq.y * inv_hw);
+    if (var < 0.0) var = 0.0;
+    mean = (float)m;
+    rstd = rsqrtf((float)var + eps);
+}
+
 // ---------------------------------------------------------------------------------------------
 // stats: sums[n][c] += (sum x, sum x^2)
 // ---------------------------------------------------------------------------------------------
@@ -318,11 +331,12 @@ __global__ void __launch_bounds__(256) inorm_apply8_kernel(const bf16* __restric
     const int n = blockIdx.z;
     const int c0 = tx * 8;
     const int HW = H * W;
+    const double inv_hw = 1.0 / (double)HW;
     float a[8], b[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float mean, rstd;
-        stat_ab(sums, n, C, c0 + j, HW, eps, mean, rstd);
+        stat_ab_fast(sums, n, C, c0 + j, inv_hw, eps, mean, rstd);
         a[j] = rstd * __ldg(gamma + c0 + j);
         b[j] = __ldg(beta + c0 + j) - mean * a[j];
     }
@@ -407,8 +421,9 @@ __global__ void __launch_bounds__(256) inorm_bwd_stats8_kernel(const bf16* __res
     const int c0 = tx * 8;
     const int pbeg = blockIdx.x * ppb, pend = min(pbeg + ppb, HW);
     float mean[8], rstd[8], a[16];
+    const double inv_hw = 1.0 / (double)HW;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { stat_ab(sums, n, C, c0 + j, HW, eps, mean[j], rstd[j]); a[j] = 0.f; a[8 + j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { stat_ab_fast(sums, n, C, c0 + j, inv_hw, eps, mean[j], rstd[j]); a[j] = 0.f; a[8 + j] = 0.f; }
     const bf16* xb = x + (long long)n * HW * ldx + c0;
     const bf16* da = dyA ? dyA + (long long)n * HW * ldA + c0 : nullptr;
     const bf16* dp = dyP ? dyP + (long long)n * (HW / 4) * ldP + c0 : nullptr;
@@ -449,13 +464,15 @@ __global__ void __launch_bounds__(256) inorm_bwd_apply8_kernel(const bf16* __res
     const int c0 = tx * 8;
     // r = g * (k0 + k1 * d + k2 * v) with g = act'(v):  a*(d - m1 - (v-mean)*rstd*m2)
     float k0[8], k1[8], k2[8], s[8];
+    const double inv_hw = 1.0 / (double)HW;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         float mean, rstd;
-        stat_ab(sums, n, C, c0 + j, HW, eps, mean, rstd);
+        stat_ab_fast(sums, n, C, c0 + j, inv_hw, eps, mean, rstd);
         const float a = rstd * __ldg(gamma + c0 + j);
-        const float m1 = (float)(bsums[((long long)n * C + c0 + j) * 2 + 0] / HW);
-        const float m2 = (float)(bsums[((long long)n * C + c0 + j) * 2 + 1] / HW);
+        const double2 bs = __ldg(reinterpret_cast<const double2*>(bsums + ((long long)n * C + c0 + j) * 2));
+        const float m1 = (float)(bs.x * inv_hw);
+        const float m2 = (float)(bs.y * inv_hw);
         k1[j] = a; k2[j] = -a * rstd * m2; k0[j] = -a * m1 + a * rstd * m2 * mean;
         s[j] = 0.f;
     }
@@ -546,7 +563,7 @@ inline int ppb8(long long units, int TY, int N) {
     long long want = (long long)shm_num_sms() * 8 / (N > 0 ? N : 1);
     if (want < 1) want = 1;
     long long upb = cdiv64(units, want);
-    const long long lo = (long long)TY * 8, hi = (long long)TY * 128;
+    const long long lo = (long long)TY * 32, hi = (long long)TY * 128;
     if (upb < lo) upb = lo;
     if (upb > hi) upb = hi;
     return (int)upb;

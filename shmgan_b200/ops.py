@@ -296,7 +296,8 @@ class PaddedConv(Conv):
 def inorm_stats(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
     sums = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
-    call("shm_inorm_stats", _p(x), n, h * w, c, ld(x), dt(x), _p(sums), _stream())
+    _prof("norm", "stats", "c%d" % c, 0, x.numel() * x.element_size(),
+          lambda: call("shm_inorm_stats", _p(x), n, h * w, c, ld(x), dt(x), _p(sums), _stream()))
     return sums
 
 
@@ -306,8 +307,10 @@ def inorm_apply(x, sums, gamma, beta, add=None, out=None, pooled=False, want_out
     if out is None and want_out:
         out = new((n, h, w, c), x.dtype)
     pl = new((n, h // 2, w // 2, c), x.dtype) if pooled else None
-    call("shm_inorm_apply", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), _p(gamma), _p(beta), IN_EPS,
-         _p(add), ld(add), 0 if add is None else add.shape[0], _p(out), ld(out), _p(pl), ld(pl), _stream())
+    nb = x.numel() * x.element_size() * ((1 if out is None else 2) + (0 if add is None else 1) + (0.25 if pooled else 0))
+    _prof("norm", "apply", "c%d" % c, 0, nb,
+          lambda: call("shm_inorm_apply", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), _p(gamma), _p(beta), IN_EPS,
+                       _p(add), ld(add), 0 if add is None else add.shape[0], _p(out), ld(out), _p(pl), ld(pl), _stream()))
     return out, pl
 
 
@@ -316,11 +319,15 @@ def inorm_bwd(x, sums, gamma, dyA=None, dyP=None, act=ACT_LRELU, dx=None, dbias=
     dbias (fp32 [C], optional) += column sums of the result: the producing conv's bias gradient, fused into the same pass."""
     n, h, w, c = x.shape
     bs = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
-    call("shm_inorm_bwd_stats", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), IN_EPS, _p(dyA), ld(dyA), _p(dyP), ld(dyP), _p(bs), _stream())
+    e = x.numel() * x.element_size()
+    rd = e * (1 + (0 if dyA is None else 1) + (0 if dyP is None else 0.25))
+    _prof("norm", "bwd_stats", "c%d" % c, 0, rd,
+          lambda: call("shm_inorm_bwd_stats", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), IN_EPS, _p(dyA), ld(dyA), _p(dyP), ld(dyP), _p(bs), _stream()))
     if dx is None:
         dx = new((n, h, w, c), x.dtype)
-    call("shm_inorm_bwd_apply", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), _p(gamma), IN_EPS, _p(dyA), ld(dyA), _p(dyP), ld(dyP),
-         _p(bs), act, _p(dx), ld(dx), _p(dbias), _stream())
+    _prof("norm", "bwd_apply", "c%d" % c, 0, rd + e,
+          lambda: call("shm_inorm_bwd_apply", _p(x), n, h, w, c, ld(x), dt(x), _p(sums), _p(gamma), IN_EPS, _p(dyA), ld(dyA), _p(dyP), ld(dyP),
+                       _p(bs), act, _p(dx), ld(dx), _p(dbias), _stream()))
     return dx
 
 
@@ -329,7 +336,8 @@ def act_bwd(dy, y, act, out=None, dbias=None):
     n, h, w, c = y.shape
     if out is None:
         out = new((n, h, w, c), y.dtype)
-    call("shm_act_bwd", _p(dy), ld(dy), _p(y), ld(y), _p(out), ld(out), n * h * w, c, act, dt(y), _p(dbias), _stream())
+    _prof("norm", "act_bwd", "c%d" % c, 0, 3 * y.numel() * y.element_size(),
+          lambda: call("shm_act_bwd", _p(dy), ld(dy), _p(y), ld(y), _p(out), ld(out), n * h * w, c, act, dt(y), _p(dbias), _stream()))
     return out
 
 
