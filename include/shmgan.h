@@ -147,6 +147,11 @@ int shm_assemble_input(const float* const src[5], const int32_t src_ld[5], int o
 /* dst (bf16, pixel stride 64) = src channels 0..C-1 (C <= 64) followed by zeros: the zero-padded input that lets the first layers
  * (Cin = 10 / 3 / 1) run on the tensor-core kernels, whose reduction dimension moves in 64-channel TMA boxes */
 int shm_pad_channels64(const void* src, int src_dtype, int lds, int C, void* dst_bf16, int64_t npix, void* stream);
+/* im2col of a 3x3 stride-2 SAME conv on a few-channel image (discriminator d1, ShmGANwithSSpecSeg.py:353): out bf16 [N,H/2,W/2,64],
+ * channel (ky*3+kx)*C + c = x[n, 2oy+ky-pb, 2ox+kx-pb, c] (zero outside / beyond 9*C); d1 then runs as a 1x1 conv on the tensor cores.
+ * col2im is its transpose (the d(image) of the generator-loss path). */
+int shm_im2col_k3s2(const void* x, int src_dtype, int ldx, int N, int H, int W, int C, void* out_bf16, void* stream);
+int shm_col2im_k3s2(const void* dP_bf16, int N, int H, int W, int C, void* dx, int dst_dtype, int lddx, void* stream);
 /* backward of the cyclic assembly: dgen[npix] += sum over listed slots of din[npix,ldin][slot] */
 int shm_assemble_bwd(const void* din, int dtype, int ldin, const int32_t slots[5], int nslots, float* dgen, int64_t npix, void* stream);
 /* yuv_to_rgb(concat(Y, CbCr)) :544,553,613-624.  Y fp32 (ld 1), cbcr fp32 [npix,2]; rgb out fp32 and / or a copy in dtype_lp with pixel

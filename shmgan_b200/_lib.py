@@ -64,6 +64,8 @@ _SIG = {
     "shm_avg_cbcr": [_P, _P, _P, _P, _P, _P, _L, _P],
     "shm_assemble_input": [C.POINTER(_P), C.POINTER(C.c_int32), _I, _P, _I, _L, _I, _P],
     "shm_pad_channels64": [_P, _I, _I, _I, _P, _L, _P],
+    "shm_im2col_k3s2": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
+    "shm_col2im_k3s2": [_P, _I, _I, _I, _I, _P, _I, _I, _P],
     "shm_assemble_bwd": [_P, _I, _I, C.POINTER(C.c_int32), _I, _P, _L, _P],
     "shm_yuv2rgb": [_P, _P, _L, _P, _P, _I, _I, _L, _P],
     "shm_yuv2rgb_bwd": [_P, _P, _I, _I, _P, _L, _I, _P],

@@ -203,6 +203,63 @@ __global__ void pad64_kernel(const S* __restrict__ src, int lds, int C, uint4* _
     }
 }
 
+
+// im2col of a 3x3 stride-2 SAME convolution on a few-channel image (the discriminator's first layer d1: Conv 3 -> 64, s2,
+// ShmGANwithSSpecSeg.py:353,:387).  Presenting the 3-channel image zero-padded to 64 channels moved 128 B per INPUT pixel through
+// every d1 kernel (wgrad ran at 10 TFLOP/s); folding the 27 patch values into the channel axis makes d1 a 1x1 convolution over
+// [N, H/2, W/2, 64] (27 real channels), one 128-byte row per OUTPUT pixel.  channel k = (ky*3 + kx)*C + c.
+template <typename S>
+__global__ void im2col_k3s2_kernel(const S* __restrict__ x, int ldx, int H, int W, int C, int pb, uint4* __restrict__ out, long long nout) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = nout * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long q = i >> 3; const int part = (int)(i & 7);
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (part * 8 < 9 * C) {
+            const int ox = (int)(q % Wo); const long long t = q / Wo; const int oy = (int)(t % Ho); const long long n = t / Ho;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = part * 8 + j;
+                v[j] = 0.f;
+                if (k < 9 * C) {
+                    const int tap = k / C, c = k - tap * C;
+                    const int iy = 2 * oy + tap / 3 - pb, ix = 2 * ox + tap % 3 - pb;
+                    if (iy >= 0 && iy < H && ix >= 0 && ix < W) v[j] = ldf(x + ((n * H + iy) * W + ix) * ldx + c);
+                }
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+        out[i] = u;
+    }
+}
+
+// transpose of the above: dx[n, iy, ix, c] = sum over taps (ky, kx) with 2*oy + ky - pb == iy, 2*ox + kx - pb == ix of dP[n, oy, ox, (ky*3+kx)*C + c]
+template <typename D>
+__global__ void col2im_k3s2_kernel(const bf16* __restrict__ dP, int H, int W, int C, int pb, D* __restrict__ dx, int lddx, long long npix) {
+    const int Ho = H / 2, Wo = W / 2;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix; p += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(p % W); const long long t = p / W; const int iy = (int)(t % H); const long long n = t / H;
+        float acc[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] = 0.f;
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ty = iy + pb - ky;
+            if (ty < 0 || (ty & 1) || (ty >> 1) >= Ho) continue;
+            for (int kx = 0; kx < 3; ++kx) {
+                const int tx = ix + pb - kx;
+                if (tx < 0 || (tx & 1) || (tx >> 1) >= Wo) continue;
+                const bf16* row = dP + ((n * Ho + (ty >> 1)) * Wo + (tx >> 1)) * 64 + (ky * 3 + kx) * C;
+                for (int c = 0; c < C; ++c) acc[c] += __bfloat162float(row[c]);
+            }
+        }
+        for (int c = 0; c < C; ++c) stf(dx + p * lddx + c, acc[c]);
+    }
+}
+
 struct Slots { int s[5]; int n; };
 template <typename T>
 __global__ void assemble_bwd_kernel(const T* __restrict__ din, int ldin, Slots sl, float* __restrict__ dgen, long long npix) {
@@ -341,6 +398,33 @@ extern "C" int shm_pad_channels64(const void* src, int src_dtype, int lds, int C
     else if (src_dtype == SHM_BF16) pad64_kernel<bf16><<<flat_grid(npix * 8), 256, 0, st>>>((const bf16*)src, lds, C, (uint4*)dst_bf16, npix);
     else SHM_FAIL(SHM_EINVAL, "shm_pad_channels64: bad dtype %d", src_dtype);
     SHM_CHECK_LAUNCH("pad64_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_im2col_k3s2(const void* x, int src_dtype, int ldx, int N, int H, int W, int C, void* out_bf16, void* stream) {
+    SHM_REQUIRE(x && out_bf16 && N > 0 && H > 0 && W > 0 && C >= 1 && 9 * C <= 64 && ldx >= C, "shm_im2col_k3s2: bad args (9*C <= 64)");
+    SHM_REQUIRE(H % 2 == 0 && W % 2 == 0, "shm_im2col_k3s2: H, W must be even");
+    SHM_REQUIRE((reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0, "shm_im2col_k3s2: out must be 16-byte aligned");
+    const long long nout = (long long)N * (H / 2) * (W / 2);
+    const int pb = same_pad_before(H, 3, 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (src_dtype == SHM_F32) im2col_k3s2_kernel<float><<<flat_grid(nout * 8), 256, 0, st>>>((const float*)x, ldx, H, W, C, pb, (uint4*)out_bf16, nout);
+    else if (src_dtype == SHM_BF16) im2col_k3s2_kernel<bf16><<<flat_grid(nout * 8), 256, 0, st>>>((const bf16*)x, ldx, H, W, C, pb, (uint4*)out_bf16, nout);
+    else SHM_FAIL(SHM_EINVAL, "shm_im2col_k3s2: bad dtype %d", src_dtype);
+    SHM_CHECK_LAUNCH("im2col_k3s2_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_col2im_k3s2(const void* dP_bf16, int N, int H, int W, int C, void* dx, int dst_dtype, int lddx, void* stream) {
+    SHM_REQUIRE(dP_bf16 && dx && N > 0 && H > 0 && W > 0 && C >= 1 && C <= 7 && lddx >= C, "shm_col2im_k3s2: bad args (C <= 7)");
+    SHM_REQUIRE(H % 2 == 0 && W % 2 == 0, "shm_col2im_k3s2: H, W must be even");
+    const long long npix = (long long)N * H * W;
+    const int pb = same_pad_before(H, 3, 2);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dst_dtype == SHM_F32) col2im_k3s2_kernel<float><<<flat_grid(npix), 256, 0, st>>>((const bf16*)dP_bf16, H, W, C, pb, (float*)dx, lddx, npix);
+    else if (dst_dtype == SHM_BF16) col2im_k3s2_kernel<bf16><<<flat_grid(npix), 256, 0, st>>>((const bf16*)dP_bf16, H, W, C, pb, (bf16*)dx, lddx, npix);
+    else SHM_FAIL(SHM_EINVAL, "shm_col2im_k3s2: bad dtype %d", dst_dtype);
+    SHM_CHECK_LAUNCH("col2im_k3s2_kernel");
     return SHM_OK;
 }
 

@@ -402,13 +402,21 @@ class Discriminator:
         self.head = s.bind(Conv("head", 3, 3, cin, 1, bias=False))
         self.dense_w = s.views["dense.w"]
         self.dense_dw = s.gviews["dense.w"]
+        # tensor-core mode: d1 (3 -> N, 3x3, stride 2) runs as im2col + a 1x1 convolution over the 27 patch values (zero-padded to
+        # 64): the Keras kernel (3,3,3,N) IS the [27][N] matrix of that 1x1 layer, so the twin shares the parameter / gradient views
+        self.d1_col = None
         if self.pad_in:
-            s.pad(self.blocks[0].conv)
+            self.d1_col = s.bind(Conv("d1", 1, 1, 27, N, stride=1, act=ACT_LRELU, bias=False))
+            s.pad(self.d1_col)
             if live_mask:
                 s.pad(self.attn[0])
 
     def in_channels(self, n, h, w) -> int:
-        return 64 if (self.pad_in and self.blocks[0].conv.can_pad(n, h, w)) else 3
+        """The discriminator takes the plain 3-channel image in every mode."""
+        return 3
+
+    def _d1_col_ok(self, n, h, w) -> bool:
+        return self.d1_col is not None and h % 2 == 0 and w % 2 == 0 and self.d1_col.can_pad(n, h // 2, w // 2)
 
     def attention(self, mask):
         """MaxPool16(mask) -> 2 x [Conv3x3 + LeakyReLU] @512 (ShmGANwithSSpecSeg.py:358, :404-412)."""
@@ -432,17 +440,14 @@ class Discriminator:
         """x [B,S,S,3] -> (rf [B,S/32,S/32,1], cls [B,5] fp32).  noise / keep: the GaussianNoise(0.1) / Dropout(0.2)
         draws of a training=True call (:352, :363); None = training=False."""
         v = self.store.version
-        if x.shape[-1] == 64 or self.in_channels(x.shape[0], x.shape[1], x.shape[2]) == 64:
-            # zero-padded 64-channel input; the noise is added into the first 3 channels (of a private copy unless the caller
-            # already handed over the padded buffer, which train_step does)
-            h = x if x.shape[-1] == 64 else ops.pad64(x)
-            if noise is not None:
-                ops.add_channels_(h, noise)
-        else:
-            h = x if noise is None else ops.add(x, noise)
-        tape = {"layers": []} if save else None
+        h = x if noise is None else ops.add(x, noise)
+        col = self._d1_col_ok(*x.shape[:3])
+        if col:
+            h = ops.im2col_k3s2(h)                      # [B,S/2,S/2,64]: the 27 patch values of d1, zero-padded
+        tape = {"layers": [], "col": col, "hw": (x.shape[1], x.shape[2])} if save else None
         for i, bl in enumerate(self.blocks):
-            z = bl.conv.fwd(h, None, self.tc, v)
+            conv = self.d1_col if (i == 0 and col) else bl.conv
+            z = conv.fwd(h, None, self.tc, v)
             sz = ops.inorm_stats(z)
             y, _ = ops.inorm_apply(z, sz, bl.gamma, bl.beta, add=attn if i == 3 else None)
             if save:
@@ -480,10 +485,13 @@ class Discriminator:
             if i == 3 and dattn is not None:
                 ops.group_sum(dh, attn_nb, dattn, accumulate=True)
             dpre = ops.inorm_bwd(z, sz, bl.gamma, dyA=dh, act=ACT_LRELU)
+            conv = self.d1_col if (i == 0 and tape["col"]) else bl.conv
             if wgrad:
-                bl.conv.wgrad(hin, dpre, self.tc)
+                conv.wgrad(hin, dpre, self.tc)
             if i > 0 or need_dx:
-                dh = bl.conv.dgrad(dpre, hin.shape, None, self.tc, v)
+                dh = conv.dgrad(dpre, hin.shape, None, self.tc, v)
+        if need_dx and tape["col"]:
+            dh = ops.col2im_k3s2(dh, 3, tape["hw"][0], tape["hw"][1], self.dtype)
         return dh if need_dx else None
 
 

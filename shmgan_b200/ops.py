@@ -497,6 +497,23 @@ def pad64(src, out=None):
     return out
 
 
+def im2col_k3s2(x):
+    """[N,H,W,C] (C <= 7, fp32 / bf16, any pixel stride) -> bf16 [N,H/2,W/2,64] patch tensor of a 3x3 stride-2 SAME conv."""
+    n, h, w, c = x.shape
+    out = new((n, h // 2, w // 2, 64), torch.bfloat16)
+    call("shm_im2col_k3s2", _p(x), dt(x), ld(x), n, h, w, c, _p(out), _stream())
+    return out
+
+
+def col2im_k3s2(dP, c, h, w, dtype=torch.bfloat16):
+    """Transpose of im2col_k3s2: bf16 [N,H/2,W/2,64] -> [N,H,W,c]."""
+    n = dP.shape[0]
+    assert dP.is_contiguous() and dP.shape[-1] == 64 and dP.dtype == torch.bfloat16
+    dx = new((n, h, w, c), dtype)
+    call("shm_col2im_k3s2", _p(dP), n, h, w, c, _p(dx), dt(dx), ld(dx), _stream())
+    return dx
+
+
 def add_channels_(a, b):
     """a[..., :C] += b  in place (C = b's channel count; a may be wider, e.g. the zero-padded discriminator input)."""
     c = b.shape[-1]

@@ -411,3 +411,27 @@ def test_pw1_kernels(C, act):
     dx = c.pw1_bwd(xd, dev(dy, torch.bfloat16), yd)
     assert rel_err(dx, gx) < 1e-2
     assert rel_err(c.dw - 0.5, gw) < 1e-3 and rel_err(c.db, gb) < 1e-3
+
+
+def test_im2col_col2im_k3s2():
+    """d1's patch tensor: channel (ky*3+kx)*C + c of output pixel (oy, ox) = x[2oy+ky, 2ox+kx, c] (TF SAME pad (0, 1) at even sizes),
+    and col2im as its exact transpose (<im2col(x), g> == <x, col2im(g)>)."""
+    from shmgan_b200 import ops
+    N, H, W, C = 2, 8, 12, 3
+    x = bf16_round(randn((N, H, W, C), 61))
+    xp = torch.zeros((N, H + 1, W + 1, C), dtype=F64)
+    xp[:, :H, :W] = x
+    want = torch.zeros((N, H // 2, W // 2, 64), dtype=F64)
+    for ky in range(3):
+        for kx in range(3):
+            want[..., (ky * 3 + kx) * C:(ky * 3 + kx + 1) * C] = xp[:, ky:ky + H:2, kx:kx + W:2]
+    got = ops.im2col_k3s2(dev(x))
+    assert got.dtype == torch.bfloat16 and torch.equal(got.double().cpu(), want)
+    xbuf = torch.zeros((N, H, W, 8), device="cuda", dtype=torch.bfloat16)       # bf16 source in a wider buffer
+    xbuf[..., :C] = dev(x, torch.bfloat16)
+    assert torch.equal(ops.im2col_k3s2(xbuf[..., :C]).double().cpu(), want)
+    g = bf16_round(randn((N, H // 2, W // 2, 64), 62))
+    dx = ops.col2im_k3s2(dev(g, torch.bfloat16), C, H, W, torch.float32)
+    lhs = float((want * g).sum())
+    rhs = float((x * dx.double().cpu()).sum())
+    assert abs(lhs - rhs) < 1e-3 * (abs(lhs) + 1.0)
