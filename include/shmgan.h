@@ -60,6 +60,8 @@ int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad);   /* 1 if th
 /* cin_real (0 = d->Cin): the Keras kernel holds only cin_real < d->Cin input channels; the rest of the bf16 copy is zero (the layer
  * then reads a zero-padded 64-channel input, see shm_pad_channels64) */
 int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc, int for_dgrad, void* stream);
+/* both layouts (fwd and dgrad) in one launch */
+int shm_conv2d_tc_prep_weights_both(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc_fwd, void* w_tc_dgrad, void* stream);
 /* forward-layout weights of a layer run in a zero-padded device geometry (d->Cin, d->Cout) >= the Keras kernel's (cin_real, cout_real):
  * device input channel k holds real channel (k / seg_pad) * seg_real + k %% seg_pad when k %% seg_pad < seg_real, zero otherwise
  * (one segment = zero-padded input; two = concat of two zero-padded halves, SpecSeg.py:65-83 at 16/32 channels) */

@@ -35,6 +35,7 @@ _SIG = {
     "shm_conv2d_wgrad": [_D, _P, _P, _P, _P, _P],
     "shm_conv2d_tc_supported": [_D, _I],
     "shm_conv2d_tc_prep_weights": [_D, _P, _I, _P, _I, _P],
+    "shm_conv2d_tc_prep_weights_both": [_D, _P, _I, _P, _P, _P],
     "shm_conv2d_tc_prep_weights_padded": [_D, _P, _I, _I, _I, _I, _P, _P],
     "shm_conv2d_tc_fwd": [_D, _P, _P, _P, _P, _P],
     "shm_conv2d_tc_dgrad": [_D, _P, _P, _P, _P],

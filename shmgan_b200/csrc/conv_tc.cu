@@ -1256,6 +1256,21 @@ __global__ void prep_w_kernel(const float* __restrict__ w, bf16* __restrict__ o,
     }
 }
 
+// both layouts of one layer in ONE launch (blockIdx.y = 0: forward [tap][Cout][Cin], 1: dgrad [tap][Cin][Cout]): the per-step weight
+// refresh of ~70 layers was 140 tiny launches
+struct PrepSet { bf16* o; int K, Nn, k_real, n_real, w_ks, w_ns; };
+__global__ void prep_w_both_kernel(const float* __restrict__ w, PrepSet a, PrepSet b, long long tap_elems, long long total) {
+    const PrepSet s = blockIdx.y == 0 ? a : b;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % s.K);
+        const long long t2 = i / s.K;
+        const int n = (int)(t2 % s.Nn);
+        const long long tap = t2 / s.Nn;
+        const float v = (k < s.k_real && n < s.n_real) ? __ldg(w + tap * tap_elems + (long long)k * s.w_ks + (long long)n * s.w_ns) : 0.f;
+        s.o[i] = __float2bfloat16_rn(v);
+    }
+}
+
 bool wgrad_halo_ok(const shm_conv_desc* d) {
     return !d->transposed && d->stride == 1 && d->kh == 3 && d->kw == 3 && d->H % 16 == 0 && d->W % 8 == 0 &&
            d->Cin % 64 == 0 && d->Cout % 64 == 0;
@@ -1336,6 +1351,29 @@ extern "C" int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w
     if (g > shm_num_sms() * 16) g = shm_num_sms() * 16;
     prep_w_kernel<<<(int)g, 256, 0, (cudaStream_t)stream>>>(w, (bf16*)w_tc, K, Nn, k_real, n_real, (long long)cin_real * d->Cout, w_ks, w_ns, K, K, total);
     SHM_CHECK_LAUNCH("prep_w_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_conv2d_tc_prep_weights_both(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc_fwd, void* w_tc_dgrad, void* stream) {
+    if (int rc = tc_check(d)) return rc;
+    SHM_REQUIRE(w && w_tc_fwd && w_tc_dgrad, "shm_conv2d_tc_prep_weights_both: NULL buffer");
+    if (cin_real <= 0) cin_real = d->Cin;
+    SHM_REQUIRE(cin_real <= d->Cin, "shm_conv2d_tc_prep_weights_both: cin_real > Cin");
+    SHM_REQUIRE(cin_real == d->Cin || !d->transposed, "shm_conv2d_tc_prep_weights_both: channel padding is for Conv2D only");
+    PrepSet a, b;
+    a.o = (bf16*)w_tc_fwd; b.o = (bf16*)w_tc_dgrad;
+    if (!d->transposed) {          // (kh,kw,Cin,Cout)
+        a.K = d->Cin; a.Nn = d->Cout; a.w_ks = d->Cout; a.w_ns = 1; a.k_real = cin_real; a.n_real = d->Cout;
+        b.K = d->Cout; b.Nn = d->Cin; b.w_ks = 1; b.w_ns = d->Cout; b.k_real = d->Cout; b.n_real = cin_real;
+    } else {                       // (kh,kw,Cout,Cin)
+        a.K = d->Cin; a.Nn = d->Cout; a.w_ks = 1; a.w_ns = d->Cin; a.k_real = a.K; a.n_real = a.Nn;
+        b.K = d->Cout; b.Nn = d->Cin; b.w_ks = d->Cin; b.w_ns = 1; b.k_real = b.K; b.n_real = b.Nn;
+    }
+    const long long total = (long long)d->kh * d->kw * d->Cin * d->Cout;
+    long long g = cdiv64(total, 256);
+    if (g > shm_num_sms() * 8) g = shm_num_sms() * 8;
+    prep_w_both_kernel<<<dim3((unsigned)g, 2), 256, 0, (cudaStream_t)stream>>>(w, a, b, (long long)cin_real * d->Cout, total);
+    SHM_CHECK_LAUNCH("prep_w_both_kernel");
     return SHM_OK;
 }
 

@@ -135,8 +135,7 @@ class Conv:
             n = self.kh * self.kw * cin * self.cout
             self.w_tc = new((n,), torch.bfloat16)
             self.w_tc_d = new((n,), torch.bfloat16)
-        call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), self.cin, _p(self.w_tc), 0, _stream())
-        call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), self.cin, _p(self.w_tc_d), 1, _stream())
+        call("shm_conv2d_tc_prep_weights_both", C.byref(d), _p(self.w), self.cin, _p(self.w_tc), _p(self.w_tc_d), _stream())
         self.tc_version = version
 
     def tc_ok(self, d: ConvDesc) -> bool:

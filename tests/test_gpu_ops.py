@@ -109,6 +109,10 @@ def test_inorm_bf16_fast_bwd_with_bias_grad(shape, act):
     scale = float(want.abs().sum(dim=(0, 1, 2)).max())
     assert float(((db - 0.5).double().cpu() - want.sum(dim=(0, 1, 2))).abs().max()) < 2e-3 * scale
     assert float((dxbuf[..., :C].float() + 1.0).abs().max()) == 0.0
+    # gradient arriving through the direct branch only (the per-pixel kernels; the call above used the 2x2-quad kernels)
+    dz_a, = torch.autograd.grad((O.instance_norm(z, gamma, beta) * dyA).sum(), z)
+    got_a = ops.inorm_bwd(zd, sums, dev(gamma), dev(dyA, BF), None, act=act)
+    assert rel_err(got_a, (dz_a * slope).detach()) < 1e-2
 
 
 def test_act_bwd_bf16_fast_with_bias_grad():
