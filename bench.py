@@ -242,21 +242,43 @@ def run_ours(a):
         net.overlap = True
         rows = [(fam, kind, name, fl, nb, e0.elapsed_time(e1)) for fam, kind, name, fl, nb, e0, e1 in ops.PROF]
         ops.PROF = None
-        tot_ms = sum(r[5] for r in rows) / 2
-        fam = {}
+        step_ms = ms / a.steps
+        fam, kern = {}, {}
         for f, kind, name, fl, nb, t in rows:
-            k = (f, kind)
-            c = fam.setdefault(k, [0, 0.0, 0.0, 0])
+            kname = f[3:] if f.startswith("tc:") else None
+            f0 = "tc" if kname else f
+            c = fam.setdefault((f0, kind), [0, 0.0, 0.0, 0])
             c[0] += fl; c[1] += t; c[2] += nb; c[3] += 1
+            if kname:
+                c = kern.setdefault(kname, [0, 0.0, 0.0, 0])
+                c[0] += fl; c[1] += t; c[2] += nb; c[3] += 1
         tc_fl = sum(v[0] for k, v in fam.items() if k[0] == "tc") / 2
         tc_ms = sum(v[1] for k, v in fam.items() if k[0] == "tc") / 2
-        tc_n = sum(v[3] for k, v in fam.items() if k[0] == "tc") // 2
-        if tc_ms > 0:
-            ach = tc_fl / (tc_ms * 1e-3) / 1e12
-            line["roofline"] = {"bound": "tensor", "kernel": "conv_tc_kernel / wgrad_tc_kernel (tcgen05 implicit-GEMM conv fwd+dgrad+wgrad)",
-                                "achieved": ach, "peak": tf_sus, "unit": "TFLOP/s", "frac": ach / tf_sus, "traffic": None,
-                                "launches_per_step": tc_n, "ms_per_step_in_kernel": tc_ms, "share_of_step": tc_ms / (ms / a.steps),
+        # measured DRAM traffic of single launches (ncu --set full, profiles/r01_ncu_kernels.json), reported beside the live numbers
+        try:
+            with open(os.path.join(ROOT, "profiles", "r01_ncu_kernels.json")) as fh:
+                ncu = json.load(fh)
+        except Exception:
+            ncu = {}
+        ktab = {}
+        for k, v in sorted(kern.items(), key=lambda kv: -kv[1][1]):
+            ktab[k] = {"launches_per_step": v[3] // 2, "ms_per_step": v[1] / 2, "share_of_step": v[1] / 2 / step_ms,
+                       "tflops": v[0] / (v[1] * 1e-3) / 1e12, "frac_of_sustained_peak": v[0] / (v[1] * 1e-3) / 1e12 / tf_sus,
+                       "avg_launch_ms": v[1] / v[3], "ncu": ncu.get(k)}
+        if ktab:
+            top = next(iter(ktab))
+            t = ktab[top]
+            line["roofline"] = {"bound": "tensor", "kernel": top + " (dominant tcgen05 kernel: all its launches in the live step, CUDA events)",
+                                "achieved": t["tflops"], "peak": tf_sus, "unit": "TFLOP/s", "frac": t["frac_of_sustained_peak"],
+                                "traffic": (ncu.get(top) or {}).get("dram_bytes_per_launch"),
+                                "traffic_note": (ncu.get(top) or {}).get("note"),
+                                "launches_per_step": t["launches_per_step"], "avg_launch_ms": t["avg_launch_ms"],
+                                "ms_per_step_in_kernel": t["ms_per_step"], "share_of_step": t["share_of_step"],
                                 "peak_kind": "bf16_tflops_sustained (%s)" % peak_src}
+            line["tc_kernels"] = ktab
+            line["tc_family"] = {"achieved": tc_fl / (tc_ms * 1e-3) / 1e12, "unit": "TFLOP/s", "frac": tc_fl / (tc_ms * 1e-3) / 1e12 / tf_sus,
+                                 "ms_per_step": tc_ms, "share_of_step": tc_ms / step_ms,
+                                 "note": "all tcgen05 conv launches (fwd + dgrad + wgrad), algorithmic FLOPs of the unpadded layers"}
         line["kernel_families"] = {"%s_%s" % k: {"ms_per_step": v[1] / 2, "tflops": (v[0] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None,
                                                   "gbs_algorithmic": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else None,
                                                   "launches": v[3] // 2} for k, v in sorted(fam.items())}

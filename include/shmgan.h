@@ -60,6 +60,9 @@ int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad);   /* 1 if th
 /* cin_real (0 = d->Cin): the Keras kernel holds only cin_real < d->Cin input channels; the rest of the bf16 copy is zero (the layer
  * then reads a zero-padded 64-channel input, see shm_pad_channels64) */
 int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc, int for_dgrad, void* stream);
+/* which tcgen05 kernel serves the layer (accounting only): pass 0 fwd, 1 dgrad, 2 wgrad -> 0 conv_tc, 1 conv_halo, 2 conv_multi (big),
+ * 3 conv_multi (stride-2 scatter), 4 wgrad_tc, 5 wgrad_halo<0>, 6 wgrad_halo<1>; -1 = not servable */
+int shm_conv2d_tc_route(const shm_conv_desc* d, int pass);
 /* both layouts (fwd and dgrad) in one launch */
 int shm_conv2d_tc_prep_weights_both(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc_fwd, void* w_tc_dgrad, void* stream);
 /* forward-layout weights of a layer run in a zero-padded device geometry (d->Cin, d->Cout) >= the Keras kernel's (cin_real, cout_real):

@@ -1409,6 +1409,33 @@ extern "C" int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad) {
     return pick_box(d->N, Qh, Qw, BW, BH, BI) ? 1 : 0;
 }
 
+// which kernel serves a layer (for per-kernel accounting in bench.py): pass 0 = fwd, 1 = dgrad, 2 = wgrad.
+// 0 conv_tc (generic)  1 conv_halo  2 conv_multi/big  3 conv_multi/scatter  4 wgrad_tc (generic)  5 wgrad_halo<0>  6 wgrad_halo<1>
+extern "C" int shm_conv2d_tc_route(const shm_conv_desc* d, int pass) {
+    if (tc_check(d) != SHM_OK) return -1;
+    int Ho, Wo; out_dims(d, Ho, Wo);
+    const int s = d->stride;
+    if (pass == 2) {
+        if (!wgrad_halo_ok(d)) return 4;
+        return (d->Cin % 128 == 0 && d->Cout % 128 == 0) ? 6 : 5;
+    }
+    if (pass == 0) {
+        if (!d->transposed) {
+            if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s)) return 1;
+            if (big_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s)) return 2;
+            return 0;
+        }
+        return (s == 2 && scatter_ok(d->H, d->W, d->Cin, d->Cout)) ? 3 : 0;
+    }
+    if (d->transposed) return 0;
+    if (s == 1) {
+        if (halo_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s)) return 1;
+        if (big_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s)) return 2;
+        return 0;
+    }
+    return (s == 2 && d->H % 2 == 0 && d->W % 2 == 0 && scatter_ok(Ho, Wo, d->Cout, d->Cin)) ? 3 : 0;
+}
+
 // forward: Conv2D (gather form) or Conv2DTranspose (scatter-by-parity form, 4 launches)
 extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, void* stream) {
     if (int rc = tc_check(d)) return rc;

@@ -19,6 +19,18 @@ BN_EPS = 1e-3       # Keras BatchNormalization default (SpecSeg.py:37)
 PROF = None
 
 
+TC_KERNELS = ("conv_tc_kernel", "conv_halo_kernel", "conv_multi_kernel (big)", "conv_multi_kernel (scatter)", "wgrad_tc_kernel",
+              "wgrad_halo_kernel<0>", "wgrad_halo_kernel<1>")
+
+
+def _route(d, pas):
+    """Name of the tcgen05 kernel that serves (desc, pass); only evaluated while profiling."""
+    if PROF is None:
+        return "tc"
+    r = call("shm_conv2d_tc_route", C.byref(d), pas)
+    return "tc:" + (TC_KERNELS[r] if 0 <= r < len(TC_KERNELS) else "?")
+
+
 def _prof(family, kind, name, flops, nbytes, fn):
     if PROF is None:
         return fn()
@@ -161,7 +173,7 @@ class Conv:
                                                               n * h * w, dt(x), _stream()))
         elif tc and self.tc_ok(d):
             self.refresh_tc(version)
-            _prof("tc", "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b), _p(y), _stream()))
+            _prof(_route(d, 0), "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b), _p(y), _stream()))
         else:
             _prof("simt", "fwd", self.name, fl, nb, lambda: call("shm_conv2d_fwd", C.byref(d), _p(x), _p(self.w), _p(self.b), _p(y), _stream()))
         return y
@@ -192,7 +204,7 @@ class Conv:
             _prof("bw", "dgrad", self.name, fl, nb, lambda: call("shm_c3to1_dgrad", _p(dy), n, h, w, self.cin, _p(self.w), _p(dx), ld(dx), dt(dy), _stream()))
         elif tc and self.tc_ok(d):
             self.refresh_tc(version)
-            _prof("tc", "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_dgrad", C.byref(d), _p(dy), _p(self.w_tc_d), _p(dx), _stream()))
+            _prof(_route(d, 1), "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_dgrad", C.byref(d), _p(dy), _p(self.w_tc_d), _p(dx), _stream()))
         else:
             _prof("simt", "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_dgrad", C.byref(d), _p(dy), _p(self.w), _p(dx), 0, _stream()))
         return dx
@@ -214,7 +226,7 @@ class Conv:
         if tc and self.c3to1_ok(x) and not self.has_bias:
             _prof("bw", "wgrad", self.name, fl, nb, lambda: call("shm_c3to1_wgrad", _p(x), n, h, w, self.cin, ld(x), _p(dy), _p(dw), dt(x), _stream()))
         elif tc and self.tc_ok(d):
-            _prof("tc", "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(dw), _stream()))
+            _prof(_route(d, 2), "wgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_wgrad", C.byref(d), _p(x), _p(dy), _p(dw), _stream()))
             if self.has_bias and not bias_done:
                 call("shm_colsum", _p(dy), dy.shape[0] * dy.shape[1] * dy.shape[2], self.cout, ld(dy), dt(dy), _p(self.db), _stream())
         else:
@@ -285,7 +297,7 @@ class PaddedConv(Conv):
         self.refresh_tc(version)
         d = self.dev_desc(n, h, w, ld(x), ld(y))
         fl, nb = self.flops(n, h, w), x.element_size() * n * (h * w * self.cin_dev + ho * wo * self.cout_dev)
-        _prof("tc", "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b_dev), _p(y), _stream()))
+        _prof(_route(d, 0), "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b_dev), _p(y), _stream()))
         return y
 
 
