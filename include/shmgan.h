@@ -61,7 +61,7 @@ int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad);   /* 1 if th
  * then reads a zero-padded 64-channel input, see shm_pad_channels64) */
 int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc, int for_dgrad, void* stream);
 /* which tcgen05 kernel serves the layer (accounting only): pass 0 fwd, 1 dgrad, 2 wgrad -> 0 conv_tc, 1 conv_halo, 2 conv_multi (big),
- * 3 conv_multi (stride-2 scatter), 4 wgrad_tc, 5 wgrad_halo<0>, 6 wgrad_halo<1>; -1 = not servable */
+ * 3 conv_multi (stride-2 scatter), 4 wgrad_tc, 5 wgrad_halo<0>, 6 wgrad_halo<1>, 7 wgrad_s2<0>, 8 wgrad_s2<1>; -1 = not servable */
 int shm_conv2d_tc_route(const shm_conv_desc* d, int pass);
 /* both layouts (fwd and dgrad) in one launch */
 int shm_conv2d_tc_prep_weights_both(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc_fwd, void* w_tc_dgrad, void* stream);

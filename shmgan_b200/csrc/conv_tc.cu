@@ -1228,6 +1228,180 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// ------------------------------------------------------------------------------------------------
+// stride-2 halo wgrad kernel: weight gradients of Conv2DTranspose(3, s=2) and of stride-2 Conv2D(3) layers.
+//
+//   dW[ky][kx][cg][cs] += sum_o G[2*o + (ky, kx), cg] * S[o, cs]
+//
+// G = the big image (dy of a transposed conv / x of a strided conv), S = the small one (x / dy), o runs over S's lattice.
+// The generic wgrad kernel re-gathers G at stride 2 once per tap (350-450 TFLOP/s).  Here the four PARITY PLANES of G's halo are
+// loaded once per 16 x 8 tile of o by TMA boxes with traversal stride 2 (dense 18 x 10 smem tiles), and tap (ky, kx) is a shifted
+// MN-major descriptor into plane (ky & 1, kx & 1) at offset (ky >> 1, kx >> 1), exactly as in wgrad_halo_kernel:
+//   MODE 0: unit = (64 cg, 64 cs); M = 128 = two taps of one plane (LBO = tap distance), five accumulators x 64 columns
+//   MODE 1: unit = (128 cg, 128 cs, filter row); M = 128 = two 64-channel tiles of a plane, three accumulators x 128 columns
+// ------------------------------------------------------------------------------------------------
+struct Ws2Params {
+    int units, splits, cblocks, nblocks;
+    int tiles_x, tiles_y, total_tiles, tiles_per_split;
+    int CG, CS;
+    float* dW;
+};
+
+template <int MODE>
+struct Ws2Cfg {
+    static constexpr int A_ONE = MODE == 0 ? HALO_STAGE : 16 * HALO_W * 128;             // one plane tile: 18 x 10 or 16 x 10 rows
+    static constexpr int A_TX = 4 * (MODE == 0 ? HALO_BYTES : 16 * HALO_W * 128);        // bytes written by TMA
+    static constexpr int A_ST = 4 * A_ONE;
+    static constexpr int B_ST = (MODE == 0 ? 1 : 2) * 16384;
+    static constexpr int STAGE_BYTES = A_ST + B_ST;
+    static constexpr int STAGES = 2;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+    static constexpr int BN = MODE == 0 ? 64 : 128;
+    static constexpr int NACC = MODE == 0 ? 5 : 3;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_s2_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmS, const Ws2Params p) {
+    using Cfg = Ws2Cfg<MODE>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + Cfg::STAGES * Cfg::A_ST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + Cfg::STAGES;
+    uint64_t* tfull = bars + 2 * Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int unit = blockIdx.x % p.units, split = blockIdx.x / p.units;
+    const int nb = unit % p.nblocks;
+    const int cb = (unit / p.nblocks) % p.cblocks;
+    const int frow = unit / (p.nblocks * p.cblocks);            // MODE 1: filter row ky
+    const int t0 = split * p.tiles_per_split;
+    int t1 = t0 + p.tiles_per_split; if (t1 > p.total_tiles) t1 = p.total_tiles;
+    const int per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmG); prefetch_tmap(&tmS);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int t = t0; t < t1; ++t) {
+            const int img = t / per_img; const int r = t - img * per_img;
+            const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one_sync()) {
+                mbar_expect_tx(&full[stage], Cfg::A_TX + Cfg::B_ST);
+                uint8_t* a = sA + stage * Cfg::A_ST;
+                uint8_t* b = sB + stage * Cfg::B_ST;
+                if (MODE == 0) {
+                    // planes (py, px) = (0,0) (0,1) (1,0) (1,1)
+#pragma unroll
+                    for (int pl = 0; pl < 4; ++pl)
+                        tma_load_4d(a + pl * Cfg::A_ONE, &tmG, &full[stage], cb * 64, 2 * x0 + (pl & 1), 2 * y0 + (pl >> 1), img);
+                    tma_load_4d(b, &tmS, &full[stage], nb * 64, x0, y0, img);
+                } else {
+                    // planes (frow & 1, px) for px = 0, 1, rows starting at (frow >> 1); two 64-channel tiles each
+                    const int gy = 2 * (y0 + (frow >> 1)) + (frow & 1);
+#pragma unroll
+                    for (int px = 0; px < 2; ++px)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            tma_load_4d(a + (px * 2 + h) * Cfg::A_ONE, &tmG, &full[stage], cb * 128 + h * 64, 2 * x0 + px, gy, img);
+                    tma_load_4d(b, &tmS, &full[stage], nb * 128, x0, y0, img);
+                    tma_load_4d(b + 16384, &tmS, &full[stage], nb * 128 + 64, x0, y0, img);
+                }
+            }
+            __syncwarp();
+            if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1) {
+        if (t1 > t0) {
+            constexpr uint32_t idesc = make_idesc(128, Cfg::BN, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t a0 = smem_u32(sA + stage * Cfg::A_ST);
+                    const uint32_t b0 = smem_u32(sB + stage * Cfg::B_ST);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {          // 16 lattice points = tile rows 2j, 2j+1 per MMA
+                        const uint64_t bdesc = make_desc_sw128(b0 + j * 2048, 16384, 1024);
+                        const uint32_t acc = (t > t0 || j > 0) ? 1u : 0u;
+                        const uint32_t rowoff = (uint32_t)(2 * j * HALO_W) * 128u;
+                        if (MODE == 0) {
+                            // (plane, first offset, LBO in rows): taps {0,2} {6,8} {1,7} {3,5} {4,-}
+                            constexpr int PL[5] = {0, 0, 1, 2, 3};
+                            constexpr int OFF[5] = {0, HALO_W, 0, 0, 0};
+                            constexpr int LBO[5] = {1, 1, HALO_W, 1, 0};
+#pragma unroll
+                            for (int pr = 0; pr < 5; ++pr) {
+                                const uint64_t adesc = make_desc_sw128(a0 + PL[pr] * Cfg::A_ONE + rowoff + OFF[pr] * 128u, LBO[pr] * 128u, HALO_W * 128);
+                                umma_bf16(tmem_base + pr * 64, adesc, bdesc, idesc, acc);
+                            }
+                        } else {
+#pragma unroll
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const uint32_t base = a0 + ((kx & 1) * 2) * Cfg::A_ONE + rowoff + (kx >> 1) * 128u;
+                                const uint64_t adesc = make_desc_sw128(base, Cfg::A_ONE, HALO_W * 128);
+                                umma_bf16(tmem_base + kx * 128, adesc, bdesc, idesc, acc);
+                            }
+                        }
+                    }
+                    umma_commit(&empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one_sync()) umma_commit(tfull);
+            __syncwarp();
+        }
+    } else if (t1 > t0) {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int a = 0; a < Cfg::NACC; ++a) {
+            int tap, cg;
+            bool ok = true;
+            if (MODE == 0) {
+                const int TA[5] = {0, 6, 1, 3, 4}, TB[5] = {2, 8, 7, 5, -1};
+                tap = (row >> 6) ? TB[a] : TA[a];
+                ok = tap >= 0;
+                cg = cb * 64 + (row & 63);
+            } else { tap = frow * 3 + a; cg = cb * 128 + row; }
+            float* dst = p.dW + ((long long)(ok ? tap : 0) * p.CG + cg) * p.CS + nb * Cfg::BN;
+#pragma unroll 1
+            for (int c = 0; c < Cfg::BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * Cfg::BN + c * 32), r);
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        red_add_v4(dst + c * 32 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                }
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
 bool pick_box64(int N, int Qh, int Qw, int& BW, int& BH, int& BI) {
     BW = Qw >= 64 ? 64 : Qw;
     if (BW <= 0 || 64 % BW != 0 || Qw % BW != 0) return false;
@@ -1311,6 +1485,57 @@ int launch_wgrad_halo(const shm_conv_desc* d, const void* x, const void* dy, flo
     if (int rc = encode_act_box(&tmX, x, d->Cin, d->W, d->H, d->N, d->ldx, HALO_W, mode ? 16 : 18)) return rc;
     if (int rc = encode_act_box(&tmDY, dy, d->Cout, d->W, d->H, d->N, d->ldy, 8, 16)) return rc;
     return mode ? launch_wgrad_halo_t<1>(tmX, tmDY, p, st) : launch_wgrad_halo_t<0>(tmX, tmDY, p, st);
+}
+
+// stride-2 3x3 weight gradients: Conv2DTranspose (G = dy, S = x) and strided Conv2D (G = x, S = dy) at even sizes
+bool wgrad_s2_ok(const shm_conv_desc* d) {
+    if (d->kh != 3 || d->kw != 3 || d->stride != 2 || d->Cin % 64 != 0 || d->Cout % 64 != 0) return false;
+    int Ho, Wo; out_dims(d, Ho, Wo);
+    const int Hs = d->transposed ? d->H : Ho, Ws = d->transposed ? d->W : Wo;       // the small image's lattice
+    const int Hg = d->transposed ? Ho : d->H, Wg = d->transposed ? Wo : d->W;
+    return Hg == 2 * Hs && Wg == 2 * Ws && Hs % 16 == 0 && Ws % 8 == 0;
+}
+
+template <int MODE>
+int launch_wgrad_s2_t(const CUtensorMap& tmG, const CUtensorMap& tmS, const Ws2Params& p, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(wgrad_s2_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Ws2Cfg<MODE>::SMEM); attr = true; }
+    wgrad_s2_kernel<MODE><<<p.units * p.splits, TC_THREADS, Ws2Cfg<MODE>::SMEM, st>>>(tmG, tmS, p);
+    SHM_CHECK_LAUNCH("wgrad_s2_kernel");
+    return SHM_OK;
+}
+
+int launch_wgrad_s2(const shm_conv_desc* d, const void* x, const void* dy, float* dw, cudaStream_t st) {
+    int Ho, Wo; out_dims(d, Ho, Wo);
+    const void* G = d->transposed ? dy : x;  const void* S = d->transposed ? x : dy;
+    const int CG = d->transposed ? d->Cout : d->Cin, CS = d->transposed ? d->Cin : d->Cout;
+    const int ldG = d->transposed ? d->ldy : d->ldx, ldS = d->transposed ? d->ldx : d->ldy;
+    const int Hs = d->transposed ? d->H : Ho, Ws = d->transposed ? d->W : Wo;
+    Ws2Params p{};
+    const int mode = (CG % 128 == 0 && CS % 128 == 0) ? 1 : 0;
+    p.cblocks = CG / (mode ? 128 : 64);
+    p.nblocks = CS / (mode ? 128 : 64);
+    p.units = p.cblocks * p.nblocks * (mode ? 3 : 1);
+    p.tiles_x = Ws / 8; p.tiles_y = Hs / 16;
+    p.total_tiles = d->N * p.tiles_x * p.tiles_y;
+    p.CG = CG; p.CS = CS; p.dW = dw;
+    const int sms = shm_num_sms();
+    long long best_cost = -1; int best_s = 1;
+    const int smax = p.total_tiles < 4 * sms ? p.total_tiles : 4 * sms;
+    for (int s = 1; s <= smax; ++s) {
+        const long long ctas = (long long)p.units * s;
+        if (ctas > 4LL * sms && s > 1) break;
+        const long long waves = (ctas + sms - 1) / sms;
+        const long long cost = waves * (cdiv(p.total_tiles, s) + 6);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s; }
+    }
+    p.tiles_per_split = cdiv(p.total_tiles, best_s);
+    p.splits = cdiv(p.total_tiles, p.tiles_per_split);
+    CUtensorMap tmG, tmS;
+    // parity-plane boxes: 10 x 18 (MODE 0) or 10 x 16 (MODE 1) plane pixels at traversal stride 2
+    if (int rc = encode_act(&tmG, G, CG, 2 * Ws, 2 * Hs, d->N, ldG, HALO_W, mode ? 16 : HALO_H, 1, 2)) return rc;
+    if (int rc = encode_act_box(&tmS, S, CS, Ws, Hs, d->N, ldS, 8, 16)) return rc;
+    return mode ? launch_wgrad_s2_t<1>(tmG, tmS, p, st) : launch_wgrad_s2_t<0>(tmG, tmS, p, st);
 }
 
 int tc_check(const shm_conv_desc* d) {
@@ -1416,8 +1641,9 @@ extern "C" int shm_conv2d_tc_route(const shm_conv_desc* d, int pass) {
     int Ho, Wo; out_dims(d, Ho, Wo);
     const int s = d->stride;
     if (pass == 2) {
-        if (!wgrad_halo_ok(d)) return 4;
-        return (d->Cin % 128 == 0 && d->Cout % 128 == 0) ? 6 : 5;
+        if (wgrad_halo_ok(d)) return (d->Cin % 128 == 0 && d->Cout % 128 == 0) ? 6 : 5;
+        if (wgrad_s2_ok(d)) return (d->Cin % 128 == 0 && d->Cout % 128 == 0) ? 8 : 7;
+        return 4;
     }
     if (pass == 0) {
         if (!d->transposed) {
@@ -1583,6 +1809,7 @@ extern "C" int shm_conv2d_tc_wgrad(const shm_conv_desc* d, const void* x, const 
             }
     }
     if (wgrad_halo_ok(d)) return launch_wgrad_halo(d, x, dy, dw, st);
+    if (wgrad_s2_ok(d)) return launch_wgrad_s2(d, x, dy, dw, st);
     if (!pick_box64(d->N, p.Qh, p.Qw, p.BW, p.BH, p.BI)) SHM_FAIL(SHM_EUNSUPPORTED, "wgrad_tc: lattice %dx%d does not tile into 64-point boxes", p.Qh, p.Qw);
     p.tiles_x = p.Qw / p.BW; p.tiles_y = p.Qh / p.BH;
     p.cblocks = Ca / 64;

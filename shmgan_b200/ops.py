@@ -20,7 +20,7 @@ PROF = None
 
 
 TC_KERNELS = ("conv_tc_kernel", "conv_halo_kernel", "conv_multi_kernel (big)", "conv_multi_kernel (scatter)", "wgrad_tc_kernel",
-              "wgrad_halo_kernel<0>", "wgrad_halo_kernel<1>")
+              "wgrad_halo_kernel<0>", "wgrad_halo_kernel<1>", "wgrad_s2_kernel<0>", "wgrad_s2_kernel<1>")
 
 
 def _route(d, pas):
