@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const float* __restrict__
         const float* __restrict__ imgB, const float* __restrict__ mmB, int H, int W, float c1, float c2, Gauss gs,
         float* __restrict__ ssim_out, float* __restrict__ maps) {
     __shared__ float su[SS_IN][SS_IN + 1], sv[SS_IN][SS_IN + 1];
+    __shared__ float hs[5][SS_IN][SS_T + 1];
     __shared__ double sm[32];
     const int n = blockIdx.z / 3, c = blockIdx.z % 3;
     const int HW = H * W, Ho = H - SS_K + 1, Wo = W - SS_K + 1;
@@ -221,21 +222,30 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const float* __restrict__
         su[ly][lx] = u; sv[ly][lx] = v;
     }
     __syncthreads();
+    // separable 11x11 Gaussian: horizontal pass over the 26 tile rows into shared memory, then the vertical pass per output
+    // (144 FMAs per output instead of 605; the non-separable form was shared-memory-load bound at 0.2 ms per call)
+    for (int i = threadIdx.x; i < SS_IN * SS_T; i += 256) {
+        const int r = i / SS_T, cx = i - r * SS_T;
+        float r1 = 0.f, r2 = 0.f, r11 = 0.f, r22 = 0.f, r12 = 0.f;
+#pragma unroll
+        for (int j = 0; j < SS_K; ++j) {
+            const float u = su[r][cx + j], v = sv[r][cx + j], g = gs.g[j];
+            r1 = fmaf(g, u, r1); r2 = fmaf(g, v, r2);
+            r11 = fmaf(g, u * u, r11); r22 = fmaf(g, v * v, r22); r12 = fmaf(g, u * v, r12);
+        }
+        hs[0][r][cx] = r1; hs[1][r][cx] = r2; hs[2][r][cx] = r11; hs[3][r][cx] = r22; hs[4][r][cx] = r12;
+    }
+    __syncthreads();
     const int tx = threadIdx.x % SS_T, ty = threadIdx.x / SS_T;
     const int ox = x0 + tx, oy = y0 + ty;
     float S = 0.f;
     if (ox < Wo && oy < Ho) {
         float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
-        for (int i = 0; i < SS_K; ++i) {
-            float r1 = 0.f, r2 = 0.f, r11 = 0.f, r22 = 0.f, r12 = 0.f;
 #pragma unroll
-            for (int j = 0; j < SS_K; ++j) {
-                const float u = su[ty + i][tx + j], v = sv[ty + i][tx + j], g = gs.g[j];
-                r1 = fmaf(g, u, r1); r2 = fmaf(g, v, r2);
-                r11 = fmaf(g, u * u, r11); r22 = fmaf(g, v * v, r22); r12 = fmaf(g, u * v, r12);
-            }
+        for (int i = 0; i < SS_K; ++i) {
             const float g = gs.g[i];
-            m1 = fmaf(g, r1, m1); m2 = fmaf(g, r2, m2); s11 = fmaf(g, r11, s11); s22 = fmaf(g, r22, s22); s12 = fmaf(g, r12, s12);
+            m1 = fmaf(g, hs[0][ty + i][tx], m1); m2 = fmaf(g, hs[1][ty + i][tx], m2);
+            s11 = fmaf(g, hs[2][ty + i][tx], s11); s22 = fmaf(g, hs[3][ty + i][tx], s22); s12 = fmaf(g, hs[4][ty + i][tx], s12);
         }
         const float num0 = 2.f * m1 * m2, den0 = m1 * m1 + m2 * m2;
         const float L = (num0 + c1) / (den0 + c1);
@@ -272,6 +282,7 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(const float* __restrict__
         const float* __restrict__ imgB, const float* __restrict__ mmB, int H, int W, Gauss gs, const float* __restrict__ maps,
         const float* __restrict__ dssim, float* __restrict__ dY, double* __restrict__ scratch) {
     __shared__ float sP[SS_IN][SS_IN + 1], sQ[SS_IN][SS_IN + 1], sR[SS_IN][SS_IN + 1];
+    __shared__ float hs[3][SS_IN][SS_T + 1];
     __shared__ double sm[32];
     const int n = blockIdx.z / 3, c = blockIdx.z % 3;
     const int HW = H * W, Ho = H - SS_K + 1, Wo = W - SS_K + 1;
@@ -290,23 +301,27 @@ __global__ void __launch_bounds__(256) ssim_bwd_kernel(const float* __restrict__
         sP[ly][lx] = P; sQ[ly][lx] = Q; sR[ly][lx] = R;
     }
     __syncthreads();
+    // separable correlation with the (symmetric) Gaussian: sum_k g(k) X(p - k) == sum_i g(i) X[tile row ty + i] by symmetry
+    for (int i = threadIdx.x; i < SS_IN * SS_T; i += 256) {
+        const int r = i / SS_T, cx = i - r * SS_T;
+        float rP = 0.f, rQ = 0.f, rR = 0.f;
+#pragma unroll
+        for (int j = 0; j < SS_K; ++j) {
+            const float g = gs.g[j];
+            rP = fmaf(g, sP[r][cx + j], rP); rQ = fmaf(g, sQ[r][cx + j], rQ); rR = fmaf(g, sR[r][cx + j], rR);
+        }
+        hs[0][r][cx] = rP; hs[1][r][cx] = rQ; hs[2][r][cx] = rR;
+    }
+    __syncthreads();
     const int tx = threadIdx.x % SS_T, ty = threadIdx.x / SS_T;
     const int px = x0 + tx, py = y0 + ty;
     float t1 = 0.f, t2 = 0.f;
     if (px < W && py < H) {
         float aP = 0.f, aQ = 0.f, aR = 0.f;
-        // p - w = k  (k = 0..10)  ->  tile index of w = (ty + 10 - ky, tx + 10 - kx)
-        for (int ky = 0; ky < SS_K; ++ky) {
-            float rP = 0.f, rQ = 0.f, rR = 0.f;
 #pragma unroll
-            for (int kx = 0; kx < SS_K; ++kx) {
-                const float g = gs.g[kx];
-                rP = fmaf(g, sP[ty + SS_K - 1 - ky][tx + SS_K - 1 - kx], rP);
-                rQ = fmaf(g, sQ[ty + SS_K - 1 - ky][tx + SS_K - 1 - kx], rQ);
-                rR = fmaf(g, sR[ty + SS_K - 1 - ky][tx + SS_K - 1 - kx], rR);
-            }
-            const float g = gs.g[ky];
-            aP = fmaf(g, rP, aP); aQ = fmaf(g, rQ, aQ); aR = fmaf(g, rR, aR);
+        for (int i = 0; i < SS_K; ++i) {
+            const float g = gs.g[i];
+            aP = fmaf(g, hs[0][ty + i][tx], aP); aQ = fmaf(g, hs[1][ty + i][tx], aQ); aR = fmaf(g, hs[2][ty + i][tx], aR);
         }
         const long long p = (long long)n * HW + (long long)py * W + px;
         const float a = c == 0 ? Y[p] : cbcr[p * 2 + (c - 1)];

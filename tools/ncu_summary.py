@@ -22,7 +22,7 @@ def main():
     out, reps = sys.argv[1], sys.argv[2:]
     res, lines = {}, []
     for item in reps:
-        label, path = item.split("=", 1)
+        label, path = item.rsplit("=", 1)
         txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(txt)))
         hdr, units = rows[0], rows[1]
