@@ -46,6 +46,7 @@ _SIG = {
     "shm_inorm_apply": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _F, _P, _I, _I, _P, _I, _P, _I, _P],
     "shm_inorm_bwd_stats": [_P, _I, _I, _I, _I, _I, _I, _P, _F, _P, _I, _P, _I, _P, _P],
     "shm_inorm_bwd_apply": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _F, _P, _I, _P, _I, _P, _I, _P, _I, _P, _P],
+    "shm_norm_tune": [_I, _I, _I],
     "shm_act_bwd": [_P, _I, _P, _I, _P, _I, _L, _I, _I, _I, _P, _P],
     "shm_maxpool": [_P, _I, _I, _I, _I, _I, _I, _P, _I, _I, _P],
     "shm_bn_eval": [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _F, _P, _I, _P, _I, _P],

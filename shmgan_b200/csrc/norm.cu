@@ -275,6 +275,8 @@ __device__ __forceinline__ f8 load_dy8(const bf16* dyA, int ldA, const bf16* dyP
     return d;
 }
 
+#include "norm_pipe.cuh"
+
 // block reduction of NV partial columns per thread over the TY pixel lanes; calls sink(column c8*8 + j-th value index, total)
 template <int NV, typename Sink>
 __device__ __forceinline__ void reduce_lanes(const float* vals, int TX, float (*red)[NV + 1], Sink sink) {
@@ -743,11 +745,28 @@ inline int units_per_block(long long units, int TY, int other_blocks) {
 
 }  // namespace
 
+// tuning hook of tools/bench_norm.py: pipe_off = 1 selects the register-staged kernels; depth / grid_mul = 0 keep the defaults
+extern "C" int shm_norm_tune(int pipe_off, int depth, int grid_mul) {
+    SHM_REQUIRE(depth == 0 || depth == 1 || depth == 2 || depth == 4 || depth == 8, "shm_norm_tune: depth must be 0, 1, 2, 4 or 8");
+    g_pipe_off = pipe_off; g_pipe_depth = depth; g_grid_mul = grid_mul;
+    return SHM_OK;
+}
+
 #define REQ_VEC(p, ld, T, name) SHM_REQUIRE(vec_ok(p, ld, sizeof(T)), name ": pointer/ld not aligned to 4 elements")
 
 extern "C" int shm_inorm_stats(const void* x, int N, int HW, int C, int ldx, int dtype, double* sums, void* stream) {
     SHM_REQUIRE(x && sums && N > 0 && HW > 0 && C > 0 && ldx >= C, "shm_inorm_stats: bad args");
     SHM_REQUIRE(C % 4 == 0, "shm_inorm_stats: C=%d must be a multiple of 4", C);
+    if (pipe_ok(dtype, C, HW) && al16(x, ldx)) {
+        const int TX = C / 8, S__ = pipe_depth(4);
+        const long long NP = (long long)N * HW, PB = NP * C * 2;
+        cudaStream_t st = (cudaStream_t)stream;
+#define CALL(S_) PIPE_LAUNCH(in_stats_p<S_>, 1, NP, 256 / TX, PB, 512 << 10, (const bf16*)x, HW, C, ldx, NP, sums, TX)
+        PIPE_DEPTHS(S__, CALL)
+#undef CALL
+        SHM_CHECK_LAUNCH("in_stats_p");
+        return SHM_OK;
+    }
     if (fast8_ok(dtype, C) && al16(x, ldx)) {
         const int TX = C / 8, pp = ppb8(HW, 256 / TX, N);
         inorm_stats8_kernel<<<dim3(cdiv(HW, pp), 1, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, HW, C, ldx, sums, pp, TX);
@@ -775,6 +794,34 @@ extern "C" int shm_inorm_apply(const void* x, int N, int H, int W, int C, int ld
     SHM_REQUIRE(!add || out, "shm_inorm_apply: add without out");
     if (nadd <= 0) nadd = N;
     SHM_REQUIRE(N % nadd == 0, "shm_inorm_apply: N %% nadd != 0");
+    if (pipe_ok(dtype, C, pooled ? (long long)(H / 2) * (W / 2) : (long long)H * W) && al16(x, ldx) && al16(add, ldadd) && al16(out, ldo) && al16(pooled, ldp)) {
+        const int TX = C / 8;
+        cudaStream_t st = (cudaStream_t)stream;
+        if (pooled) {
+            const long long NQ = (long long)N * (H / 2) * (W / 2);
+            const int S__ = pipe_depth((out && add) ? 2 : 4) > 4 ? 4 : pipe_depth((out && add) ? 2 : 4);
+            const long long PB = NQ * 4 * C * 2;
+#define POOL_ARGS (const bf16*)x, H, W, C, ldx, NQ, sums, gamma, beta, eps, (const bf16*)add, ldadd, nadd, (bf16*)out, ldo, (bf16*)pooled, ldp, TX
+#define CALL(S_) { if (out && add) PIPE_LAUNCH((in_apply_pool_p<S_, true, true>), 8, NQ, 256 / TX, PB, 128 << 10, POOL_ARGS) \
+                   else if (out) PIPE_LAUNCH((in_apply_pool_p<S_, true, false>), 4, NQ, 256 / TX, PB, 128 << 10, POOL_ARGS) \
+                   else PIPE_LAUNCH((in_apply_pool_p<S_, false, false>), 4, NQ, 256 / TX, PB, 256 << 10, POOL_ARGS) }
+            PIPE_DEPTHS3(S__, CALL)
+#undef CALL
+#undef POOL_ARGS
+        } else {
+            const long long NP = (long long)N * H * W;
+            const int S__ = pipe_depth(4);
+            const long long PB = NP * C * 2;
+#define APPLY_ARGS (const bf16*)x, H * W, C, ldx, NP, sums, gamma, beta, eps, (const bf16*)add, ldadd, nadd, (bf16*)out, ldo, TX
+#define CALL(S_) { if (add) PIPE_LAUNCH((in_apply_p<S_, true>), 2, NP, 256 / TX, PB, 128 << 10, APPLY_ARGS) \
+                   else PIPE_LAUNCH((in_apply_p<S_, false>), 1, NP, 256 / TX, PB, 128 << 10, APPLY_ARGS) }
+            PIPE_DEPTHS(S__, CALL)
+#undef CALL
+#undef APPLY_ARGS
+        }
+        SHM_CHECK_LAUNCH("in_apply_p");
+        return SHM_OK;
+    }
     if (fast8_ok(dtype, C) && al16(x, ldx) && al16(add, ldadd) && al16(out, ldo) && al16(pooled, ldp)) {
         const int TX = C / 8;
         const long long un = pooled ? (long long)(H / 2) * (W / 2) : (long long)H * W;
@@ -805,6 +852,20 @@ extern "C" int shm_inorm_bwd_stats(const void* x, int N, int H, int W, int C, in
     SHM_REQUIRE(x && sums && bsums && (dyA || dyP) && N > 0 && H > 0 && W > 0, "shm_inorm_bwd_stats: bad args");
     SHM_REQUIRE(C % 4 == 0, "shm_inorm_bwd_stats: C=%d must be a multiple of 4", C);
     SHM_REQUIRE(!dyP || (H % 2 == 0 && W % 2 == 0), "shm_inorm_bwd_stats: pooled gradient needs even H, W");
+    if (pipe_ok(dtype, C, (long long)H * W) && al16(x, ldx) && al16(dyA, ldA) && al16(dyP, ldP)) {
+        const int TX = C / 8, S__ = pipe_depth(4) > 4 ? 4 : pipe_depth(4);
+        const long long NP = (long long)N * H * W, PB = NP * C * 2;
+        cudaStream_t st = (cudaStream_t)stream;
+#define BS_ARGS (const bf16*)x, H, W, C, ldx, NP, sums, eps, (const bf16*)dyA, ldA, (const bf16*)dyP, ldP, bsums, TX
+#define CALL(S_) { if (dyA && dyP) PIPE_LAUNCH((in_bwd_stats_p<S_, 3>), 3, NP, 256 / TX, PB, 512 << 10, BS_ARGS) \
+                   else if (dyA) PIPE_LAUNCH((in_bwd_stats_p<S_, 1>), 2, NP, 256 / TX, PB, 512 << 10, BS_ARGS) \
+                   else PIPE_LAUNCH((in_bwd_stats_p<S_, 2>), 2, NP, 256 / TX, PB, 512 << 10, BS_ARGS) }
+        PIPE_DEPTHS3(S__, CALL)
+#undef CALL
+#undef BS_ARGS
+        SHM_CHECK_LAUNCH("in_bwd_stats_p");
+        return SHM_OK;
+    }
     if (fast8_ok(dtype, C) && al16(x, ldx) && al16(dyA, ldA) && al16(dyP, ldP)) {
         const int TX = C / 8, pp = ppb8((long long)H * W, 256 / TX, N);
         inorm_bwd_stats8_kernel<<<dim3(cdiv(H * W, pp), 1, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, ldx, sums, eps, (const bf16*)dyA, ldA, (const bf16*)dyP, ldP, bsums, pp, TX);
@@ -828,6 +889,20 @@ extern "C" int shm_inorm_bwd_apply(const void* x, int N, int H, int W, int C, in
     SHM_REQUIRE(x && sums && gamma && bsums && dx && (dyA || dyP) && N > 0 && H > 0 && W > 0, "shm_inorm_bwd_apply: bad args");
     SHM_REQUIRE(C % 4 == 0, "shm_inorm_bwd_apply: C=%d must be a multiple of 4", C);
     SHM_REQUIRE(!dyP || (H % 2 == 0 && W % 2 == 0), "shm_inorm_bwd_apply: pooled gradient needs even H, W");
+    if (pipe_ok(dtype, C, (long long)H * W) && al16(x, ldx) && al16(dyA, ldA) && al16(dyP, ldP) && al16(dx, lddx) && act != SHM_ACT_SIGMOID) {
+        const int TX = C / 8, S__ = pipe_depth(4) > 4 ? 4 : pipe_depth(4);
+        const long long NP = (long long)N * H * W, PB = NP * C * 2;
+        cudaStream_t st = (cudaStream_t)stream;
+#define BA_ARGS (const bf16*)x, H, W, C, ldx, NP, sums, gamma, eps, (const bf16*)dyA, ldA, (const bf16*)dyP, ldP, bsums, act, (bf16*)dx, lddx, dbias, TX
+#define CALL(S_) { if (dyA && dyP) PIPE_LAUNCH((in_bwd_apply_p<S_, 3>), 3, NP, 256 / TX, PB, 128 << 10, BA_ARGS) \
+                   else if (dyA) PIPE_LAUNCH((in_bwd_apply_p<S_, 1>), 2, NP, 256 / TX, PB, 128 << 10, BA_ARGS) \
+                   else PIPE_LAUNCH((in_bwd_apply_p<S_, 2>), 2, NP, 256 / TX, PB, 128 << 10, BA_ARGS) }
+        PIPE_DEPTHS3(S__, CALL)
+#undef CALL
+#undef BA_ARGS
+        SHM_CHECK_LAUNCH("in_bwd_apply_p");
+        return SHM_OK;
+    }
     if (fast8_ok(dtype, C) && al16(x, ldx) && al16(dyA, ldA) && al16(dyP, ldP) && al16(dx, lddx) && act != SHM_ACT_SIGMOID) {
         const int TX = C / 8, pp = ppb8((long long)H * W, 256 / TX, N);
         inorm_bwd_apply8_kernel<<<dim3(cdiv(H * W, pp), 1, N), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, H, W, C, ldx, sums, gamma, eps, (const bf16*)dyA, ldA, (const bf16*)dyP, ldP, bsums, act, (bf16*)dx, lddx, dbias, pp, TX);
@@ -871,6 +946,15 @@ extern "C" int shm_act_bwd(const void* dy, int lddy, const void* y, int ldy, voi
     SHM_REQUIRE(dy && y && dpre && npix >= 0 && C > 0, "shm_act_bwd: bad args");
     if (npix == 0) return SHM_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    if (pipe_ok(dtype, C, npix) && al16(dy, lddy) && al16(y, ldy) && al16(dpre, ldd) && act != SHM_ACT_SIGMOID) {
+        const int TX = C / 8, S__ = pipe_depth(4);
+        cudaStream_t st = (cudaStream_t)stream;
+#define CALL(S_) PIPE_LAUNCH(act_bwd_p<S_>, 2, npix, 256 / TX, (long long)npix * C * 2, 128 << 10, (const bf16*)dy, lddy, (const bf16*)y, ldy, (bf16*)dpre, ldd, (long long)npix, act, dbias, TX)
+        PIPE_DEPTHS(S__, CALL)
+#undef CALL
+        SHM_CHECK_LAUNCH("act_bwd_p");
+        return SHM_OK;
+    }
     if (fast8_ok(dtype, C) && al16(dy, lddy) && al16(y, ldy) && al16(dpre, ldd) && act != SHM_ACT_SIGMOID) {
         const int TX = C / 8, pp = ppb8(npix, 256 / TX, 1);
         act_bwd8_kernel<<<(unsigned)cdiv64(npix, pp), 256, 0, st>>>((const bf16*)dy, lddy, (const bf16*)y, ldy, (bf16*)dpre, ldd, npix, act, dbias, pp, TX);
