@@ -41,6 +41,11 @@ CASES = [
     ("inorm_bwd dyP", lambda: ops.inorm_bwd(x, sums, gamma, None, dyp, dx=out, dbias=db), 3.5 * e),
     ("act_bwd + dbias", lambda: ops.act_bwd(dy, x, 1, out=out, dbias=db), 3 * e),
 ]
+if os.environ.get("BN_ONCE"):            # one launch of each case at the default configuration (for an ncu --set full capture)
+    for name, fn, nbytes in CASES:
+        fn()
+    torch.cuda.synchronize()
+    sys.exit(0)
 CONFIGS = [("regs", (1, 0, 0))] + [("d%d g%d" % (d, g), (0, d, g)) for d in (1, 2, 4) for g in (0, 8, 16, 32)]
 print("N=%d %dx%d C=%d bf16 (%.0f MB per tensor); GB/s of algorithmic bytes (%% of 6544)" % (N, H, W, C, e / 1e6))
 print("%-32s" % "" + "".join("%9s" % c[0] for c in CONFIGS))
