@@ -282,6 +282,13 @@ def run_ours(a):
         line["kernel_families"] = {"%s_%s" % k: {"ms_per_step": v[1] / 2, "tflops": (v[0] / (v[1] * 1e-3) / 1e12) if v[1] > 0 else None,
                                                   "gbs_algorithmic": (v[2] / (v[1] * 1e-3) / 1e9) if v[1] > 0 else None,
                                                   "launches": v[3] // 2} for k, v in sorted(fam.items())}
+        nb_norm = sum(v[2] for k, v in fam.items() if k[0] == "norm") / 2
+        ms_norm = sum(v[1] for k, v in fam.items() if k[0] == "norm") / 2
+        if ms_norm > 0:
+            line["hbm_family"] = {"achieved": nb_norm / (ms_norm * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s", "frac": nb_norm / (ms_norm * 1e-3) / 1e9 / hbm,
+                                  "ms_per_step": ms_norm, "share_of_step": ms_norm / step_ms,
+                                  "note": "all instance-norm / activation-backward launches of the live step (cp.async-pipelined range kernels), "
+                                          "algorithmic bytes / CUDA-event time"}
         line["conv_ms_per_step"] = sum(r[5] for r in rows if r[0] != "norm") / 2
         line["norm_ms_per_step"] = sum(r[5] for r in rows if r[0] == "norm") / 2
         try:

@@ -190,7 +190,8 @@ int shm_style_loss(const double* gramA, const double* gramB, int N, int HW, int 
 /* dY[n,p] += sum_d (dgram[c=0,d] + dgram[d,0]) * x_d / HW  (only the Y channel carries gradient to G) */
 int shm_gram3_bwd(const float* Y, const float* cbcr, int N, int HW, const float* dgram, float* dY, void* stream);
 /* tf.image.ssim on rescale_01'd images (:759-779, utils.py:190-195).  imgA = concat(Y,cbcr) (generated), imgB = yuv [N,HW,3] (reference image).
- * ssim_out[N]; maps[N][3][Ho][Wo][3] saved partials for the backward (may be NULL to skip). */
+ * ssim_out[N]; maps[N][3][Ho][Wo][3] saved partials for the backward (may be NULL to skip).
+ * cbcr == NULL: Y is a packed [N,HW,3] image (the value-only form the test-time metric test.py:335 uses; maps must be NULL). */
 int shm_ssim_fwd(const float* Y, const float* cbcr, const float* mmA, const float* imgB, const float* mmB, int N, int H, int W,
                  float max_val, float* ssim_out, float* maps, void* stream);
 /* loss term: weight * mean_b(-log((1+ssim_b)/2)); dssim[N] = gscale * d/dssim_b */
@@ -207,6 +208,19 @@ int shm_spec_loss(const float* Y, const float* cbcr, const float* yuv, const flo
  *      (1/world for the data-parallel average).  */
 int shm_clip_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
                   float eps, float clip, float gscale, void* stream);
+
+/* ---- rows SURVEY.md 8(f) marks "next": loader contract, degree of polarisation, test-time metrics (csrc/extras.cu) ---- */
+/* datasetLoader.py:48-62: decoded uint8 images src [N,Hs,Ws,3] -> tf.image.resize(bilinear, half-pixel centres) to [N,Ho,Wo,3] fp32,
+ * x / 255.0 (:60), rows reversed when flip_ud != 0 (tf.image.flip_up_down, :61 -- the reference flips when random_flip is False).
+ * Bit-exact with the float32 order of operations of TF's ResizeBilinear kernel. */
+int shm_load_u8_bilinear(const void* src, int N, int Hs, int Ws, float* dst, int Ho, int Wo, int flip_ud, void* stream);
+/* calcDOP ShmGANwithSSpecSeg.py:1157-1169: dop = divide_no_nan(sqrt((I0-I90)^2 + (I45-I135)^2), I0+I90); aop (may be NULL) = 0.5 atan2(S2, S1) */
+int shm_dop(const float* i0, const float* i45, const float* i90, const float* i135, float* dop, float* aop, int64_t n, void* stream);
+/* test.py:338,343 (tf.image.psnr / MeanSquaredError): out[n] += sum over the `per` elements of image n of (a - b)^2, fp64 */
+int shm_sqerr_per_image(const float* a, const float* b, int N, int64_t per, double* out, void* stream);
+/* test.py:346-349: sRGB -> Lab (tfio rgb_to_lab: D65, 2 degree) of both images, then sums[n][0] += sum dE76, sums[n][1] += sum dE94
+ * (skimage deltaE_cie76 / deltaE_ciede94 defaults, rgb1 = the reference colour).  rgb [N,HW,3] fp32 in [0,1]. */
+int shm_delta_e(const float* rgb1, const float* rgb2, int N, int64_t HW, double* sums, void* stream);
 
 #ifdef __cplusplus
 }

@@ -91,6 +91,10 @@ _SIG = {
     "shm_ssim_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "shm_spec_loss": [_P, _P, _P, _P, _L, _P, _F, _P],
     "shm_clip_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P],
+    "shm_load_u8_bilinear": [_P, _I, _I, _I, _P, _I, _I, _I, _P],
+    "shm_dop": [_P, _P, _P, _P, _P, _P, _L, _P],
+    "shm_sqerr_per_image": [_P, _P, _I, _L, _P, _P],
+    "shm_delta_e": [_P, _P, _I, _L, _P, _P],
     "shm_conv2d_tc_weight_elems": [_D],
     "shm_ssim_map_elems": [_I, _I, _I],
     "shm_last_error": [],

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libshmgan.so")
-SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "norm.cu", "prep.cu", "loss.cu", "dense.cu"]
+SOURCES = ["api.cu", "conv_simt.cu", "conv_tc.cu", "norm.cu", "prep.cu", "loss.cu", "dense.cu", "extras.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]

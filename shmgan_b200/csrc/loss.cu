@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(256) ssim_fwd_kernel(const float* __restrict__
         float u = 0.f, v = 0.f;
         if (gy < H && gx < W) {
             const long long p = (long long)n * HW + (long long)gy * W + gx;
-            const float a = c == 0 ? Y[p] : cbcr[p * 2 + (c - 1)];
+            const float a = cbcr == nullptr ? Y[p * 3 + c] : (c == 0 ? Y[p] : cbcr[p * 2 + (c - 1)]);   // cbcr == NULL: A is a packed [N,H,W,3] image
             u = (a - mnA) * iA;
             v = (imgB[p * 3 + c] - mnB) * iB;
         }
@@ -496,7 +496,8 @@ extern "C" int64_t shm_ssim_map_elems(int N, int H, int W) {
 }
 extern "C" int shm_ssim_fwd(const float* Y, const float* cbcr, const float* mmA, const float* imgB, const float* mmB, int N, int H, int W,
                             float max_val, float* ssim_out, float* maps, void* stream) {
-    SHM_REQUIRE(Y && cbcr && mmA && imgB && mmB && ssim_out && N > 0, "shm_ssim_fwd: bad args");
+    SHM_REQUIRE(Y && mmA && imgB && mmB && ssim_out && N > 0, "shm_ssim_fwd: bad args");
+    SHM_REQUIRE(cbcr || !maps, "shm_ssim_fwd: the packed-image form (cbcr == NULL) is value-only");
     SHM_REQUIRE(H >= SS_K && W >= SS_K, "shm_ssim_fwd: image smaller than the 11x11 window");
     const float c1 = (0.01f * max_val) * (0.01f * max_val), c2 = (0.03f * max_val) * (0.03f * max_val);
     cudaStream_t st = (cudaStream_t)stream;

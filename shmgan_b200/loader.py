@@ -1,0 +1,73 @@
+"""Dataset-loader contract of datasetLoader.py:19-170, device side.
+
+The reference zips five `image_dataset_from_directory` streams (folders I0, I60, I90, I150, ED -- or I0, I45, I90, I135, ED --
+:29-33), each `batch_size=1`, resized to (image_size, image_size) with bilinear interpolation, `/255.0` (:60) and flipped
+vertically when `random_flip` is False (:61).  File decoding stays on the host (PNG/JPEG decode is control-plane work, out of
+scope); this module takes the DECODED uint8 arrays, stages them through pinned memory and runs resize + scale + flip as one
+kernel per folder (`shm_load_u8_bilinear`), yielding exactly the 5-tuple `train_step(orig0, orig45, orig90, orig135, origED)` takes.
+"""
+from __future__ import annotations
+
+import os
+from typing import Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+FOLDERS_PSD = ("I0", "I60", "I90", "I150", "ED")         # datasetLoader.py:29-33 (PSD polar dataset)
+FOLDERS_SHMGAN = ("I0", "I45", "I90", "I135", "ED")      # datasetLoader.py:22-26 (commented alternative)
+_EXT = (".bmp", ".gif", ".jpeg", ".jpg", ".png")         # keras image_dataset_from_directory's allow-list
+
+
+def list_folder(path: str) -> List[str]:
+    """File order of image_dataset_from_directory(shuffle=False): sorted walk, allow-listed extensions."""
+    return [os.path.join(path, f) for f in sorted(os.listdir(path)) if f.lower().endswith(_EXT)]
+
+
+def decode_rgb_u8(path: str) -> np.ndarray:
+    """Host-side decode to uint8 [H,W,3] RGB (color_mode='rgb').  Uses whichever decoder this image has."""
+    try:
+        from PIL import Image
+        with Image.open(path) as im:
+            return np.asarray(im.convert("RGB"), dtype=np.uint8)
+    except ImportError:
+        import cv2
+        return cv2.cvtColor(cv2.imread(path, cv2.IMREAD_COLOR), cv2.COLOR_BGR2RGB)
+
+
+class PolarimetricLoader:
+    """Iterates 5-tuples of [B,S,S,3] fp32 device tensors in the reference's zip order.
+
+    sources: five sequences of decoded uint8 [H,W,3] arrays (or five folder paths).  batch_size images of equal source size are
+    stacked per step (the reference uses batch_size = 1, datasetLoader.py:57); `repeat` = num_epochs (:161)."""
+
+    def __init__(self, sources: Sequence, image_size: int, batch_size: int = 1, random_flip: bool = True, repeat: int = 1):
+        assert len(sources) == 5, "five streams: I0, I45|I60, I90, I135|I150, ED"
+        self.streams = [([decode_rgb_u8(p) for p in list_folder(s)] if isinstance(s, str) else list(s)) for s in sources]
+        n = {len(s) for s in self.streams}
+        assert len(n) == 1, "the five folders must hold the same number of images (tf.data.Dataset.zip truncates silently)"
+        self.length_dataset = n.pop()                      # datasetLoader.py:165
+        self.image_size, self.batch_size, self.flip, self.repeat = image_size, batch_size, (not random_flip), repeat
+        self._pinned: Optional[torch.Tensor] = None
+
+    def __len__(self) -> int:
+        return self.repeat * ((self.length_dataset + self.batch_size - 1) // self.batch_size)
+
+    def _stage(self, imgs: List[np.ndarray]) -> torch.Tensor:
+        arr = np.stack(imgs)
+        if self._pinned is None or self._pinned.shape != arr.shape:
+            self._pinned = torch.empty(arr.shape, dtype=torch.uint8, pin_memory=True)
+        self._pinned.copy_(torch.from_numpy(arr))
+        return self._pinned.cuda(non_blocking=True)
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
+        for _ in range(self.repeat):
+            for i in range(0, self.length_dataset, self.batch_size):
+                out = []
+                for s in self.streams:
+                    dev = self._stage(s[i:i + self.batch_size])
+                    out.append(ops.load_u8_images(dev, self.image_size, self.flip))
+                    torch.cuda.current_stream().synchronize()        # the pinned staging buffer is reused by the next stream
+                yield tuple(out)

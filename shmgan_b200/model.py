@@ -192,6 +192,10 @@ class ShmGANwithSSpecSeg:
         """utils.py:68-123: pseudo-diffuse = per-pixel, per-channel min over the four polarisation images."""
         return ops.pseudo_diffuse_min4(i0.contiguous(), i45.contiguous(), i90.contiguous(), i135.contiguous())
 
+    def calcDOP(self, I0_Ych, I45_Ych, I90_Ych, I135_Ych):
+        """:1157-1169: degree of polarisation from the four Y planes (Stokes S0, S1, S2; divide_no_nan)."""
+        return ops.dop(_f32(I0_Ych), _f32(I45_Ych), _f32(I90_Ych), _f32(I135_Ych))
+
     def _y_plane(self, yuv, dtype):
         """Y channel [B,S,S,1] of a yuv tensor, converted to `dtype` (:486-490)."""
         B, S = yuv.shape[0], yuv.shape[1]

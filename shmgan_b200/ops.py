@@ -545,3 +545,26 @@ def yuv2rgb_bwd(drgb_f32, drgb_lp, dY, accumulate):
     code = dt(drgb_lp) if drgb_lp is not None else F32
     call("shm_yuv2rgb_bwd", _p(drgb_f32), _p(drgb_lp), code, 3 if drgb_lp is None else drgb_lp.shape[-1], _p(dY), dY.numel(),
          int(accumulate), _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# rows SURVEY 8(f): loader contract, degree of polarisation (csrc/extras.cu)
+# ------------------------------------------------------------------------------------------------
+def load_u8_images(img_u8: torch.Tensor, image_size: int, flip_ud: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """datasetLoader.py:48-62 on the device: uint8 [N,Hs,Ws,3] -> bilinear resize (TF2 half-pixel) -> /255 -> optional vertical flip."""
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3, "uint8 [N,H,W,3] expected"
+    n, hs, ws, _ = img_u8.shape
+    if out is None:
+        out = new((n, image_size, image_size, 3), torch.float32)
+    if n == 0:                                # empty batch -> empty output, no launch
+        return out
+    call("shm_load_u8_bilinear", _p(img_u8.contiguous()), n, hs, ws, _p(out), image_size, image_size, int(bool(flip_ud)), _stream())
+    return out
+
+
+def dop(i0, i45, i90, i135, want_angle: bool = False):
+    """calcDOP (ShmGANwithSSpecSeg.py:1157-1169) on fp32 planes of any shape; returns DoP (and the angle of polarisation)."""
+    out = torch.empty_like(i0)
+    aop = torch.empty_like(i0) if want_angle else None
+    call("shm_dop", _p(i0.contiguous()), _p(i45.contiguous()), _p(i90.contiguous()), _p(i135.contiguous()), _p(out), _p(aop), i0.numel(), _stream())
+    return (out, aop) if want_angle else out
