@@ -339,6 +339,18 @@ def run_ours(a):
                 gf = 119.5 * (isz / 256.0) ** 2              # SpecSeg + G1 with the live mask branch, GFLOP per image
                 inf[tag] = {"images_per_s": ib / (t * 1e-3), "ms_per_batch": t, "batch": ib, "size": isz,
                             "tflops": gf * ib / t}
+                # where the batch's time goes: per-launch CUDA events of one more pass, by kernel family
+                ops.PROF = []
+                inet.inference_step(img)
+                torch.cuda.synchronize()
+                fams = {}
+                for f, kind, name, fl, nb, ev0, ev1 in ops.PROF:
+                    c = fams.setdefault(("tc" if f.startswith("tc:") else f) + "_" + kind, [0.0, 0.0, 0.0, 0])
+                    c[0] += ev0.elapsed_time(ev1); c[1] += fl; c[2] += nb; c[3] += 1
+                ops.PROF = None
+                inf[tag]["families"] = {k: {"ms": v[0], "tflops": v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else None,
+                                            "gbs": v[2] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else None, "launches": v[3]}
+                                        for k, v in sorted(fams.items(), key=lambda kv: -kv[1][0])}
                 del inet, img
                 torch.cuda.empty_cache()
             except Exception as ex:                          # report, do not hide

@@ -43,8 +43,13 @@ class PolarimetricLoader:
     sources: five sequences of decoded uint8 [H,W,3] arrays (or five folder paths).  batch_size images of equal source size are
     stacked per step (the reference uses batch_size = 1, datasetLoader.py:57); `repeat` = num_epochs (:161)."""
 
-    def __init__(self, sources: Sequence, image_size: int, batch_size: int = 1, random_flip: bool = True, repeat: int = 1):
-        assert len(sources) == 5, "five streams: I0, I45|I60, I90, I135|I150, ED"
+    def __init__(self, sources: Sequence, image_size: int, batch_size: int = 1, random_flip: bool = True, repeat: int = 1,
+                 est_diffuse: bool = False):
+        # est_diffuse (main.py:36 declares the flag, nothing reads it): four polarisation streams only; the fifth (ED) is the
+        # pseudo-diffuse min-of-4 of the DECODED uint8 images (utils.py:68-123 works on the originals), computed on the device
+        # and then sent through the same resize / scale / flip kernel as a pre-populated ED folder would be
+        self.est_diffuse = est_diffuse
+        assert len(sources) == (4 if est_diffuse else 5), "streams: I0, I45|I60, I90, I135|I150 (, ED unless est_diffuse)"
         self.streams = [([decode_rgb_u8(p) for p in list_folder(s)] if isinstance(s, str) else list(s)) for s in sources]
         n = {len(s) for s in self.streams}
         assert len(n) == 1, "the five folders must hold the same number of images (tf.data.Dataset.zip truncates silently)"
@@ -65,9 +70,13 @@ class PolarimetricLoader:
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
         for _ in range(self.repeat):
             for i in range(0, self.length_dataset, self.batch_size):
-                out = []
+                out, raw = [], []
                 for s in self.streams:
                     dev = self._stage(s[i:i + self.batch_size])
                     out.append(ops.load_u8_images(dev, self.image_size, self.flip))
                     torch.cuda.current_stream().synchronize()        # the pinned staging buffer is reused by the next stream
+                    if self.est_diffuse:
+                        raw.append(dev)
+                if self.est_diffuse:
+                    out.append(ops.load_u8_images(ops.pseudo_diffuse_min4(*raw), self.image_size, self.flip))
                 yield tuple(out)

@@ -64,7 +64,7 @@ def minmax3(Y_or_yuv, cbcr):
 def gram3(Y_or_yuv, cbcr):
     n = Y_or_yuv.shape[0]
     hw = Y_or_yuv.shape[1] * Y_or_yuv.shape[2]
-    g = torch.zeros((n, 9), dtype=torch.float64, device=Y_or_yuv.device)
+    g = ops.zeros64((n, 9), Y_or_yuv.device)
     call("shm_gram3", _p(Y_or_yuv), _p(cbcr), n, hw, _p(g), _stream())
     return g
 

@@ -208,6 +208,7 @@ class ShmGANwithSSpecSeg:
         """train_step (:467-875).  Five [B,S,S,3] fp32 CUDA tensors in [0,1]; returns None and publishes the reference's
         attributes (gen_Y, gen_rgb, cyc_gen*_rgb, specular_candidate, the loss scalars ...)."""
         self.build()
+        ops.arena_begin()
         G, D = self.G.net, self.D.net
         origs = [t.contiguous() for t in (orig0, orig45, orig90, orig135, origED)]
         B, S = origs[0].shape[0], origs[0].shape[1]
@@ -435,6 +436,7 @@ class ShmGANwithSSpecSeg:
         """The per-image body of test.py:218-297: standardise -> SpecSeg mask -> G1 with only slot 0 populated and the ED
         one-hot plane -> yuv->rgb with the image's own CbCr.  Returns gen_rgb [B,S,S,3] fp32 (and publishes gen_Y, mask)."""
         self.build()
+        ops.arena_begin()
         G = self.G.net
         rgb = rgb.contiguous()
         B, S = rgb.shape[0], rgb.shape[1]

@@ -42,6 +42,42 @@ def _prof(family, kind, name, flops, nbytes, fn):
     return r
 
 
+# fp64 accumulator arena: the ~100 statistics buffers of one step (sum / sum^2 per (n, c), loss partials) are slices of ONE buffer
+# that is cleared by a single memset when the step begins, instead of one torch.zeros fill kernel each.  Outside a step
+# (arena_begin not called, or the arena is exhausted) zeros64 falls back to torch.zeros.
+_ARENA = None
+_ARENA_USED = 0
+_ARENA_ON = False
+ARENA_DOUBLES = 8 << 20
+
+
+def arena_begin():
+    """Start of a train / inference step: recycle the arena (clears the part the previous step used, on the current stream)."""
+    global _ARENA, _ARENA_USED, _ARENA_ON
+    if _ARENA is None:
+        _ARENA = torch.zeros(ARENA_DOUBLES, dtype=torch.float64, device="cuda")
+    elif _ARENA_USED:
+        _ARENA[:_ARENA_USED].zero_()
+    _ARENA_USED, _ARENA_ON = 0, True
+
+
+def arena_end():
+    global _ARENA_ON
+    _ARENA_ON = False
+
+
+def zeros64(shape, device) -> torch.Tensor:
+    global _ARENA_USED
+    n = 1
+    for v in shape:
+        n *= int(v)
+    if not _ARENA_ON or _ARENA_USED + n > ARENA_DOUBLES or _ARENA.device != torch.device(device):
+        return torch.zeros(shape, dtype=torch.float64, device=device)
+    t = _ARENA[_ARENA_USED:_ARENA_USED + n].view(shape)
+    _ARENA_USED += (n + 1) // 2 * 2                      # keep 16-byte alignment (double2 loads)
+    return t
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -306,7 +342,7 @@ class PaddedConv(Conv):
 # ------------------------------------------------------------------------------------------------
 def inorm_stats(x: torch.Tensor) -> torch.Tensor:
     n, h, w, c = x.shape
-    sums = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    sums = zeros64((n, c, 2), x.device)
     _prof("norm", "stats", "c%d" % c, 0, x.numel() * x.element_size(),
           lambda: call("shm_inorm_stats", _p(x), n, h * w, c, ld(x), dt(x), _p(sums), _stream()))
     return sums
@@ -329,7 +365,7 @@ def inorm_bwd(x, sums, gamma, dyA=None, dyP=None, act=ACT_LRELU, dx=None, dbias=
     """dL/d(pre-activation of the producing conv) from dL/dy, y = IN(x), x = post-activation conv output.
     dbias (fp32 [C], optional) += column sums of the result: the producing conv's bias gradient, fused into the same pass."""
     n, h, w, c = x.shape
-    bs = torch.zeros((n, c, 2), dtype=torch.float64, device=x.device)
+    bs = zeros64((n, c, 2), x.device)
     e = x.numel() * x.element_size()
     rd = e * (1 + (0 if dyA is None else 1) + (0 if dyP is None else 0.25))
     _prof("norm", "bwd_stats", "c%d" % c, 0, rd,
@@ -467,7 +503,7 @@ def pseudo_diffuse_min4(i0, i45, i90, i135):
 def yuv_standardize(rgb):
     """rgb [N,H,W,3] fp32 -> (standardised yuv [N,H,W,3] fp32, scale [N])."""
     n, h, w, _ = rgb.shape
-    sums = torch.zeros((n, 2), dtype=torch.float64, device=rgb.device)
+    sums = zeros64((n, 2), rgb.device)
     call("shm_yuv_stats", _p(rgb), n, h * w, _p(sums), _stream())
     yuv = torch.empty_like(rgb)
     scale = new((n,), torch.float32)

@@ -103,3 +103,14 @@ def test_loader_feeds_train_step():
     net = _net()
     net.train_step(*batches[0])
     assert np.isfinite(net.total_Generator_loss) and np.isfinite(net.total_Discriminator_loss)
+
+
+def test_loader_estimates_diffuse_on_device():
+    from shmgan_b200 import loader
+    rng = np.random.default_rng(22)
+    pol = [[rng.integers(0, 256, size=(70, 90, 3), dtype=np.uint8) for _ in range(3)] for _ in range(4)]
+    ld = loader.PolarimetricLoader(pol, image_size=64, batch_size=3, random_flip=True, est_diffuse=True)
+    (b,) = list(ld)
+    assert len(b) == 5
+    ed = np.minimum(np.minimum(np.stack(pol[0]), np.stack(pol[1])), np.minimum(np.stack(pol[2]), np.stack(pol[3])))
+    assert np.array_equal(b[4].cpu().numpy(), E.load_images(ed, 64, random_flip=True))
