@@ -71,6 +71,10 @@ int shm_conv2d_tc_prep_weights_both(const shm_conv_desc* d, const float* w, int 
 int shm_conv2d_tc_prep_weights_padded(const shm_conv_desc* d, const float* w, int cin_real, int seg_real, int seg_pad, int cout_real,
                                       void* w_tc, void* stream);
 int shm_conv2d_tc_fwd  (const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, void* stream);
+/* Same, storing only the first `nstore` (multiple of 8) output channels of every pixel: the remaining Cout - nstore columns are the zero
+ * padding of a layer whose real channel count is below the tensor-core granule (SpecSeg.py:68,78: Conv2DTranspose to 32 / 16 channels
+ * written into the [up | skip] concat buffer).  Served by the Conv2DTranspose scatter kernel only (SHM_EUNSUPPORTED otherwise). */
+int shm_conv2d_tc_fwd_cols(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream);
 int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const void* w_tc_dgrad, void* dx, void* stream);
 int shm_conv2d_tc_wgrad(const shm_conv_desc* d, const void* x, const void* dy, float* dw, void* stream);   /* dw += (fp32 atomics) */
 /* dbias[c] += sum over pixels of dy[pix, c] */
@@ -157,6 +161,8 @@ int shm_assemble_input(const float* const src[5], const int32_t src_ld[5], int o
 /* dst (bf16, pixel stride 64) = src channels 0..C-1 (C <= 64) followed by zeros: the zero-padded input that lets the first layers
  * (Cin = 10 / 3 / 1) run on the tensor-core kernels, whose reduction dimension moves in 64-channel TMA boxes */
 int shm_pad_channels64(const void* src, int src_dtype, int lds, int C, void* dst_bf16, int64_t npix, void* stream);
+/* same with a padded width Cpad in {16, 32, 64}: the inputs of the thin tensor-core layers (16 / 32 reduction channels per pixel row) */
+int shm_pad_channels(const void* src, int src_dtype, int lds, int C, void* dst_bf16, int Cpad, int64_t npix, void* stream);
 /* im2col of a 3x3 stride-2 SAME conv on a few-channel image (discriminator d1, ShmGANwithSSpecSeg.py:353): out bf16 [N,H/2,W/2,64],
  * channel (ky*3+kx)*C + c = x[n, 2oy+ky-pb, 2ox+kx-pb, c] (zero outside / beyond 9*C); d1 then runs as a 1x1 conv on the tensor cores.
  * col2im is its transpose (the d(image) of the generator-loss path). */

@@ -39,6 +39,7 @@ _SIG = {
     "shm_conv2d_tc_prep_weights_both": [_D, _P, _I, _P, _P, _P],
     "shm_conv2d_tc_prep_weights_padded": [_D, _P, _I, _I, _I, _I, _P, _P],
     "shm_conv2d_tc_fwd": [_D, _P, _P, _P, _P, _P],
+    "shm_conv2d_tc_fwd_cols": [_D, _P, _P, _P, _P, _I, _P],
     "shm_conv2d_tc_dgrad": [_D, _P, _P, _P, _P],
     "shm_conv2d_tc_wgrad": [_D, _P, _P, _P, _P],
     "shm_colsum": [_P, _L, _I, _I, _I, _P, _P],
@@ -67,6 +68,7 @@ _SIG = {
     "shm_avg_cbcr": [_P, _P, _P, _P, _P, _P, _L, _P],
     "shm_assemble_input": [C.POINTER(_P), C.POINTER(C.c_int32), _I, _P, _I, _L, _I, _P],
     "shm_pad_channels64": [_P, _I, _I, _I, _P, _L, _P],
+    "shm_pad_channels": [_P, _I, _I, _I, _P, _I, _L, _P],
     "shm_im2col_k3s2": [_P, _I, _I, _I, _I, _I, _I, _P, _P],
     "shm_col2im_k3s2": [_P, _I, _I, _I, _I, _P, _I, _I, _P],
     "shm_assemble_bwd": [_P, _I, _I, C.POINTER(C.c_int32), _I, _P, _L, _P],

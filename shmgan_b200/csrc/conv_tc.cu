@@ -121,6 +121,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
     d |= (uint64_t)2 << 61;      // SWIZZLE_128B
     return d;
 }
+// same with an explicit swizzle mode for rows of 128 / 64 / 32 bytes (descriptor layout-type codes 2 / 4 / 6)
+__device__ __forceinline__ uint64_t make_desc_swz(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_code) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)layout_code << 61;
+    return d;
+}
 // instruction descriptor: bf16 x bf16 -> fp32, M x N, A/B major bits
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -151,8 +161,45 @@ __device__ __forceinline__ void tmem_wait_ld32(uint32_t* r) {
         :: "memory");
 }
 
+// 32 lanes x 16 columns (thin layers with 16 output channels), without / with the wait
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+          "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+        :: "memory");
+}
+// bias + activation + bf16 + 32 contiguous bytes for 16 accumulator columns
+__device__ __forceinline__ void epi_store16(const uint32_t* r, const float* sbias, int act, bf16* __restrict__ dst) {
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (sbias ? sbias[j] : 0.f);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        if (act == SHM_ACT_LRELU) v[j] = fmaxf(v[j], 0.2f * v[j]);
+        else if (act == SHM_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+        else if (act == SHM_ACT_SIGMOID) v[j] = 1.f / (1.f + __expf(-v[j]));
+    }
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+        uint4 u;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + j) = u;
+    }
+}
+
 // bias (shared memory, broadcast reads) + activation + bf16 + 64 contiguous bytes for 32 accumulator columns in registers
-__device__ __forceinline__ void epi_store32(const uint32_t* r, const float* sbias, int act, bf16* __restrict__ dst, bool ok) {
+__device__ __forceinline__ void epi_store32(const uint32_t* r, const float* sbias, int act, bf16* __restrict__ dst, bool ok, int ncols = 32) {
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
@@ -177,6 +224,7 @@ __device__ __forceinline__ void epi_store32(const uint32_t* r, const float* sbia
     if (ok) {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
+            if (j >= ncols) break;                       // partial store: only the first ncols channels of this chunk exist in dst
             uint4 u;
             __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
             __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
@@ -192,14 +240,14 @@ __device__ __forceinline__ void epi_store32(const uint32_t* r, const float* sbia
 // warps' samples on the first use of the tcgen05.ld result (the load competes with the MMAs for TMEM bandwidth), which made
 // every 64-channel layer epilogue-bound (3300 cycles per 128 x 64 tile against 1360 tensor cycles).
 template <int NC>
-__device__ __forceinline__ void epi_row(uint32_t taddr, const float* sbias, int act, bf16* __restrict__ dst, bool ok) {
+__device__ __forceinline__ void epi_row(uint32_t taddr, const float* sbias, int act, bf16* __restrict__ dst, bool ok, int ncols = NC * 32) {
     uint32_t r[2][32];
     tmem_ld32_nw(taddr, r[0]);
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
         tmem_wait_ld32(r[c & 1]);
         if (c + 1 < NC) tmem_ld32_nw(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
-        epi_store32(r[c & 1], sbias ? sbias + c * 32 : nullptr, act, dst + c * 32, ok);
+        epi_store32(r[c & 1], sbias ? sbias + c * 32 : nullptr, act, dst + c * 32, ok, ncols - c * 32);
     }
 }
 
@@ -380,22 +428,35 @@ struct HaloParams {
     bf16* out;
 };
 
-template <int KC, int BN>
+// CPX = bytes of one pixel row of the A operand = 2 x (reduction channels per k-chunk): 128 (64 channels, SWIZZLE_128B) for the
+// regular layers; 64 / 32 (32 / 16 channels, SWIZZLE_64B / 32B) for the THIN layers -- SpecSeg's 16/32-channel levels
+// (SpecSeg.py:34-44, :76-86), the 1-channel mask inputs of the attention branches (ShmGANwithSSpecSeg.py:404-412) and the
+// 10-channel generator input (:243) -- which otherwise run zero-padded to 64 channels (4x the bytes, up to 16x the MMAs).
+// The shifted-descriptor trick is unchanged: the swizzle is a function of absolute shared-memory address bits in every mode.
+template <int KC, int BN, int CPX = 128>
 struct HaloCfg {
-    static constexpr int W_BYTES = 9 * KC * BN * 128;
+    static_assert(CPX == 128 || KC == 1, "thin rows hold the whole reduction dimension");
+    static constexpr int W_TILE = BN * CPX;                       // one tap, one k-chunk
+    static constexpr int W_BYTES = 9 * KC * W_TILE;
+    static constexpr int W_SPACE = (W_BYTES + 1023) / 1024 * 1024;
+    static constexpr int A_BYTES = HALO_W * HALO_H * CPX;
+    static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
     static constexpr int STAGES = (W_BYTES <= 73728) ? 6 : 3;
-    static constexpr int SMEM = W_BYTES + STAGES * HALO_STAGE + 1024 + 256 + BIAS_SMEM;
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM = W_SPACE + STAGES * A_STAGE + 1024 + 256 + BIAS_SMEM;
+    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    static constexpr uint32_t LAYOUT = CPX == 128 ? 2u : (CPX == 64 ? 4u : 6u);
 };
 
-template <int KC, int BN>
+template <int KC, int BN, int CPX = 128>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
-    using Cfg = HaloCfg<KC, BN>;
+    using Cfg = HaloCfg<KC, BN, CPX>;
+    constexpr int HALO_STAGE = Cfg::A_STAGE;
+    constexpr int HALO_BYTES = Cfg::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sW = smem;                                   // [9 taps][KC][BN rows x 128 B]
-    uint8_t* sA = smem + Cfg::W_BYTES;                    // [STAGES][HALO_STAGE]
+    uint8_t* sW = smem;                                   // [9 taps][KC][BN rows x CPX B]
+    uint8_t* sA = smem + Cfg::W_SPACE;                    // [STAGES][HALO_STAGE]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::STAGES * HALO_STAGE);
     uint64_t* full = bars;
     uint64_t* empty = bars + Cfg::STAGES;
@@ -429,7 +490,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_expect_tx(wbar, Cfg::W_BYTES);
                 for (int t = 0; t < 9; ++t)
                     for (int kc = 0; kc < KC; ++kc)
-                        tma_load_2d(sW + (t * KC + kc) * (BN * 128), &tmB, wbar, kc * 64, p.wrow[t]);
+                        tma_load_2d(sW + (t * KC + kc) * Cfg::W_TILE, &tmB, wbar, kc * 64, p.wrow[t]);
             }
             __syncwarp();
             int stage = 0; uint32_t phase = 0;
@@ -464,10 +525,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (elect_one_sync()) {
 #pragma unroll
                     for (int t = 0; t < 9; ++t) {
-                        const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(p.tdy[t] * HALO_W + p.tdx[t]) * 128u, 16, HALO_W * 128);
-                        const uint64_t bdesc = make_desc_sw128(smem_u32(sW + (t * KC + kc) * (BN * 128)), 16, 1024);
+                        const uint64_t adesc = make_desc_swz(a0 + (uint32_t)(p.tdy[t] * HALO_W + p.tdx[t]) * (uint32_t)CPX, 16, HALO_W * CPX, Cfg::LAYOUT);
+                        const uint64_t bdesc = make_desc_swz(smem_u32(sW + (t * KC + kc) * Cfg::W_TILE), 16, 8 * CPX, Cfg::LAYOUT);
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
+                        for (int k = 0; k < CPX / 32; ++k)
                             umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
                     }
                     umma_commit(&empty[stage]);
@@ -490,7 +551,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             bf16* dst = p.out + ((long long)(img * p.H + oy) * p.W + ox) * p.ldout;
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
-            {
+            if constexpr (BN == 16) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+                uint32_t r[16];
+                tmem_ld16_nw(taddr, r);
+                tmem_wait_ld16(r);
+                epi_store16(r, p.bias ? sbias : nullptr, p.act, dst);
+            } else {
                 constexpr int NC = BN / 32;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
                 uint32_t r[NC][32];
@@ -538,6 +605,7 @@ struct MultiParams {
     int OS, TH, a_bytes, hy, hx;              // output stride, tile height, bytes of the halo box, halo origin relative to the tile origin
     int kchunks, tiles_x, tiles_y, m_tiles, n_tiles;
     int Hout, Wout, ldout;
+    int nstore;                               // output channels that exist in `out` (<= Nn; the rest are zero-padding columns)
     const float* bias; int act;
     bf16* out;
 };
@@ -668,7 +736,7 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const bool ok = oy < p.Hout && ox < p.Wout;
                 bf16* dst = p.out + ((long long)(img * p.Hout + oy) * p.Wout + ox) * p.ldout + nt * BN;
                 epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN), p.bias ? sbias + nt * BN : nullptr,
-                                 p.act, dst, ok);
+                                 p.act, dst, ok, p.nstore - nt * BN);
             }
             tc_fence_before();
             __syncwarp();
@@ -712,15 +780,18 @@ int encode_act(CUtensorMap* tm, const void* base, int C, int W, int H, int N, in
     return SHM_OK;
 }
 // 2-D weight map: dims (K, rows), bf16, box (64, bn)
-int encode_w(CUtensorMap* tm, const void* base, int K, long long rows, int bn) {
+inline CUtensorMapSwizzle swizzle_for(int inner) {
+    return inner == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (inner == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+int encode_w(CUtensorMap* tm, const void* base, int K, long long rows, int bn, int inner = 64) {
     EncodeTiledFn enc = get_encode();
     if (!enc) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)bn};
+    cuuint32_t box[2] = {(cuuint32_t)inner, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(inner), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled(weights K=%d rows=%lld) failed: %d", K, rows, (int)r);
     return SHM_OK;
@@ -787,15 +858,15 @@ int launch_tc(const Geometry& g, int N, const void* in, const void* w_tc, int wr
 
 
 // encode a 4-D activation map with an explicit box (halo kernel)
-int encode_act_box(CUtensorMap* tm, const void* base, int C, int W, int H, int N, int ld, int bx, int by) {
+int encode_act_box(CUtensorMap* tm, const void* base, int C, int W, int H, int N, int ld, int bx, int by, int inner = 64) {
     EncodeTiledFn enc = get_encode();
     if (!enc) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-    cuuint32_t box[4] = {64, (cuuint32_t)bx, (cuuint32_t)by, 1};
+    cuuint32_t box[4] = {(cuuint32_t)inner, (cuuint32_t)bx, (cuuint32_t)by, 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(inner), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled(halo C=%d W=%d H=%d N=%d ld=%d) failed: %d", C, W, H, N, ld, (int)r);
     return SHM_OK;
@@ -842,6 +913,7 @@ int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, con
     p.kchunks = K / 64;
     p.tiles_x = W / 8; p.tiles_y = H / 32;
     p.m_tiles = N * p.tiles_x * p.tiles_y; p.n_tiles = Nn / 128;
+    p.nstore = Nn;
     p.Hout = H; p.Wout = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
     CUtensorMap tmA, tmB;
     if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, BIG_H)) return rc;
@@ -858,8 +930,9 @@ bool scatter_ok(int Hq, int Wq, int K, int Nn) {
 struct ScatterTap { int ry, rx, dy, dx, wrow; };
 
 int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
-                   void* out, int Hout, int Wout, int ldout, const ScatterTap* taps, int ntaps, cudaStream_t st) {
+                   void* out, int Hout, int Wout, int ldout, const ScatterTap* taps, int ntaps, cudaStream_t st, int nstore = 0) {
     MultiParams p{};
+    p.nstore = nstore > 0 ? nstore : Nn;
     if (ntaps > 9) SHM_FAIL(SHM_EUNSUPPORTED, "conv_scatter: more than 9 taps");
     bool seen[4] = {false, false, false, false};
     p.ntaps = ntaps;
@@ -891,13 +964,22 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
     return launch_multi_t<64, 2, 1>(tmA, tmB, p, st);                   // 4 x 64 columns, double-buffered
 }
 
-template <int KC, int BN>
+// thin stride-1 3x3 layers (fewer than 64 reduction or output channels) the halo kernel serves with 32- / 64-byte pixel rows
+bool thin_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
+    if (!(kh == 3 && kw == 3 && stride == 1 && H % 16 == 0 && W % 8 == 0)) return false;
+    if (K == 16) return Nn == 16 || Nn == 32 || Nn == 64 || Nn == 128;
+    if (K == 32) return Nn == 16 || Nn == 32 || Nn == 64;
+    if (K == 64) return Nn == 16 || Nn == 32;
+    return false;
+}
+
+template <int KC, int BN, int CPX = 128>
 int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<KC, BN>::SMEM); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<KC, BN, CPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<KC, BN, CPX>::SMEM); attr = true; }
     int grid = shm_num_sms();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    conv_halo_kernel<KC, BN><<<grid, TC_THREADS, HaloCfg<KC, BN>::SMEM, st>>>(tmA, tmB, p);
+    conv_halo_kernel<KC, BN, CPX><<<grid, TC_THREADS, HaloCfg<KC, BN, CPX>::SMEM, st>>>(tmA, tmB, p);
     SHM_CHECK_LAUNCH("conv_halo_kernel");
     return SHM_OK;
 }
@@ -916,8 +998,20 @@ int launch_halo(int N, int H, int W, int K, int Nn, const void* in, int ldin, co
     p.tiles_x = W / 8; p.tiles_y = H / 16; p.total_tiles = N * p.tiles_x * p.tiles_y;
     p.H = H; p.W = W; p.ldout = ldout; p.Nn = Nn; p.bias = bias; p.act = act; p.out = (bf16*)out;
     CUtensorMap tmA, tmB;
-    if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, HALO_H)) return rc;
-    if (int rc = encode_w(&tmB, w_tc, K, wrows_total, Nn)) return rc;
+    const int inner = K < 64 ? K : 64;
+    if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, HALO_H, inner)) return rc;
+    if (int rc = encode_w(&tmB, w_tc, K, wrows_total, Nn, inner)) return rc;
+    if (K == 16) {
+        if (Nn == 16) return launch_halo_t<1, 16, 32>(tmA, tmB, p, st);
+        if (Nn == 32) return launch_halo_t<1, 32, 32>(tmA, tmB, p, st);
+        if (Nn == 64) return launch_halo_t<1, 64, 32>(tmA, tmB, p, st);
+        if (Nn == 128) return launch_halo_t<1, 128, 32>(tmA, tmB, p, st);
+    } else if (K == 32) {
+        if (Nn == 16) return launch_halo_t<1, 16, 64>(tmA, tmB, p, st);
+        if (Nn == 32) return launch_halo_t<1, 32, 64>(tmA, tmB, p, st);
+        if (Nn == 64) return launch_halo_t<1, 64, 64>(tmA, tmB, p, st);
+    } else if (K == 64 && Nn == 16) return launch_halo_t<1, 16, 128>(tmA, tmB, p, st);
+    else if (K == 64 && Nn == 32) return launch_halo_t<1, 32, 128>(tmA, tmB, p, st);
     if (K == 64 && Nn == 64) return launch_halo_t<1, 64>(tmA, tmB, p, st);
     if (K == 128 && Nn == 64) return launch_halo_t<2, 64>(tmA, tmB, p, st);
     if (K == 64 && Nn == 128) return launch_halo_t<1, 128>(tmA, tmB, p, st);
@@ -1541,7 +1635,11 @@ int launch_wgrad_s2(const shm_conv_desc* d, const void* x, const void* dy, float
 int tc_check(const shm_conv_desc* d) {
     SHM_REQUIRE(d != nullptr, "conv desc is NULL");
     if (d->dtype != SHM_BF16) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: needs dtype bf16");
-    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: Cin=%d / Cout=%d must be multiples of 64", d->Cin, d->Cout);
+    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) {
+        // thin layers: the forward pass (K = Cin, N = Cout) of a stride-1 3x3 conv goes through the halo kernel with narrow pixel rows
+        const bool thin = !d->transposed && thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride);
+        if (!thin) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: Cin=%d / Cout=%d must be multiples of 64 (or a thin 3x3 stride-1 layer)", d->Cin, d->Cout);
+    }
     if (d->ldx % 8 != 0 || d->ldy % 8 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: ld must be a multiple of 8");
     if (d->kh < 1 || d->kh > 3 || d->kw < 1 || d->kw > 3 || (d->stride != 1 && d->stride != 2)) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: kernel/stride unsupported");
     if (d->transposed && d->stride != 2) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: transposed conv needs stride 2");
@@ -1625,9 +1723,9 @@ extern "C" int shm_conv2d_tc_prep_weights_padded(const shm_conv_desc* d, const f
 
 extern "C" int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad) {
     if (tc_check(d) != SHM_OK) return 0;
+    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) return for_dgrad ? 0 : 1;      // thin layer (tc_check admitted it): forward only
     int Ho, Wo; out_dims(d, Ho, Wo);
     int BW, BH, BI;
-    (void)for_dgrad;
     // in every form the lattice is the SMALL image: Ho x Wo of a strided conv, H x W of a transposed conv
     const int Qh = d->transposed ? d->H : Ho, Qw = d->transposed ? d->W : Wo;
     if (d->stride == 2 && ((d->transposed ? Ho : d->H) % 2 != 0 || (d->transposed ? Wo : d->W) % 2 != 0)) return 0;
@@ -1647,7 +1745,7 @@ extern "C" int shm_conv2d_tc_route(const shm_conv_desc* d, int pass) {
     }
     if (pass == 0) {
         if (!d->transposed) {
-            if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s)) return 1;
+            if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s) || thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s)) return 1;
             if (big_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s)) return 2;
             return 0;
         }
@@ -1663,9 +1761,19 @@ extern "C" int shm_conv2d_tc_route(const shm_conv_desc* d, int pass) {
 }
 
 // forward: Conv2D (gather form) or Conv2DTranspose (scatter-by-parity form, 4 launches)
+static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream);
 extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, void* stream) {
+    return tc_fwd_impl(d, x, w_tc, bias, y, 0, stream);
+}
+extern "C" int shm_conv2d_tc_fwd_cols(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream) {
+    SHM_REQUIRE(d && nstore > 0 && nstore <= d->Cout && nstore % 8 == 0, "shm_conv2d_tc_fwd_cols: nstore must be a multiple of 8 in (0, Cout]");
+    return tc_fwd_impl(d, x, w_tc, bias, y, nstore, stream);
+}
+static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream) {
     if (int rc = tc_check(d)) return rc;
     SHM_REQUIRE(x && w_tc && y, "shm_conv2d_tc_fwd: NULL buffer");
+    if (nstore > 0 && nstore < d->Cout && !(d->transposed && d->stride == 2 && scatter_ok(d->H, d->W, d->Cin, d->Cout)))
+        SHM_FAIL(SHM_EUNSUPPORTED, "shm_conv2d_tc_fwd_cols: partial column stores are served by the Conv2DTranspose scatter kernel only");
     SHM_REQUIRE((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "shm_conv2d_tc_fwd: bias must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int Ho, Wo; out_dims(d, Ho, Wo);
@@ -1677,8 +1785,9 @@ extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const vo
         int nt = 0;
         for (int ky = 0; ky < d->kh; ++ky)
             for (int kx = 0; kx < d->kw; ++kx) { tdy[nt] = ky - pby; tdx[nt] = kx - pbx; twr[nt] = (ky * d->kw + kx) * d->Cout; ++nt; }
-        if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
+        if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s) || thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
             return launch_halo(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st);
+        if (d->Cin % 64 != 0 || d->Cout % 64 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc fwd: thin layer %d -> %d not servable", d->Cin, d->Cout);
         if (big_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
             return launch_big(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st);
         Geometry g{d->H, d->W, d->ldx, d->Cin, Ho, Wo, s, Ho, Wo, d->ldy, d->Cout, 1};
@@ -1698,8 +1807,9 @@ extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const vo
                     taps[n++] = ScatterTap{ry, rx, oy, ox, (ky * d->kw + kx) * d->Cout};
                 }
             }
-        if (fits) return launch_scatter(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, Ho, Wo, d->ldy, taps, n, st);
+        if (fits) return launch_scatter(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, Ho, Wo, d->ldy, taps, n, st, nstore);
     }
+    if (nstore > 0 && nstore < d->Cout) SHM_FAIL(SHM_EUNSUPPORTED, "shm_conv2d_tc_fwd_cols: this transposed conv does not fit the scatter kernel");
     for (int ry = 0; ry < s; ++ry)
         for (int rx = 0; rx < s; ++rx) {
             int nt = 0;
@@ -1721,6 +1831,7 @@ extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const vo
 extern "C" int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const void* w_tc, void* dx, void* stream) {
     if (int rc = tc_check(d)) return rc;
     SHM_REQUIRE(dy && w_tc && dx, "shm_conv2d_tc_dgrad: NULL buffer");
+    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc dgrad: thin layers (%d -> %d) are forward-only", d->Cin, d->Cout);
     cudaStream_t st = (cudaStream_t)stream;
     int Ho, Wo; out_dims(d, Ho, Wo);
     const int s = d->stride;
@@ -1776,6 +1887,7 @@ extern "C" int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const
 extern "C" int shm_conv2d_tc_wgrad(const shm_conv_desc* d, const void* x, const void* dy, float* dw, void* stream) {
     if (int rc = tc_check(d)) return rc;
     SHM_REQUIRE(x && dy && dw, "shm_conv2d_tc_wgrad: NULL buffer");
+    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc wgrad: thin layers (%d -> %d) are forward-only", d->Cin, d->Cout);
     cudaStream_t st = (cudaStream_t)stream;
     int Ho, Wo; out_dims(d, Ho, Wo);
     const int s = d->stride;

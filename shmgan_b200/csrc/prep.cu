@@ -162,10 +162,11 @@ __global__ void assemble_kernel(AsmSrc s, int onehot, T* __restrict__ out, long 
 }
 
 // bf16 rows of 64 channels (the zero-padded tensor-core input): 8 threads per pixel, one 16-byte store each
-__global__ void assemble64_kernel(AsmSrc s, int onehot, uint4* __restrict__ out, long long npix) {
-    const long long total = npix * 8;
+// (parts = 8; parts = 2 serves the 16-channel rows of the thin first layer)
+__global__ void assemble64_kernel(AsmSrc s, int onehot, uint4* __restrict__ out, long long npix, int parts) {
+    const long long total = npix * parts;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i >> 3; const int part = (int)(i & 7);
+        const long long p = i / parts; const int part = (int)(i - p * parts);
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
         if (part < 2) {
             float v[8];
@@ -185,10 +186,10 @@ __global__ void assemble64_kernel(AsmSrc s, int onehot, uint4* __restrict__ out,
 
 // dst[p, 0..C) = src[p, 0..C), dst[p, C..64) = 0: the zero-padded input of a tensor-core first layer
 template <typename S>
-__global__ void pad64_kernel(const S* __restrict__ src, int lds, int C, uint4* __restrict__ out, long long npix) {
-    const long long total = npix * 8;
+__global__ void pad64_kernel(const S* __restrict__ src, int lds, int C, uint4* __restrict__ out, long long npix, int parts) {
+    const long long total = npix * parts;                  // parts = padded width / 8 (8 for 64 channels, 4 for 32, 2 for 16)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long p = i >> 3; const int part = (int)(i & 7);
+        const long long p = i / parts; const int part = (int)(i - p * parts);
         uint4 u = make_uint4(0u, 0u, 0u, 0u);
         if (part * 8 < C) {
             float v[8];
@@ -378,8 +379,8 @@ extern "C" int shm_assemble_input(const float* const src[5], const int32_t src_l
     SHM_REQUIRE(src && src_ld && out && npix > 0 && onehot >= 0 && onehot < 5 && ldo >= 10, "shm_assemble_input: bad args");
     AsmSrc s;
     for (int j = 0; j < 5; ++j) { s.p[j] = src[j]; s.ld[j] = src_ld[j]; }
-    if (dtype == SHM_BF16 && ldo == 64 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-        assemble64_kernel<<<flat_grid(npix * 8), 256, 0, (cudaStream_t)stream>>>(s, onehot, (uint4*)out, npix);
+    if (dtype == SHM_BF16 && (ldo == 64 || ldo == 16) && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        assemble64_kernel<<<flat_grid(npix * (ldo / 8)), 256, 0, (cudaStream_t)stream>>>(s, onehot, (uint4*)out, npix, ldo / 8);
         SHM_CHECK_LAUNCH("assemble64_kernel");
         return SHM_OK;
     }
@@ -394,9 +395,22 @@ extern "C" int shm_pad_channels64(const void* src, int src_dtype, int lds, int C
     SHM_REQUIRE(src && dst_bf16 && npix > 0 && C >= 1 && C <= 64 && lds >= C, "shm_pad_channels64: bad args (1 <= C <= 64)");
     SHM_REQUIRE((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0, "shm_pad_channels64: dst must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    if (src_dtype == SHM_F32) pad64_kernel<float><<<flat_grid(npix * 8), 256, 0, st>>>((const float*)src, lds, C, (uint4*)dst_bf16, npix);
-    else if (src_dtype == SHM_BF16) pad64_kernel<bf16><<<flat_grid(npix * 8), 256, 0, st>>>((const bf16*)src, lds, C, (uint4*)dst_bf16, npix);
+    if (src_dtype == SHM_F32) pad64_kernel<float><<<flat_grid(npix * 8), 256, 0, st>>>((const float*)src, lds, C, (uint4*)dst_bf16, npix, 8);
+    else if (src_dtype == SHM_BF16) pad64_kernel<bf16><<<flat_grid(npix * 8), 256, 0, st>>>((const bf16*)src, lds, C, (uint4*)dst_bf16, npix, 8);
     else SHM_FAIL(SHM_EINVAL, "shm_pad_channels64: bad dtype %d", src_dtype);
+    SHM_CHECK_LAUNCH("pad64_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_pad_channels(const void* src, int src_dtype, int lds, int C, void* dst_bf16, int Cpad, int64_t npix, void* stream) {
+    SHM_REQUIRE(src && dst_bf16 && npix >= 0 && C >= 1 && (Cpad == 16 || Cpad == 32 || Cpad == 64) && C <= Cpad && lds >= C, "shm_pad_channels: bad args (Cpad in {16, 32, 64})");
+    if (npix == 0) return SHM_OK;
+    SHM_REQUIRE((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0, "shm_pad_channels: dst must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int parts = Cpad / 8;
+    if (src_dtype == SHM_F32) pad64_kernel<float><<<flat_grid(npix * parts), 256, 0, st>>>((const float*)src, lds, C, (uint4*)dst_bf16, npix, parts);
+    else if (src_dtype == SHM_BF16) pad64_kernel<bf16><<<flat_grid(npix * parts), 256, 0, st>>>((const bf16*)src, lds, C, (uint4*)dst_bf16, npix, parts);
+    else SHM_FAIL(SHM_EINVAL, "shm_pad_channels: bad dtype %d", src_dtype);
     SHM_CHECK_LAUNCH("pad64_kernel");
     return SHM_OK;
 }

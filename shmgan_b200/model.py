@@ -444,8 +444,8 @@ class ShmGANwithSSpecSeg:
         yuv = ops.yuv_standardize(rgb)[0]
         mask = self.SpecSeg.net.predict(self._y_plane(yuv, dt))
         self.specular_candidate = _f32(mask)
-        attn = G.attention(mask)[0] if self.live_mask else None
-        gin = ops.new((B, S, S, G.in_channels(B, S, S)), dt)
+        attn = G.attention(mask, infer=True)[0] if self.live_mask else None
+        gin = ops.new((B, S, S, G.in_channels(B, S, S, infer=True)), dt)
         ops.assemble_input([yuv, None, None, None, None], [3, 0, 0, 0, 0], 4, gin)                   # test.py:227-235
         self.gen_Y = _f32(G.forward(gin, attn))
         cbcr = ops.new((B, S, S, 2), torch.float32)
@@ -455,7 +455,7 @@ class ShmGANwithSSpecSeg:
         if cyclic:                                          # test.py:252-284 (Q11: the R channel stands in for Y)
             R = ops.new((B, S, S, 1), torch.float32)
             ops.cast_into(self.gen_rgb[..., 0:1], R)
-            cin = ops.new((5 * B, S, S, G.in_channels(5 * B, S, S)), dt)
+            cin = ops.new((5 * B, S, S, G.in_channels(5 * B, S, S, infer=True)), dt)
             for k in range(5):
                 srcs = [None if j == k else R for j in range(5)]
                 ops.assemble_input(srcs, [1] * 5, k, cin[k * B:(k + 1) * B])

@@ -246,28 +246,48 @@ class Generator:
             self.dec.append((_CLI(s, f"dec{u}a", 2 * N, N), _CLI(s, f"dec{u}b", N, N)))
             cin = N
         self.out = s.bind(Conv("out", 1, 1, cin, 1))
+        # forward-only (inference) twins of the few-channel first layers on the THIN halo kernel: the 10-channel input / 1-channel mask
+        # padded to 16 channels (32-byte pixel rows) instead of 64 -- a quarter of the bytes and of the MMAs.  Training keeps the
+        # 64-channel form because its weight-gradient kernels read the same padded tensor.
+        self.thin = {}
         if self.pad_in:
             s.pad(self.enc[0][0].conv)
             for ca, _ in self.attn:
                 s.pad(ca)
+            if filter_size == 64:
+                P = ops.PaddedConv
+                self.thin["enc1a"] = s.bind(P("enc1a", 3, 3, 10, 64, 10, 1, act=ACT_LRELU, seg_pad=16, cout_dev=64))
+                if live_mask:
+                    self.thin["attn1a"] = s.bind(P("attn1a", 3, 3, 1, 64, 1, 1, act=ACT_LRELU, seg_pad=16, cout_dev=64))
+                    self.thin["attn2a"] = s.bind(P("attn2a", 3, 3, 1, 128, 1, 1, act=ACT_LRELU, seg_pad=16, cout_dev=128))
 
     # -- helpers -----------------------------------------------------------------------------------
-    def in_channels(self, n, h, w) -> int:
-        """Channel count of the input buffer forward() wants for an [n,h,w] batch: 64 (zero-padded, tensor-core first layer)
-        when that form can serve the shape, else the plain 10."""
+    def in_channels(self, n, h, w, infer: bool = False) -> int:
+        """Channel count of the input buffer forward() wants for an [n,h,w] batch: 16 (thin first layer, forward-only passes),
+        64 (zero-padded, tensor-core first layer) when that form can serve the shape, else the plain 10."""
+        if infer and "enc1a" in self.thin and self.thin["enc1a"].servable(n, h, w):
+            return 16
         return 64 if (self.pad_in and self.enc[0][0].conv.can_pad(n, h, w)) else 10
 
     def _conv(self, c: Conv, x, y=None):
         return c.fwd(x, y, self.tc, self.store.version)
 
-    def attention(self, mask: torch.Tensor):
+    def attention(self, mask: torch.Tensor, infer: bool = False):
         """attention_layer on a live mask: level 1 un-pooled, then MaxPool2 chain; 2 x [Conv3x3 + LeakyReLU] per level.
-        Returns (features, saved) ; computed ONCE per step and shared by every generator pass."""
+        Returns (features, saved) ; computed ONCE per step and shared by every generator pass.  infer: no backward will follow
+        (the first conv of levels 1-2 then runs on the thin kernel)."""
         feats, saved, pooled = [], [], ops.cast(mask, self.dtype) if mask.dtype != self.dtype else mask
         for lvl in range(4):
             if lvl > 0:
                 pooled = ops.maxpool(pooled, 2)
             ca, cb = self.attn[lvl]
+            thin = self.thin.get("attn%da" % (lvl + 1)) if infer else None
+            if thin is not None and thin.servable(*pooled.shape[:3]):
+                a1 = thin.fwd(ops.pad_channels(pooled, 16), None, True, self.store.version)
+                a2 = self._conv(cb, a1)
+                feats.append(a2)
+                saved.append((None, a1, a2))
+                continue
             pin = ops.pad64(pooled) if (self.pad_in and ca.can_pad(*pooled.shape[:3])) else pooled
             a1 = self._conv(ca, pin)
             a2 = self._conv(cb, a1)
@@ -292,12 +312,16 @@ class Generator:
         B, S = x.shape[0], x.shape[1]
         if x.shape[-1] == 10 and self.in_channels(B, S, x.shape[2]) == 64:
             x = ops.pad64(x)
+        assert x.shape[-1] != 16 or (not save and "enc1a" in self.thin), "the 16-channel input form is forward-only"
         tape = {"x": x, "enc": [], "dec": [], "bott": []} if save else None
         h, cats = x, []
         for lvl in range(4):
             a, b = self.enc[lvl]
             C = a.conv.cout
-            za = self._conv(a.conv, h)
+            if lvl == 0 and x.shape[-1] == 16:
+                za = self.thin["enc1a"].fwd(h, None, True, self.store.version)
+            else:
+                za = self._conv(a.conv, h)
             sa = ops.inorm_stats(za)
             ya, _ = ops.inorm_apply(za, sa, a.gamma, a.beta)
             zb = self._conv(b.conv, ya)
@@ -522,14 +546,20 @@ class SpecSegNet:
         self.padded = None
         if tensor_core and dtype == torch.bfloat16:
             P = ops.PaddedConv
+            # thin geometry: 16- / 32-channel tensors stay 16 / 32 wide (32- / 64-byte pixel rows in the halo kernel); only the two
+            # transposed convs run with 64 padded output columns and store the real ones (nstore) into the [up | skip] concat buffer
             self.padded = {
-                "c1a": s.bind(P("c1a", 3, 3, 1, 16, 1, 1)), "c1b": s.bind(P("c1b", 3, 3, 16, 16, 16, 1)),
-                "c2a": s.bind(P("c2a", 3, 3, 16, 32, 16, 1)), "c2b": s.bind(P("c2b", 3, 3, 32, 32, 32, 1)),
-                "c3a": s.bind(P("c3a", 3, 3, 32, 64, 32, 1)),
-                "u8": s.bind(P("u8", 2, 2, 64, 32, 64, 1, stride=2, transposed=True, act=ACT_NONE)),
-                "c8a": s.bind(P("c8a", 3, 3, 64, 32, 32, 2)), "c8b": s.bind(P("c8b", 3, 3, 32, 32, 32, 1)),
-                "u9": s.bind(P("u9", 2, 2, 32, 16, 32, 1, stride=2, transposed=True, act=ACT_NONE)),
-                "c9a": s.bind(P("c9a", 3, 3, 32, 16, 16, 2)), "c9b": s.bind(P("c9b", 3, 3, 16, 16, 16, 1)),
+                "c1a": s.bind(P("c1a", 3, 3, 1, 16, 1, 1, seg_pad=16, cout_dev=16)),
+                "c1b": s.bind(P("c1b", 3, 3, 16, 16, 16, 1, seg_pad=16, cout_dev=16)),
+                "c2a": s.bind(P("c2a", 3, 3, 16, 32, 16, 1, seg_pad=16, cout_dev=32)),
+                "c2b": s.bind(P("c2b", 3, 3, 32, 32, 32, 1, seg_pad=32, cout_dev=32)),
+                "c3a": s.bind(P("c3a", 3, 3, 32, 64, 32, 1, seg_pad=32, cout_dev=64)),
+                "u8": s.bind(P("u8", 2, 2, 64, 32, 64, 1, stride=2, transposed=True, act=ACT_NONE, nstore=32)),
+                "c8a": s.bind(P("c8a", 3, 3, 64, 32, 64, 1, seg_pad=64, cout_dev=32)),
+                "c8b": s.bind(P("c8b", 3, 3, 32, 32, 32, 1, seg_pad=32, cout_dev=64)),       # 64 columns (32 zero): u9 reads 64-channel rows
+                "u9": s.bind(P("u9", 2, 2, 32, 16, 32, 1, stride=2, transposed=True, act=ACT_NONE, nstore=16)),
+                "c9a": s.bind(P("c9a", 3, 3, 32, 16, 32, 1, seg_pad=32, cout_dev=16)),
+                "c9b": s.bind(P("c9b", 3, 3, 16, 16, 16, 1, seg_pad=16, cout_dev=16)),
             }
         self._zbuf = {}
 
@@ -578,15 +608,15 @@ class SpecSegNet:
         v, sv, P = self.store.version, self.store.views, self.padded
         B, H, W = x.shape[:3]
         bn = lambda i: (sv[f"bn{i}.gamma"], sv[f"bn{i}.beta"], sv[f"bn{i}.mean"], sv[f"bn{i}.var"])
-        # level 1 (16 real channels) and level 2 (32): 64-wide tensors; skips land in the upper half of 128-wide concat buffers
-        cat9 = self._zeros("cat9", (B, H, W, 128))
-        cat8 = self._zeros("cat8", (B, H // 2, W // 2, 128))
-        p1 = self._zeros("p1", (B, H // 2, W // 2, 64))
-        p2 = self._zeros("p2", (B, H // 4, W // 4, 64))
-        h = P["c1b"].fwd(P["c1a"].fwd(ops.pad64(x), None, True, v), None, True, v)
-        ops.bn_eval(h[..., :16], *bn(1), out=cat9[..., 64:80], pooled=p1[..., :16])
+        # level 1 (16 channels) and level 2 (32): thin tensors; skips land in the upper half of the [up | skip] concat buffers
+        cat9 = ops.new((B, H, W, 32), self.dtype)
+        cat8 = ops.new((B, H // 2, W // 2, 64), self.dtype)
+        p1 = ops.new((B, H // 2, W // 2, 16), self.dtype)
+        p2 = ops.new((B, H // 4, W // 4, 32), self.dtype)
+        h = P["c1b"].fwd(P["c1a"].fwd(ops.pad_channels(x, 16), None, True, v), None, True, v)
+        ops.bn_eval(h, *bn(1), out=cat9[..., 16:32], pooled=p1)
         h = P["c2b"].fwd(P["c2a"].fwd(p1, None, True, v), None, True, v)
-        ops.bn_eval(h[..., :32], *bn(2), out=cat8[..., 64:96], pooled=p2[..., :32])
+        ops.bn_eval(h, *bn(2), out=cat8[..., 32:64], pooled=p2)
         h = P["c3a"].fwd(p2, None, True, v)
         cats = []
         for ca, cb, i in self.enc[2:]:
@@ -604,8 +634,8 @@ class SpecSegNet:
             c = up.cout
             up.fwd(h, cat[..., :c], True, v)
             h = cb.fwd(ca.fwd(cat, None, True, v), None, True, v)
-        P["u8"].fwd(h, cat8[..., :64], True, v)
+        P["u8"].fwd(h, cat8[..., :32], True, v)
         h = P["c8b"].fwd(P["c8a"].fwd(cat8, None, True, v), None, True, v)
-        P["u9"].fwd(h, cat9[..., :64], True, v)
+        P["u9"].fwd(h, cat9[..., :16], True, v)
         h = P["c9b"].fwd(P["c9a"].fwd(cat9, None, True, v), None, True, v)
-        return self.out.fwd(h[..., :16], None, True, v)
+        return self.out.fwd(h, None, True, v)

@@ -296,11 +296,16 @@ class PaddedConv(Conv):
     go through the halo tcgen05 kernel instead of the exact-fp32 SIMT kernel (6.9 ms -> < 1 ms per step for the mask network).
     The padded output channels are exactly zero after ReLU / LeakyReLU / no activation (zero weights, zero bias)."""
 
-    def __init__(self, name, kh, kw, cin, cout, seg_real, nseg, stride=1, transposed=False, act=ACT_RELU, bias=True):
+    def __init__(self, name, kh, kw, cin, cout, seg_real, nseg, stride=1, transposed=False, act=ACT_RELU, bias=True,
+                 seg_pad=64, cout_dev=None, nstore=None):
+        """seg_pad / cout_dev below 64 select the THIN halo kernel (32- / 64-byte pixel rows, 16 / 32 output columns) for stride-1
+        3x3 layers; nstore (transposed layers) = output channels actually stored (the rest of the cout_dev columns are padding)."""
         super().__init__(name, kh, kw, cin, cout, stride=stride, transposed=transposed, act=act, bias=bias)
-        assert seg_real * nseg == cin and act != ACT_SIGMOID
-        self.seg_real, self.nseg = seg_real, nseg
-        self.cin_dev, self.cout_dev = 64 * nseg, max(64, cout)
+        assert seg_real * nseg == cin and act != ACT_SIGMOID and seg_pad >= seg_real
+        self.seg_real, self.nseg, self.seg_pad = seg_real, nseg, seg_pad
+        self.cin_dev, self.cout_dev = seg_pad * nseg, (max(64, cout) if cout_dev is None else cout_dev)
+        assert self.cout_dev >= cout
+        self.nstore = nstore
         self.b_dev = None
 
     def refresh_tc(self, version: int):
@@ -311,7 +316,7 @@ class PaddedConv(Conv):
         if self.w_tc is None:
             self.w_tc = new((self.kh * self.kw * self.cin_dev * self.cout_dev,), torch.bfloat16)
             self.b_dev = torch.zeros((self.cout_dev,), dtype=torch.float32, device=self.w.device)
-        call("shm_conv2d_tc_prep_weights_padded", C.byref(d), _p(self.w), self.cin, self.seg_real, 64, self.cout, _p(self.w_tc), _stream())
+        call("shm_conv2d_tc_prep_weights_padded", C.byref(d), _p(self.w), self.cin, self.seg_real, self.seg_pad, self.cout, _p(self.w_tc), _stream())
         if self.has_bias:
             call("shm_cast", _p(self.b), F32, _p(self.b_dev), F32, self.cout, _stream())
         self.tc_version = version
@@ -327,13 +332,17 @@ class PaddedConv(Conv):
         n, h, w, cx = x.shape
         assert tc and x.dtype == torch.bfloat16 and cx == self.cin_dev, (self.name, tuple(x.shape))
         ho, wo = self.out_hw(h, w)
+        nst = self.nstore or self.cout_dev
         if y is None:
-            y = new((n, ho, wo, self.cout_dev), x.dtype)
-        assert y.shape[-1] == self.cout_dev
+            y = new((n, ho, wo, nst), x.dtype)
+        assert y.shape[-1] == nst
         self.refresh_tc(version)
         d = self.dev_desc(n, h, w, ld(x), ld(y))
-        fl, nb = self.flops(n, h, w), x.element_size() * n * (h * w * self.cin_dev + ho * wo * self.cout_dev)
-        _prof(_route(d, 0), "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b_dev), _p(y), _stream()))
+        fl, nb = self.flops(n, h, w), x.element_size() * n * (h * w * self.cin_dev + ho * wo * nst)
+        if nst != self.cout_dev:
+            _prof(_route(d, 0), "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd_cols", C.byref(d), _p(x), _p(self.w_tc), _p(self.b_dev), _p(y), nst, _stream()))
+        else:
+            _prof(_route(d, 0), "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd", C.byref(d), _p(x), _p(self.w_tc), _p(self.b_dev), _p(y), _stream()))
         return y
 
 
@@ -541,6 +550,16 @@ def pad64(src, out=None):
         out = new((n, h, w, 64), torch.bfloat16)
     assert out.is_contiguous() and out.shape[-1] == 64 and out.dtype == torch.bfloat16
     call("shm_pad_channels64", _p(src), dt(src), ld(src), c, _p(out), n * h * w, _stream())
+    return out
+
+
+def pad_channels(src, cpad: int, out=None):
+    """[N,H,W,C] (C <= cpad in {16, 32, 64}) -> dense bf16 [N,H,W,cpad] with channels C.. zero (inputs of the thin tensor-core layers)."""
+    n, h, w, c = src.shape
+    if out is None:
+        out = new((n, h, w, cpad), torch.bfloat16)
+    assert out.is_contiguous() and out.shape[-1] == cpad and out.dtype == torch.bfloat16
+    call("shm_pad_channels", _p(src), dt(src), ld(src), c, _p(out), cpad, n * h * w, _stream())
     return out
 
 

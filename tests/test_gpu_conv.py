@@ -238,3 +238,63 @@ def test_conv_tc_matches_simt_bf16_inputs():
     y_tc = c.fwd(xd, tc=True, version=1).float()
     y_simt = c.fwd(xd, tc=False).float()
     assert rel_err(y_tc, y_simt) < 1e-2
+
+
+# ---- thin layers: fewer than 64 reduction / output channels through the halo kernel with 32- / 64-byte pixel rows -----------------
+# (N, H, W, cin, cout, seg_pad, cout_dev, act)
+THIN_CASES = [
+    (2, 32, 32, 1, 16, 16, 16, 2),        # SpecSeg c1a: 1 -> 16 (SWIZZLE_32B rows, 16 accumulator columns)
+    (3, 16, 24, 16, 16, 16, 16, 2),       # c1b / c9b
+    (2, 32, 16, 16, 32, 16, 32, 2),       # c2a
+    (2, 16, 16, 32, 32, 32, 32, 2),       # c2b (SWIZZLE_64B rows)
+    (2, 32, 32, 32, 64, 32, 64, 2),       # c3a
+    (2, 16, 32, 32, 16, 32, 16, 2),       # c9a on the [up16 | skip16] concat
+    (2, 32, 32, 64, 32, 64, 32, 2),       # c8a on the [up32 | skip32] concat (128-byte rows, 32 columns)
+    (1, 48, 40, 64, 16, 64, 16, 1),       # 64 -> 16
+    (2, 32, 32, 10, 64, 16, 64, 1),       # generator enc1a: 10 -> 64 with the input padded to 16
+    (2, 16, 16, 1, 128, 16, 128, 1),      # attention first conv 1 -> 128
+    (40, 32, 32, 16, 16, 16, 16, 2),      # 320 tiles: persistent loop, ring wrap, accumulator double buffering
+    (2, 32, 32, 32, 32, 32, 64, 2),       # c8b: 32 real output channels in 64 columns
+]
+
+
+@pytest.mark.parametrize("case", THIN_CASES)
+def test_conv_tc_thin_layers(case):
+    from shmgan_b200 import ops
+    N, H, W, cin, cout, seg_pad, cout_dev, act = case
+    x = bf16_round(randn((N, H, W, cin), 31))
+    w = bf16_round(randn((3, 3, cin, cout), 32, 0.1))
+    b = randn((cout,), 33, 0.1).float().to(F64)
+    want = oracle_conv(x, w, b, 1, False, act)
+    c = ops.PaddedConv("thin", 3, 3, cin, cout, cin, 1, act=act, seg_pad=seg_pad, cout_dev=cout_dev)
+    c.w, c.b = dev(w), dev(b)
+    assert c.servable(N, H, W)
+    xd = ops.pad_channels(dev(x, torch.bfloat16), seg_pad) if cin != seg_pad else dev(x, torch.bfloat16)
+    y = c.fwd(xd, None, True, 1)
+    assert y.shape == (N, H, W, cout_dev) and y.dtype == torch.bfloat16
+    assert rel_err(y[..., :cout], want) < BF16_TOL
+    if cout_dev > cout:
+        assert float(y[..., cout:].float().abs().max()) == 0.0
+    # output placed into a channel slice of a wider buffer (concat placement)
+    wide = torch.full((N, H, W, cout_dev + 16), 7.0, dtype=torch.bfloat16, device="cuda")
+    c.fwd(xd, wide[..., 16:], True, 1)
+    assert torch.equal(wide[..., 16:], y) and float((wide[..., :16].float() - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("cin,cout,k", [(64, 32, 2), (32, 16, 2), (64, 16, 3)])
+def test_conv_transpose_partial_column_store(cin, cout, k):
+    """Conv2DTranspose whose real output channels (32 / 16) sit in 64 accumulator columns: only the real ones are stored, into the
+    [up | skip] concat buffer, and the skip half is untouched (SpecSeg.py:68,78)."""
+    from shmgan_b200 import ops
+    N, H, W = 3, 16, 24
+    x = bf16_round(randn((N, H, W, cin), 41))
+    w = bf16_round(randn((k, k, cout, cin), 42, 0.1))
+    b = randn((cout,), 43, 0.1).float().to(F64)
+    want = oracle_conv(x, w, b, 2, True, 0)
+    c = ops.PaddedConv("up", k, k, cin, cout, cin, 1, stride=2, transposed=True, act=0, nstore=cout)
+    c.w, c.b = dev(w), dev(b)
+    xd = ops.pad64(dev(x, torch.bfloat16)) if cin < 64 else dev(x, torch.bfloat16)
+    cat = torch.full((N, 2 * H, 2 * W, 2 * cout), 3.0, dtype=torch.bfloat16, device="cuda")
+    c.fwd(xd, cat[..., :cout], True, 1)
+    assert rel_err(cat[..., :cout], want) < BF16_TOL
+    assert float((cat[..., cout:].float() - 3.0).abs().max()) == 0.0

@@ -185,7 +185,7 @@ def test_specseg_predict(dtype, tol):
 
 
 def test_specseg_padded_tensor_core_path():
-    """The 16/32-channel SpecSeg levels in the zero-padded 64-channel geometry (every layer on the tcgen05 kernels) vs the
+    """The 16/32-channel SpecSeg levels in the thin tensor-core geometry (32- / 64-byte pixel rows; every layer on the tcgen05 kernels) vs the
     oracle, and vs the mixed SIMT/tensor-core path on the same weights: same bf16 arithmetic, so the two device paths agree
     to bf16 rounding and the binarised masks agree >= 99.9 %."""
     from shmgan_b200 import nets
@@ -209,5 +209,4 @@ def test_specseg_padded_tensor_core_path():
     net.padded = padded
     assert rel_err(got, ref) < 2e-2
     assert float(((got > 0.5) == (ref > 0.5)).double().mean()) >= 0.999
-    # the padding channels of the cached concat buffers were never written
-    assert float(net._zbuf["cat9"][..., 80:].float().abs().max()) == 0.0 and float(net._zbuf["cat9"][..., 16:64].float().abs().max()) == 0.0
+
