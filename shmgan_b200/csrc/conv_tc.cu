@@ -176,25 +176,36 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t* r) {
           "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
         :: "memory");
 }
-// bias + activation + bf16 + 32 contiguous bytes for 16 accumulator columns
-__device__ __forceinline__ void epi_store16(const uint32_t* r, const float* sbias, int act, bf16* __restrict__ dst) {
-    float v[16];
+// bias + activation + bf16 of NV accumulator columns -> NV / 8 packed 16-byte chunks (registers)
+template <int NV>
+__device__ __forceinline__ void epi_pack(const uint32_t* r, const float* sbias, int act, uint4* out) {
+    float v[NV];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) + (sbias ? sbias[j] : 0.f);
+    for (int j = 0; j < NV; ++j) v[j] = __uint_as_float(r[j]);
+    if (sbias != nullptr) {
+        const float4* b4 = reinterpret_cast<const float4*>(sbias);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        if (act == SHM_ACT_LRELU) v[j] = fmaxf(v[j], 0.2f * v[j]);
-        else if (act == SHM_ACT_RELU) v[j] = fmaxf(v[j], 0.f);
-        else if (act == SHM_ACT_SIGMOID) v[j] = 1.f / (1.f + __expf(-v[j]));
+        for (int j = 0; j < NV / 4; ++j) {
+            const float4 b = b4[j];
+            v[4 * j] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+    }
+    if (act == SHM_ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+    } else if (act == SHM_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == SHM_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
     }
 #pragma unroll
-    for (int j = 0; j < 16; j += 8) {
-        uint4 u;
+    for (int j = 0; j < NV; j += 8) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(v[j], v[j + 1]), h1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
         __nv_bfloat162 h2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), h3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-        u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
-        *reinterpret_cast<uint4*>(dst + j) = u;
+        out[j / 8] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
     }
 }
 
@@ -433,24 +444,42 @@ struct HaloParams {
 // (SpecSeg.py:34-44, :76-86), the 1-channel mask inputs of the attention branches (ShmGANwithSSpecSeg.py:404-412) and the
 // 10-channel generator input (:243) -- which otherwise run zero-padded to 64 channels (4x the bytes, up to 16x the MMAs).
 // The shifted-descriptor trick is unchanged: the swizzle is a function of absolute shared-memory address bits in every mode.
-template <int KC, int BN, int CPX = 128>
+// T = 16 x 8 sub-tiles stacked vertically in one work item (one (16 T + 2) x 10 halo box, T accumulators, one epilogue pass over
+// T x BN columns).  A thin tile has 9-18 MMAs of 8-16 cycles against ~1000 cycles of fixed per-tile latency (barrier round trips,
+// tcgen05.ld, commit): with T = 1 the thin layers ran at 1.8-2.7 TB/s; T = 4 amortises that latency over 512 pixels.
+template <int KC, int BN, int CPX = 128, int T = 1>
 struct HaloCfg {
     static_assert(CPX == 128 || KC == 1, "thin rows hold the whole reduction dimension");
+    static_assert(2 * T * BN <= 512, "accumulators exceed TMEM");
     static constexpr int W_TILE = BN * CPX;                       // one tap, one k-chunk
     static constexpr int W_BYTES = 9 * KC * W_TILE;
     static constexpr int W_SPACE = (W_BYTES + 1023) / 1024 * 1024;
-    static constexpr int A_BYTES = HALO_W * HALO_H * CPX;
+    static constexpr int A_BYTES = HALO_W * (16 * T + 2) * CPX;
     static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
-    static constexpr int STAGES = (W_BYTES <= 73728) ? 6 : 3;
-    static constexpr int SMEM = W_SPACE + STAGES * A_STAGE + 1024 + 256 + BIAS_SMEM;
-    static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+    // Coalesced epilogue (BN <= 64, one k-chunk): a thread owns one pixel row of the accumulator, so direct stores put the 32 lanes
+    // of every STG.128 on 32 different 128-byte lines (32 L1 wavefronts per instruction: ~1000 cycles per 128 x 64 tile, which
+    // bounded the 64-column layers).  Each epilogue warp instead stages its 32 rows in shared memory and writes them back with
+    // 2 BN / 16 lanes per pixel, i.e. whole lines per instruction.
+    // Measured (64 x 512 x 512, profiles/r01_thin_layers.txt): 64 -> 64 layers 1.32 -> 1.18 ms; the stacked thin layers are bound by the
+    // serial latency of their four epilogue warps instead and lose 10-15 % to the extra smem round trip, so they keep direct stores.
+    static constexpr bool COAL = BN <= 64 && KC == 1 && T == 1 && CPX == 128;
+    static constexpr int STG_PITCH = 2 * BN + 16;                         // bytes per staged row (+16: conflict-free 16-byte columns)
+    static constexpr int STG_WARP = 32 * STG_PITCH;
+    static constexpr int STG_BYTES = COAL ? 4 * STG_WARP : 0;
+    static constexpr int FIXED = 1024 + 256 + BIAS_SMEM + STG_BYTES;
+    static constexpr int FIT = (227 * 1024 - FIXED - W_SPACE) / A_STAGE;  // halo stages that fit beside the resident weights
+    static constexpr int WANT = T > 1 ? 4 : ((W_BYTES <= 73728) ? 6 : 3);
+    static constexpr int STAGES = FIT < WANT ? FIT : WANT;
+    static_assert(STAGES >= 2, "halo kernel shared memory");
+    static constexpr int SMEM = W_SPACE + STAGES * A_STAGE + FIXED;
+    static constexpr int TMEM_COLS = 2 * T * BN < 32 ? 32 : 2 * T * BN;
     static constexpr uint32_t LAYOUT = CPX == 128 ? 2u : (CPX == 64 ? 4u : 6u);
 };
 
-template <int KC, int BN, int CPX = 128>
+template <int KC, int BN, int CPX = 128, int T = 1>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
-    using Cfg = HaloCfg<KC, BN, CPX>;
+    using Cfg = HaloCfg<KC, BN, CPX, T>;
     constexpr int HALO_STAGE = Cfg::A_STAGE;
     constexpr int HALO_BYTES = Cfg::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
@@ -465,6 +494,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     float* sbias = reinterpret_cast<float*>(sA + Cfg::STAGES * HALO_STAGE + 256);
+    uint8_t* sStage = sA + Cfg::STAGES * HALO_STAGE + 256 + BIAS_SMEM;      // [4 epilogue warps][32 rows][STG_PITCH]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_img = p.tiles_x * p.tiles_y;
@@ -496,7 +526,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
                 const int img = tile / per_img; const int r = tile - img * per_img;
-                const int y0 = (r / p.tiles_x) * 16 + p.oy, x0 = (r % p.tiles_x) * 8 + p.ox;
+                const int y0 = (r / p.tiles_x) * (16 * T) + p.oy, x0 = (r % p.tiles_x) * 8 + p.ox;
                 for (int kc = 0; kc < KC; ++kc) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     if (elect_one_sync()) {
@@ -517,19 +547,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int as = local & 1;
             mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + as * BN;
+            const uint32_t d_tmem = tmem_base + as * (T * BN);
             for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(&full[stage], phase);
                 tc_fence_after();
                 const uint32_t a0 = smem_u32(sA + stage * HALO_STAGE);
                 if (elect_one_sync()) {
 #pragma unroll
-                    for (int t = 0; t < 9; ++t) {
-                        const uint64_t adesc = make_desc_swz(a0 + (uint32_t)(p.tdy[t] * HALO_W + p.tdx[t]) * (uint32_t)CPX, 16, HALO_W * CPX, Cfg::LAYOUT);
-                        const uint64_t bdesc = make_desc_swz(smem_u32(sW + (t * KC + kc) * Cfg::W_TILE), 16, 8 * CPX, Cfg::LAYOUT);
+                    for (int j = 0; j < T; ++j) {
 #pragma unroll
-                        for (int k = 0; k < CPX / 32; ++k)
-                            umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+                        for (int t = 0; t < 9; ++t) {
+                            const uint64_t adesc = make_desc_swz(a0 + (uint32_t)((p.tdy[t] + 16 * j) * HALO_W + p.tdx[t]) * (uint32_t)CPX, 16, HALO_W * CPX, Cfg::LAYOUT);
+                            const uint64_t bdesc = make_desc_swz(smem_u32(sW + (t * KC + kc) * Cfg::W_TILE), 16, 8 * CPX, Cfg::LAYOUT);
+#pragma unroll
+                            for (int k = 0; k < CPX / 32; ++k)
+                                umma_bf16(d_tmem + j * BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc | t | k) != 0);
+                        }
                     }
                     umma_commit(&empty[stage]);
                 }
@@ -547,30 +580,79 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
             const int as = local & 1;
             const int img = tile / per_img; const int r = tile - img * per_img;
-            const int oy = (r / p.tiles_x) * 16 + ty, ox = (r % p.tiles_x) * 8 + tx;
-            bf16* dst = p.out + ((long long)(img * p.H + oy) * p.W + ox) * p.ldout;
+            const int y0t = (r / p.tiles_x) * (16 * T), x0t = (r % p.tiles_x) * 8;
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
-            if constexpr (BN == 16) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-                uint32_t r[16];
-                tmem_ld16_nw(taddr, r);
-                tmem_wait_ld16(r);
-                epi_store16(r, p.bias ? sbias : nullptr, p.act, dst);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * (T * BN));
+            if constexpr (Cfg::COAL) {
+                constexpr int CH = BN / 8, RP = 32 / CH;                 // 16-byte chunks per pixel; pixels per store instruction
+                const uint32_t stg = smem_u32(sStage + quad * Cfg::STG_WARP);
+                uint4 pk[T][CH];
+                // all T sub-tiles: TMEM -> registers (loads in flight together), bias / activation / bf16 pack
+                if constexpr (BN == 16) {
+                    uint32_t r16[T][16];
+#pragma unroll
+                    for (int j = 0; j < T; ++j) tmem_ld16_nw(taddr + (uint32_t)(j * BN), r16[j]);
+#pragma unroll
+                    for (int j = 0; j < T; ++j) { tmem_wait_ld16(r16[j]); epi_pack<16>(r16[j], p.bias ? sbias : nullptr, p.act, pk[j]); }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < T; ++j) {
+                        uint32_t r32[BN / 32][32];
+#pragma unroll
+                        for (int c = 0; c < BN / 32; ++c) tmem_ld32_nw(taddr + (uint32_t)(j * BN + c * 32), r32[c]);
+#pragma unroll
+                        for (int c = 0; c < BN / 32; ++c) {
+                            tmem_wait_ld32(r32[c]);
+                            epi_pack<32>(r32[c], p.bias ? sbias + c * 32 : nullptr, p.act, pk[j] + c * 4);
+                        }
+                    }
+                }
+                // the accumulators are in registers: hand the TMEM buffer back before the (slower) store phase
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+#pragma unroll
+                    for (int c = 0; c < CH; ++c)
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * Cfg::STG_PITCH + c * 16),
+                                     "r"(pk[j][c].x), "r"(pk[j][c].y), "r"(pk[j][c].z), "r"(pk[j][c].w) : "memory");
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const int row = i * RP + lane / CH, chunk = lane % CH;
+                        const int rowg = quad * 32 + row;
+                        uint4 u;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                     : "r"(stg + row * Cfg::STG_PITCH + chunk * 16) : "memory");
+                        bf16* g = p.out + ((long long)(img * p.H + y0t + 16 * j + (rowg >> 3)) * p.W + x0t + (rowg & 7)) * p.ldout + chunk * 8;
+                        *reinterpret_cast<uint4*>(g) = u;
+                    }
+                    __syncwarp();
+                }
             } else {
-                constexpr int NC = BN / 32;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-                uint32_t r[NC][32];
+                const int oy = y0t + ty, ox = x0t + tx;
+                bf16* dst = p.out + ((long long)(img * p.H + oy) * p.W + ox) * p.ldout;
+                if constexpr (T > 1) {
+                    const long long rowstep = (long long)16 * p.W * p.ldout;
 #pragma unroll
-                for (int c = 0; c < NC; ++c) tmem_ld32_nw(taddr + (uint32_t)(c * 32), r[c]);
+                    for (int j = 0; j < T; ++j)
+                        epi_row<BN / 32>(taddr + (uint32_t)(j * BN), p.bias ? sbias : nullptr, p.act, dst + j * rowstep, true);
+                } else {
+                    constexpr int NC = BN / 32;
+                    uint32_t r[NC][32];
 #pragma unroll
-                for (int c = 0; c < NC; ++c) tmem_wait_ld32(r[c]);
+                    for (int c = 0; c < NC; ++c) tmem_ld32_nw(taddr + (uint32_t)(c * 32), r[c]);
 #pragma unroll
-                for (int c = 0; c < NC; ++c) epi_store32(r[c], p.bias ? sbias + c * 32 : nullptr, p.act, dst + c * 32, true);
+                    for (int c = 0; c < NC; ++c) tmem_wait_ld32(r[c]);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) epi_store32(r[c], p.bias ? sbias + c * 32 : nullptr, p.act, dst + c * 32, true);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[as]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
         }
     }
     tc_fence_before();
@@ -973,15 +1055,23 @@ bool thin_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
     return false;
 }
 
-template <int KC, int BN, int CPX = 128>
+template <int KC, int BN, int CPX = 128, int T = 1>
 int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloParams& p, cudaStream_t st) {
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<KC, BN, CPX>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<KC, BN, CPX>::SMEM); attr = true; }
+    if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<KC, BN, CPX, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<KC, BN, CPX, T>::SMEM); attr = true; }
     int grid = shm_num_sms();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    conv_halo_kernel<KC, BN, CPX><<<grid, TC_THREADS, HaloCfg<KC, BN, CPX>::SMEM, st>>>(tmA, tmB, p);
+    conv_halo_kernel<KC, BN, CPX, T><<<grid, TC_THREADS, HaloCfg<KC, BN, CPX, T>::SMEM, st>>>(tmA, tmB, p);
     SHM_CHECK_LAUNCH("conv_halo_kernel");
     return SHM_OK;
+}
+// thin layer: stacked sub-tiles per work item when the image height allows it
+template <int BN, int CPX>
+int launch_thin(const CUtensorMap& tmA1, const CUtensorMap& tmAT, const CUtensorMap& tmB, HaloParams& p, bool stack, cudaStream_t st) {
+    constexpr int T = BN <= 64 ? 4 : 2;
+    if (!stack) return launch_halo_t<1, BN, CPX, 1>(tmA1, tmB, p, st);
+    p.tiles_y /= T; p.total_tiles /= T;
+    return launch_halo_t<1, BN, CPX, T>(tmAT, tmB, p, st);
 }
 
 // in: [N,H,W,K] (ld ldin), out: [N,H,W,Nn] (ld ldout); taps (tdy, tdx) in {-1,0,1} with weight rows twrow
@@ -1001,17 +1091,24 @@ int launch_halo(int N, int H, int W, int K, int Nn, const void* in, int ldin, co
     const int inner = K < 64 ? K : 64;
     if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, HALO_H, inner)) return rc;
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, Nn, inner)) return rc;
-    if (K == 16) {
-        if (Nn == 16) return launch_halo_t<1, 16, 32>(tmA, tmB, p, st);
-        if (Nn == 32) return launch_halo_t<1, 32, 32>(tmA, tmB, p, st);
-        if (Nn == 64) return launch_halo_t<1, 64, 32>(tmA, tmB, p, st);
-        if (Nn == 128) return launch_halo_t<1, 128, 32>(tmA, tmB, p, st);
-    } else if (K == 32) {
-        if (Nn == 16) return launch_halo_t<1, 16, 64>(tmA, tmB, p, st);
-        if (Nn == 32) return launch_halo_t<1, 32, 64>(tmA, tmB, p, st);
-        if (Nn == 64) return launch_halo_t<1, 64, 64>(tmA, tmB, p, st);
-    } else if (K == 64 && Nn == 16) return launch_halo_t<1, 16, 128>(tmA, tmB, p, st);
-    else if (K == 64 && Nn == 32) return launch_halo_t<1, 32, 128>(tmA, tmB, p, st);
+    if (K < 64 || Nn < 64) {
+        const int T = Nn <= 64 ? 4 : 2;
+        const bool stack = H % (16 * T) == 0;
+        CUtensorMap tmS = tmA;
+        if (stack) { if (int rc = encode_act_box(&tmS, in, K, W, H, N, ldin, HALO_W, 16 * T + 2, inner)) return rc; }
+        if (K == 16) {
+            if (Nn == 16) return launch_thin<16, 32>(tmA, tmS, tmB, p, stack, st);
+            if (Nn == 32) return launch_thin<32, 32>(tmA, tmS, tmB, p, stack, st);
+            if (Nn == 64) return launch_thin<64, 32>(tmA, tmS, tmB, p, stack, st);
+            if (Nn == 128) return launch_thin<128, 32>(tmA, tmS, tmB, p, stack, st);
+        } else if (K == 32) {
+            if (Nn == 16) return launch_thin<16, 64>(tmA, tmS, tmB, p, stack, st);
+            if (Nn == 32) return launch_thin<32, 64>(tmA, tmS, tmB, p, stack, st);
+            if (Nn == 64) return launch_thin<64, 64>(tmA, tmS, tmB, p, stack, st);
+        } else if (K == 64 && Nn == 16) return launch_thin<16, 128>(tmA, tmS, tmB, p, stack, st);
+        else if (K == 64 && Nn == 32) return launch_thin<32, 128>(tmA, tmS, tmB, p, stack, st);
+        SHM_FAIL(SHM_EUNSUPPORTED, "conv_halo (thin): K=%d Nn=%d", K, Nn);
+    }
     if (K == 64 && Nn == 64) return launch_halo_t<1, 64>(tmA, tmB, p, st);
     if (K == 128 && Nn == 64) return launch_halo_t<2, 64>(tmA, tmB, p, st);
     if (K == 64 && Nn == 128) return launch_halo_t<1, 128>(tmA, tmB, p, st);
