@@ -474,10 +474,14 @@ struct HaloCfg {
     static constexpr int SMEM = W_SPACE + STAGES * A_STAGE + FIXED;
     static constexpr int TMEM_COLS = 2 * T * BN < 32 ? 32 : 2 * T * BN;
     static constexpr uint32_t LAYOUT = CPX == 128 ? 2u : (CPX == 64 ? 4u : 6u);
+    // stacked items: TWO epilogue warps per TMEM lane quadrant (warps 2-5 take the even sub-tiles, 6-9 the odd ones) -- the four-warp
+    // epilogue of a stacked thin item was a serial latency chain (ncu: 0.19 IPC per epilogue warp, tensor pipe 13 % busy)
+    static constexpr int EPI_WARPS = T > 1 ? 8 : 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
 };
 
 template <int KC, int BN, int CPX = 128, int T = 1>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__((HaloCfg<KC, BN, CPX, T>::THREADS), 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
     using Cfg = HaloCfg<KC, BN, CPX, T>;
     constexpr int HALO_STAGE = Cfg::A_STAGE;
@@ -503,7 +507,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], Cfg::EPI_WARPS); }
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
@@ -636,9 +640,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 bf16* dst = p.out + ((long long)(img * p.H + oy) * p.W + ox) * p.ldout;
                 if constexpr (T > 1) {
                     const long long rowstep = (long long)16 * p.W * p.ldout;
+                    const int eg = (warp - 2) >> 2;                   // epilogue warp group: sub-tiles eg, eg + 2, ...
+                    if constexpr (BN == 16) {
+                        uint32_t r16[T / 2][16];
 #pragma unroll
-                    for (int j = 0; j < T; ++j)
-                        epi_row<BN / 32>(taddr + (uint32_t)(j * BN), p.bias ? sbias : nullptr, p.act, dst + j * rowstep, true);
+                        for (int jj = 0; jj < T / 2; ++jj) tmem_ld16_nw(taddr + (uint32_t)((2 * jj + eg) * BN), r16[jj]);
+#pragma unroll
+                        for (int jj = 0; jj < T / 2; ++jj) {
+                            tmem_wait_ld16(r16[jj]);
+                            uint4 pk[2];
+                            epi_pack<16>(r16[jj], p.bias ? sbias : nullptr, p.act, pk);
+                            uint4* g = reinterpret_cast<uint4*>(dst + (2 * jj + eg) * rowstep);
+                            g[0] = pk[0]; g[1] = pk[1];
+                        }
+                    } else {
+#pragma unroll
+                        for (int jj = 0; jj < T / 2; ++jj)
+                            epi_row<BN / 32>(taddr + (uint32_t)((2 * jj + eg) * BN), p.bias ? sbias : nullptr, p.act, dst + (2 * jj + eg) * rowstep, true);
+                    }
+                } else if constexpr (BN == 16) {
+                    uint32_t r16[16];
+                    tmem_ld16_nw(taddr, r16);
+                    tmem_wait_ld16(r16);
+                    uint4 pk[2];
+                    epi_pack<16>(r16, p.bias ? sbias : nullptr, p.act, pk);
+                    uint4* g = reinterpret_cast<uint4*>(dst);
+                    g[0] = pk[0]; g[1] = pk[1];
                 } else {
                     constexpr int NC = BN / 32;
                     uint32_t r[NC][32];
@@ -1061,7 +1088,7 @@ int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloPara
     if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<KC, BN, CPX, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<KC, BN, CPX, T>::SMEM); attr = true; }
     int grid = shm_num_sms();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    conv_halo_kernel<KC, BN, CPX, T><<<grid, TC_THREADS, HaloCfg<KC, BN, CPX, T>::SMEM, st>>>(tmA, tmB, p);
+    conv_halo_kernel<KC, BN, CPX, T><<<grid, HaloCfg<KC, BN, CPX, T>::THREADS, HaloCfg<KC, BN, CPX, T>::SMEM, st>>>(tmA, tmB, p);
     SHM_CHECK_LAUNCH("conv_halo_kernel");
     return SHM_OK;
 }
