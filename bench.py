@@ -232,6 +232,23 @@ def run_ours(a):
                        "l2": "inputs+activations of one step >> 126 MB L2 (no flush needed)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "peaks": peak_src}
 
+    if not a.no_extras:
+        # ---- inference img/s at N GPUs (BASELINE.json metric; configs[3] shape: SpecSeg mask + generator, batch 64 at 512 x 512):
+        # inference is embarrassingly parallel per image -> N replicas, no communication; max-over-ranks device time
+        try:
+            ib, isz = 64, 512
+            inet = M.ShmGANwithSSpecSeg(M.default_args(image_size=isz, batch_size=ib), dtype=a.dtype).build()
+            img = torch.rand((ib, isz, isz, 3), device="cuda")
+            for _ in range(2):
+                inet.inference_step(img)
+            ms_inf = timed(lambda: inet.inference_step(img), 5)
+            line["inference_replicas"] = {"images_per_s": world * ib * 5 / (ms_inf * 1e-3), "ms_per_batch": ms_inf / 5, "batch_per_gpu": ib,
+                                          "size": isz, "n_gpus": world, "scaling": "replicas only (no collective)"}
+            del inet, img
+            torch.cuda.empty_cache()
+        except Exception as ex:                              # report, do not hide
+            line["inference_replicas"] = {"error": str(ex)[:200]}
+
     if rank == 0 and not a.no_extras:
         # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions), CUDA events per launch
         ops.PROF = []

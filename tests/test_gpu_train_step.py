@@ -168,3 +168,29 @@ def test_inference_step_matches_oracle():
         agree = ((net.specular_candidate.cpu() > 0.5) == (want["mask"] > 0.5)).double().mean()
         near = ((want["mask"] - 0.5).abs() < (1e-4 if dtype == "fp32" else 5e-3)).double().mean()
         assert float(agree) >= 0.999 - float(near)
+
+
+def test_inference_step_full_width_thin_first_layers():
+    """filter_size 64 at 64 x 64: the inference body runs SpecSeg's 16/32-channel levels, the attention first convs (1 -> 64 / 128) and
+    enc1a (10 -> 64) on the thin tensor-core kernels (16-channel pixel rows); the training-shaped path (64-channel padding) must agree."""
+    from shmgan_b200 import model as M
+    B, S, fs = 2, 64, 64
+    net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B, filter_size=fs), dtype="bf16").build()
+    Gp = O.init_params(O.generator_param_specs(fs, True), 1, F64, randomize_all=True)
+    Sp = O.init_params(O.specseg_param_specs(), 3, F64, randomize_all=True)
+    for k in Sp:
+        if k.endswith(".var"):
+            Sp[k] = Sp[k].abs() + 0.5
+    Gp, Sp = (OrderedDict((k, bf16_round(v)) for k, v in d.items()) for d in (Gp, Sp))
+    net.G.net.store.load(Gp); net.SpecSeg.load(Sp)
+    assert net.G.net.in_channels(B, S, S, infer=True) == 16 and net.G.net.in_channels(B, S, S) == 64
+    rgb = rand((B, S, S, 3), 31)
+    want = O.inference_step(Gp, Sp, rgb)
+    got = net.inference_step(dev(rgb)).clone()
+    assert rel_err(net.specular_candidate, want["mask"]) < 2e-2
+    assert rel_err(got, want["gen_rgb"]) < 2e-2
+    thin = net.G.net.thin
+    net.G.net.thin = {}                                  # same weights through the 64-channel padded first layers
+    ref = net.inference_step(dev(rgb))
+    net.G.net.thin = thin
+    assert rel_err(got, ref.double().cpu()) < 1e-2
