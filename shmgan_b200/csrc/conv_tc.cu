@@ -456,16 +456,18 @@ struct HaloCfg {
     static constexpr int W_SPACE = (W_BYTES + 1023) / 1024 * 1024;
     static constexpr int A_BYTES = HALO_W * (16 * T + 2) * CPX;
     static constexpr int A_STAGE = (A_BYTES + 1023) / 1024 * 1024;
-    // Coalesced epilogue (BN <= 64, one k-chunk): a thread owns one pixel row of the accumulator, so direct stores put the 32 lanes
-    // of every STG.128 on 32 different 128-byte lines (32 L1 wavefronts per instruction: ~1000 cycles per 128 x 64 tile, which
-    // bounded the 64-column layers).  Each epilogue warp instead stages its 32 rows in shared memory and writes them back with
-    // 2 BN / 16 lanes per pixel, i.e. whole lines per instruction.
-    // Measured (64 x 512 x 512, profiles/r01_thin_layers.txt): 64 -> 64 layers 1.32 -> 1.18 ms; the stacked thin layers are bound by the
-    // serial latency of their four epilogue warps instead and lose 10-15 % to the extra smem round trip, so they keep direct stores.
-    static constexpr bool COAL = BN <= 64 && KC == 1 && T == 1 && CPX == 128;
-    static constexpr int STG_PITCH = 2 * BN + 16;                         // bytes per staged row (+16: conflict-free 16-byte columns)
-    static constexpr int STG_WARP = 32 * STG_PITCH;
-    static constexpr int STG_BYTES = COAL ? 4 * STG_WARP : 0;
+    // TMA-store epilogue (BN <= 64, one k-chunk).  A thread owns one pixel row of the accumulator, so direct stores put the 32 lanes
+    // of every STG.128 on 32 different 128-byte lines (32 L1 wavefronts per instruction: ~1000 cycles per 128 x 64 tile), and the
+    // store address arithmetic made the four epilogue warps a serial latency chain (ncu on a stacked thin layer: 0.19 IPC per
+    // epilogue warp while the MMA warp waits for the accumulator).  Instead each group of four epilogue warps packs a sub-tile,
+    // writes it into a swizzled shared-memory tile (conflict-free STS.128), and one thread hands the 128-pixel x BN tile to the TMA
+    // engine (cp.async.bulk.tensor store): whole lines, no per-thread global addresses, asynchronous.  Two staging tiles per group.
+    static constexpr int EPI_WARPS = T > 1 ? 8 : 4;                       // stacked items: two warps per TMEM lane quadrant
+    static constexpr int EPI_GROUPS = EPI_WARPS / 4;
+    static constexpr bool TSTORE = BN <= 64 && KC == 1;
+    static constexpr int SROW = 2 * BN;                                   // bytes of one staged pixel row: 128 / 64 / 32
+    static constexpr int STG_TILE = 128 * SROW;                           // one sub-tile: 16 / 8 / 4 KB
+    static constexpr int STG_BYTES = TSTORE ? ((2 * EPI_GROUPS * STG_TILE + 1023) / 1024 * 1024) : 0;
     static constexpr int FIXED = 1024 + 256 + BIAS_SMEM + STG_BYTES;
     static constexpr int FIT = (227 * 1024 - FIXED - W_SPACE) / A_STAGE;  // halo stages that fit beside the resident weights
     static constexpr int WANT = T > 1 ? 4 : ((W_BYTES <= 73728) ? 6 : 3);
@@ -474,22 +476,21 @@ struct HaloCfg {
     static constexpr int SMEM = W_SPACE + STAGES * A_STAGE + FIXED;
     static constexpr int TMEM_COLS = 2 * T * BN < 32 ? 32 : 2 * T * BN;
     static constexpr uint32_t LAYOUT = CPX == 128 ? 2u : (CPX == 64 ? 4u : 6u);
-    // stacked items: TWO epilogue warps per TMEM lane quadrant (warps 2-5 take the even sub-tiles, 6-9 the odd ones) -- the four-warp
-    // epilogue of a stacked thin item was a serial latency chain (ncu: 0.19 IPC per epilogue warp, tensor pipe 13 % busy)
-    static constexpr int EPI_WARPS = T > 1 ? 8 : 4;
-    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;               // warps 2-5 take the even sub-tiles of a stacked item, 6-9 the odd ones
 };
 
 template <int KC, int BN, int CPX = 128, int T = 1>
 __global__ void __launch_bounds__((HaloCfg<KC, BN, CPX, T>::THREADS), 1)
-conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const HaloParams p) {
+conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                 const HaloParams p) {
     using Cfg = HaloCfg<KC, BN, CPX, T>;
     constexpr int HALO_STAGE = Cfg::A_STAGE;
     constexpr int HALO_BYTES = Cfg::A_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW = smem;                                   // [9 taps][KC][BN rows x CPX B]
-    uint8_t* sA = smem + Cfg::W_SPACE;                    // [STAGES][HALO_STAGE]
+    uint8_t* sStage = smem + Cfg::W_SPACE;                // [EPI_GROUPS][2][128 rows x SROW B] output staging (1024-aligned)
+    uint8_t* sA = sStage + Cfg::STG_BYTES;                // [STAGES][HALO_STAGE]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::STAGES * HALO_STAGE);
     uint64_t* full = bars;
     uint64_t* empty = bars + Cfg::STAGES;
@@ -498,7 +499,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* wbar = tempty + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
     float* sbias = reinterpret_cast<float*>(sA + Cfg::STAGES * HALO_STAGE + 256);
-    uint8_t* sStage = sA + Cfg::STAGES * HALO_STAGE + 256 + BIAS_SMEM;      // [4 epilogue warps][32 rows][STG_PITCH]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_img = p.tiles_x * p.tiles_y;
@@ -506,6 +506,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        if (Cfg::TSTORE) prefetch_tmap(&tmO);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], Cfg::EPI_WARPS); }
         mbar_init(wbar, 1);
@@ -581,6 +582,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int row = quad * 32 + lane;
         const int ty = row >> 3, tx = row & 7;
         int local = 0;
+        uint32_t nstore = 0;                              // sub-tiles this epilogue group has handed to the TMA engine
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
             const int as = local & 1;
             const int img = tile / per_img; const int r = tile - img * per_img;
@@ -588,52 +590,57 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * (T * BN));
-            if constexpr (Cfg::COAL) {
-                constexpr int CH = BN / 8, RP = 32 / CH;                 // 16-byte chunks per pixel; pixels per store instruction
-                const uint32_t stg = smem_u32(sStage + quad * Cfg::STG_WARP);
-                uint4 pk[T][CH];
-                // all T sub-tiles: TMEM -> registers (loads in flight together), bias / activation / bf16 pack
+            if constexpr (Cfg::TSTORE) {
+                constexpr int CH = BN / 8;                                // 16-byte chunks per staged pixel row
+                constexpr int G = Cfg::EPI_GROUPS, TJ = T / G;            // sub-tiles of this item handled by my group
+                const int eg = (warp - 2) >> 2;                           // epilogue group; its sub-tiles are eg, eg + G, ...
+                const bool leader = ((warp - 2) & 3) == 0 && lane == 0;
+                uint4 pk[TJ][CH];
                 if constexpr (BN == 16) {
-                    uint32_t r16[T][16];
+                    uint32_t r16[TJ][16];
 #pragma unroll
-                    for (int j = 0; j < T; ++j) tmem_ld16_nw(taddr + (uint32_t)(j * BN), r16[j]);
+                    for (int jj = 0; jj < TJ; ++jj) tmem_ld16_nw(taddr + (uint32_t)((G * jj + eg) * BN), r16[jj]);
 #pragma unroll
-                    for (int j = 0; j < T; ++j) { tmem_wait_ld16(r16[j]); epi_pack<16>(r16[j], p.bias ? sbias : nullptr, p.act, pk[j]); }
+                    for (int jj = 0; jj < TJ; ++jj) { tmem_wait_ld16(r16[jj]); epi_pack<16>(r16[jj], p.bias ? sbias : nullptr, p.act, pk[jj]); }
                 } else {
 #pragma unroll
-                    for (int j = 0; j < T; ++j) {
+                    for (int jj = 0; jj < TJ; ++jj) {
                         uint32_t r32[BN / 32][32];
 #pragma unroll
-                        for (int c = 0; c < BN / 32; ++c) tmem_ld32_nw(taddr + (uint32_t)(j * BN + c * 32), r32[c]);
+                        for (int c = 0; c < BN / 32; ++c) tmem_ld32_nw(taddr + (uint32_t)((G * jj + eg) * BN + c * 32), r32[c]);
 #pragma unroll
                         for (int c = 0; c < BN / 32; ++c) {
                             tmem_wait_ld32(r32[c]);
-                            epi_pack<32>(r32[c], p.bias ? sbias + c * 32 : nullptr, p.act, pk[j] + c * 4);
+                            epi_pack<32>(r32[c], p.bias ? sbias + c * 32 : nullptr, p.act, pk[jj] + c * 4);
                         }
                     }
                 }
-                // the accumulators are in registers: hand the TMEM buffer back before the (slower) store phase
+                // the accumulators are in registers: hand the TMEM buffer back before the store phase
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
 #pragma unroll
-                for (int j = 0; j < T; ++j) {
+                for (int jj = 0; jj < TJ; ++jj) {
+                    const uint32_t sb = smem_u32(sStage + (eg * 2 + (nstore & 1)) * Cfg::STG_TILE);
+                    // the bulk store that read this staging tile two sub-tiles ago must be done reading it
+                    if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+                    const uint32_t rowa = sb + (uint32_t)row * Cfg::SROW;
 #pragma unroll
-                    for (int c = 0; c < CH; ++c)
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * Cfg::STG_PITCH + c * 16),
-                                     "r"(pk[j][c].x), "r"(pk[j][c].y), "r"(pk[j][c].z), "r"(pk[j][c].w) : "memory");
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < CH; ++i) {
-                        const int row = i * RP + lane / CH, chunk = lane % CH;
-                        const int rowg = quad * 32 + row;
-                        uint4 u;
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
-                                     : "r"(stg + row * Cfg::STG_PITCH + chunk * 16) : "memory");
-                        bf16* g = p.out + ((long long)(img * p.H + y0t + 16 * j + (rowg >> 3)) * p.W + x0t + (rowg & 7)) * p.ldout + chunk * 8;
-                        *reinterpret_cast<uint4*>(g) = u;
+                    for (int c = 0; c < CH; ++c) {
+                        const uint32_t a = rowa + c * 16;
+                        const uint32_t sw = a ^ (((a >> 7) & (uint32_t)(Cfg::SROW / 16 - 1)) << 4);   // TMA swizzle of the row width
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(sw),
+                                     "r"(pk[jj][c].x), "r"(pk[jj][c].y), "r"(pk[jj][c].z), "r"(pk[jj][c].w) : "memory");
                     }
-                    __syncwarp();
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
+                    if (leader) {
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(&tmO), "r"(sb), "r"(0), "r"(x0t), "r"(y0t + 16 * (G * jj + eg)), "r"(img) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    ++nstore;
                 }
             } else {
                 const int oy = y0t + ty, ox = x0t + tx;
@@ -681,6 +688,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (lane == 0) mbar_arrive(&tempty[as]);
             }
         }
+        if (Cfg::TSTORE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every bulk store of this thread has completed
+        (void)nstore; (void)ty; (void)tx;
     }
     tc_fence_before();
     __syncthreads();
@@ -1088,14 +1097,19 @@ int launch_halo_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const HaloPara
     if (!attr) { cudaFuncSetAttribute(conv_halo_kernel<KC, BN, CPX, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, HaloCfg<KC, BN, CPX, T>::SMEM); attr = true; }
     int grid = shm_num_sms();
     if (grid > p.total_tiles) grid = p.total_tiles;
-    conv_halo_kernel<KC, BN, CPX, T><<<grid, HaloCfg<KC, BN, CPX, T>::THREADS, HaloCfg<KC, BN, CPX, T>::SMEM, st>>>(tmA, tmB, p);
+    // output map for the TMA-store epilogue: (BN channels, W, H, N) over the destination slice, box = one 16 x 8-pixel sub-tile
+    CUtensorMap tmO = tmA;
+    if (HaloCfg<KC, BN, CPX, T>::TSTORE) {
+        if (int rc = encode_act_box(&tmO, p.out, BN, p.W, p.H, p.total_tiles / (p.tiles_x * p.tiles_y), p.ldout, 8, 16, BN)) return rc;
+    }
+    conv_halo_kernel<KC, BN, CPX, T><<<grid, HaloCfg<KC, BN, CPX, T>::THREADS, HaloCfg<KC, BN, CPX, T>::SMEM, st>>>(tmA, tmB, tmO, p);
     SHM_CHECK_LAUNCH("conv_halo_kernel");
     return SHM_OK;
 }
 // thin layer: stacked sub-tiles per work item when the image height allows it
 template <int BN, int CPX>
 int launch_thin(const CUtensorMap& tmA1, const CUtensorMap& tmAT, const CUtensorMap& tmB, HaloParams& p, bool stack, cudaStream_t st) {
-    constexpr int T = BN <= 64 ? 4 : 2;
+    constexpr int T = (BN <= 64 && CPX < 128) ? 4 : 2;
     if (!stack) return launch_halo_t<1, BN, CPX, 1>(tmA1, tmB, p, st);
     p.tiles_y /= T; p.total_tiles /= T;
     return launch_halo_t<1, BN, CPX, T>(tmAT, tmB, p, st);
@@ -1119,7 +1133,7 @@ int launch_halo(int N, int H, int W, int K, int Nn, const void* in, int ldin, co
     if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, HALO_H, inner)) return rc;
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, Nn, inner)) return rc;
     if (K < 64 || Nn < 64) {
-        const int T = Nn <= 64 ? 4 : 2;
+        const int T = (Nn <= 64 && K < 64) ? 4 : 2;
         const bool stack = H % (16 * T) == 0;
         CUtensorMap tmS = tmA;
         if (stack) { if (int rc = encode_act_box(&tmS, in, K, W, H, N, ldin, HALO_W, 16 * T + 2, inner)) return rc; }
