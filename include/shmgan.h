@@ -65,6 +65,13 @@ int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, int cin_r
 int shm_conv2d_tc_route(const shm_conv_desc* d, int pass);
 /* both layouts (fwd and dgrad) in one launch */
 int shm_conv2d_tc_prep_weights_both(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc_fwd, void* w_tc_dgrad, void* stream);
+/* Batched form of shm_conv2d_tc_prep_weights_both for a whole network: fill one job record per layer in HOST memory
+ * (shm_conv2d_tc_prep_job_bytes() bytes each, contiguous), finalize the array (returns the launch's block count), copy it to the
+ * device once; shm_conv2d_tc_prep_multi then refreshes every layer's two bf16 layouts in ONE launch per optimiser step. */
+int shm_conv2d_tc_prep_job_bytes(void);
+int shm_conv2d_tc_prep_job(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc_fwd, void* w_tc_dgrad, void* job_out);
+int shm_conv2d_tc_prep_jobs_finalize(void* jobs_host, int njobs);
+int shm_conv2d_tc_prep_multi(const void* jobs_dev, int njobs, int total_blocks, void* stream);
 /* forward-layout weights of a layer run in a zero-padded device geometry (d->Cin, d->Cout) >= the Keras kernel's (cin_real, cout_real):
  * device input channel k holds real channel (k / seg_pad) * seg_real + k %% seg_pad when k %% seg_pad < seg_real, zero otherwise
  * (one segment = zero-padded input; two = concat of two zero-padded halves, SpecSeg.py:65-83 at 16/32 channels) */

@@ -10,6 +10,7 @@
 // Replaces the cuDNN kernels TF dispatches for Conv2D / Conv2DTranspose forward and dgrad
 // (ShmGANwithSSpecSeg.py:244-326, :365, :387, :410-411; tape.gradient :859,:868).
 #include "common.cuh"
+#include <string.h>
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -1677,6 +1678,30 @@ __global__ void prep_w_both_kernel(const float* __restrict__ w, PrepSet a, PrepS
     }
 }
 
+// the same for MANY layers in one launch: the per-step weight refresh of a network (~40 layers) is launch-bound otherwise.
+// blockIdx.x -> (job, chunk of 2048 elements) through the jobs' block_begin prefix; blockIdx.y = layout (0 forward, 1 dgrad).
+struct PrepJob { const float* w; PrepSet a, b; long long tap_elems, total; int block_begin, nblocks; };
+constexpr int PREP_CHUNK = 2048;
+__global__ void __launch_bounds__(256) prep_w_multi_kernel(const PrepJob* __restrict__ jobs, int njobs) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (jobs[mid].block_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const PrepJob J = jobs[lo];
+    const PrepSet s = blockIdx.y == 0 ? J.a : J.b;
+    const long long beg = (long long)((int)blockIdx.x - J.block_begin) * PREP_CHUNK;
+    const long long end = beg + PREP_CHUNK < J.total ? beg + PREP_CHUNK : J.total;
+    for (long long i = beg + threadIdx.x; i < end; i += 256) {
+        const int k = (int)(i % s.K);
+        const long long t2 = i / s.K;
+        const int n = (int)(t2 % s.Nn);
+        const long long tap = t2 / s.Nn;
+        const float v = (k < s.k_real && n < s.n_real) ? __ldg(J.w + tap * J.tap_elems + (long long)k * s.w_ks + (long long)n * s.w_ns) : 0.f;
+        s.o[i] = __float2bfloat16_rn(v);
+    }
+}
+
 bool wgrad_halo_ok(const shm_conv_desc* d) {
     return !d->transposed && d->stride == 1 && d->kh == 3 && d->kw == 3 && d->H % 16 == 0 && d->W % 8 == 0 &&
            d->Cin % 64 == 0 && d->Cout % 64 == 0;
@@ -1835,6 +1860,46 @@ extern "C" int shm_conv2d_tc_prep_weights_both(const shm_conv_desc* d, const flo
     if (g > shm_num_sms() * 8) g = shm_num_sms() * 8;
     prep_w_both_kernel<<<dim3((unsigned)g, 2), 256, 0, (cudaStream_t)stream>>>(w, a, b, (long long)cin_real * d->Cout, total);
     SHM_CHECK_LAUNCH("prep_w_both_kernel");
+    return SHM_OK;
+}
+
+// ---- batched form of shm_conv2d_tc_prep_weights_both: fill one job record per layer (host memory, shm_conv2d_tc_prep_job_bytes()
+//      each), finalize the array (block prefix), copy it to the device once, then ONE launch per optimiser step refreshes every layer.
+extern "C" int shm_conv2d_tc_prep_job_bytes(void) { return (int)sizeof(PrepJob); }
+extern "C" int shm_conv2d_tc_prep_job(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc_fwd, void* w_tc_dgrad, void* job_out) {
+    if (int rc = tc_check(d)) return rc;
+    SHM_REQUIRE(w && w_tc_fwd && w_tc_dgrad && job_out, "shm_conv2d_tc_prep_job: NULL buffer");
+    if (cin_real <= 0) cin_real = d->Cin;
+    SHM_REQUIRE(cin_real <= d->Cin, "shm_conv2d_tc_prep_job: cin_real > Cin");
+    SHM_REQUIRE(cin_real == d->Cin || !d->transposed, "shm_conv2d_tc_prep_job: channel padding is for Conv2D only");
+    PrepJob J{};
+    J.w = w;
+    PrepSet& a = J.a; PrepSet& b = J.b;
+    a.o = (bf16*)w_tc_fwd; b.o = (bf16*)w_tc_dgrad;
+    if (!d->transposed) {          // (kh,kw,Cin,Cout)
+        a.K = d->Cin; a.Nn = d->Cout; a.w_ks = d->Cout; a.w_ns = 1; a.k_real = cin_real; a.n_real = d->Cout;
+        b.K = d->Cout; b.Nn = d->Cin; b.w_ks = 1; b.w_ns = d->Cout; b.k_real = d->Cout; b.n_real = cin_real;
+    } else {                       // (kh,kw,Cout,Cin)
+        a.K = d->Cin; a.Nn = d->Cout; a.w_ks = 1; a.w_ns = d->Cin; a.k_real = a.K; a.n_real = a.Nn;
+        b.K = d->Cout; b.Nn = d->Cin; b.w_ks = d->Cin; b.w_ns = 1; b.k_real = b.K; b.n_real = b.Nn;
+    }
+    J.tap_elems = (long long)cin_real * d->Cout;
+    J.total = (long long)d->kh * d->kw * d->Cin * d->Cout;
+    J.nblocks = (int)cdiv64(J.total, PREP_CHUNK);
+    memcpy(job_out, &J, sizeof(J));
+    return SHM_OK;
+}
+extern "C" int shm_conv2d_tc_prep_jobs_finalize(void* jobs_host, int njobs) {
+    if (!jobs_host || njobs <= 0) return 0;
+    PrepJob* J = reinterpret_cast<PrepJob*>(jobs_host);
+    int acc = 0;
+    for (int i = 0; i < njobs; ++i) { J[i].block_begin = acc; acc += J[i].nblocks; }
+    return acc;                                       // total blocks of the launch
+}
+extern "C" int shm_conv2d_tc_prep_multi(const void* jobs_dev, int njobs, int total_blocks, void* stream) {
+    SHM_REQUIRE(jobs_dev && njobs > 0 && total_blocks > 0, "shm_conv2d_tc_prep_multi: bad args");
+    prep_w_multi_kernel<<<dim3((unsigned)total_blocks, 2), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const PrepJob*>(jobs_dev), njobs);
+    SHM_CHECK_LAUNCH("prep_w_multi_kernel");
     return SHM_OK;
 }
 

@@ -209,8 +209,9 @@ __global__ void pad64_kernel(const S* __restrict__ src, int lds, int C, uint4* _
 // ShmGANwithSSpecSeg.py:353,:387).  Presenting the 3-channel image zero-padded to 64 channels moved 128 B per INPUT pixel through
 // every d1 kernel (wgrad ran at 10 TFLOP/s); folding the 27 patch values into the channel axis makes d1 a 1x1 convolution over
 // [N, H/2, W/2, 64] (27 real channels), one 128-byte row per OUTPUT pixel.  channel k = (ky*3 + kx)*C + c.
-template <typename S>
-__global__ void im2col_k3s2_kernel(const S* __restrict__ x, int ldx, int H, int W, int C, int pb, uint4* __restrict__ out, long long nout) {
+template <typename S, int CT>
+__global__ void im2col_k3s2_kernel(const S* __restrict__ x, int ldx, int H, int W, int Crt, int pb, uint4* __restrict__ out, long long nout) {
+    const int C = CT > 0 ? CT : Crt;                     // CT = 3 (the discriminator's RGB input): tap / channel split by a constant
     const int Ho = H / 2, Wo = W / 2;
     const long long total = nout * 8;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -422,8 +423,13 @@ extern "C" int shm_im2col_k3s2(const void* x, int src_dtype, int ldx, int N, int
     const long long nout = (long long)N * (H / 2) * (W / 2);
     const int pb = same_pad_before(H, 3, 2);
     cudaStream_t st = (cudaStream_t)stream;
-    if (src_dtype == SHM_F32) im2col_k3s2_kernel<float><<<flat_grid(nout * 8), 256, 0, st>>>((const float*)x, ldx, H, W, C, pb, (uint4*)out_bf16, nout);
-    else if (src_dtype == SHM_BF16) im2col_k3s2_kernel<bf16><<<flat_grid(nout * 8), 256, 0, st>>>((const bf16*)x, ldx, H, W, C, pb, (uint4*)out_bf16, nout);
+    if (src_dtype == SHM_F32) {
+        if (C == 3) im2col_k3s2_kernel<float, 3><<<flat_grid(nout * 8), 256, 0, st>>>((const float*)x, ldx, H, W, C, pb, (uint4*)out_bf16, nout);
+        else im2col_k3s2_kernel<float, 0><<<flat_grid(nout * 8), 256, 0, st>>>((const float*)x, ldx, H, W, C, pb, (uint4*)out_bf16, nout);
+    } else if (src_dtype == SHM_BF16) {
+        if (C == 3) im2col_k3s2_kernel<bf16, 3><<<flat_grid(nout * 8), 256, 0, st>>>((const bf16*)x, ldx, H, W, C, pb, (uint4*)out_bf16, nout);
+        else im2col_k3s2_kernel<bf16, 0><<<flat_grid(nout * 8), 256, 0, st>>>((const bf16*)x, ldx, H, W, C, pb, (uint4*)out_bf16, nout);
+    }
     else SHM_FAIL(SHM_EINVAL, "shm_im2col_k3s2: bad dtype %d", src_dtype);
     SHM_CHECK_LAUNCH("im2col_k3s2_kernel");
     return SHM_OK;

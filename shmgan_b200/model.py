@@ -210,6 +210,8 @@ class ShmGANwithSSpecSeg:
         self.build()
         ops.arena_begin()
         G, D = self.G.net, self.D.net
+        G.store.refresh_tc_all()                            # bf16 weight copies of every layer, one launch per network
+        D.store.refresh_tc_all()
         origs = [t.contiguous() for t in (orig0, orig45, orig90, orig135, origED)]
         B, S = origs[0].shape[0], origs[0].shape[1]
         assert S == self.image_size and all(tuple(t.shape) == (B, S, S, 3) and t.dtype == torch.float32 for t in origs)

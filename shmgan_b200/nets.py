@@ -119,6 +119,8 @@ class ParamStore:
             self.gviews = OrderedDict((k, self.grad[o:o + n].view(shape)) for k, (o, n, shape) in self.offsets.items()
                                       if _is_trainable(k))
         self.version = 0
+        self.tc_convs: List[Conv] = []
+        self._tc_jobs = None
         self.step = 0
         self.padded_convs: List[Conv] = []
         self.init(seed)
@@ -169,6 +171,7 @@ class ParamStore:
         return OrderedDict((k, host[o:o + n].view(shape).clone()) for k, (o, n, shape) in self.offsets.items() if _is_trainable(k))
 
     def bind(self, conv: Conv):
+        conv.store = self
         conv.w = self.views[conv.name + ".w"]
         conv.dw = self.gviews.get(conv.name + ".w")
         if conv.has_bias:
@@ -182,6 +185,30 @@ class ParamStore:
         conv.enable_pad()
         self.padded_convs.append(conv)
         return conv
+
+    # -- batched refresh of the bf16 tensor-core weight copies --------------------------------------------------------
+    def register_tc(self, conv: Conv):
+        if conv not in self.tc_convs and type(conv) is Conv:
+            self.tc_convs.append(conv)
+            self._tc_jobs = None
+
+    def refresh_tc_all(self):
+        """ONE launch re-lays every registered layer's weights (fwd + dgrad layouts) after an optimiser step; layers seen for the
+        first time are refreshed individually by Conv.refresh_tc and join the batch from the next step on."""
+        todo = [c for c in self.tc_convs if c.tc_version != self.version]
+        if len(todo) < 2:
+            return
+        if self._tc_jobs is None or self._tc_jobs[0] != len(self.tc_convs):
+            blob = bytearray(b"".join(c.prep_job() for c in self.tc_convs))
+            import ctypes as C
+            host = (C.c_char * len(blob)).from_buffer(blob)
+            total = int(ops.call("shm_conv2d_tc_prep_jobs_finalize", host, len(self.tc_convs)))
+            dev = torch.frombuffer(blob, dtype=torch.uint8).clone().to(self.flat.device)
+            self._tc_jobs = (len(self.tc_convs), dev, total)
+        n, dev, total = self._tc_jobs
+        ops.call("shm_conv2d_tc_prep_multi", ops._p(dev), n, total, ops._stream())
+        for c in self.tc_convs:
+            c.tc_version = self.version
 
     def zero_grad(self):
         self.grad.zero_()

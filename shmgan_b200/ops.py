@@ -129,6 +129,7 @@ class Conv:
         self.w = self.b = self.dw = self.db = None          # views set by ParamStore.bind
         self.w_tc = self.w_tc_d = None                      # bf16 [tap][n][k] copies for the tensor-core path
         self.tc_version = -1
+        self.store = None                                   # the ParamStore this layer is bound to (batched weight refresh)
         self.cin_pad = None                                 # 64 when the layer reads a zero-padded input on the tensor cores
         self.dw_pad = None                                  # fp32 [kh,kw,cin_pad,cout] weight-gradient scratch of the padded layer
 
@@ -183,8 +184,18 @@ class Conv:
             n = self.kh * self.kw * cin * self.cout
             self.w_tc = new((n,), torch.bfloat16)
             self.w_tc_d = new((n,), torch.bfloat16)
+            if self.store is not None:
+                self.store.register_tc(self)                # from the next optimiser step on, refreshed by the store's one batched launch
         call("shm_conv2d_tc_prep_weights_both", C.byref(d), _p(self.w), self.cin, _p(self.w_tc), _p(self.w_tc_d), _stream())
         self.tc_version = version
+
+    def prep_job(self) -> bytes:
+        """This layer's record for the batched weight refresh (shm_conv2d_tc_prep_multi)."""
+        cin = self.cin_pad or self.cin
+        d = self.desc(1, 16, 16, cin, self.cout, BF16, cin=cin)
+        buf = C.create_string_buffer(int(call("shm_conv2d_tc_prep_job_bytes")))
+        call("shm_conv2d_tc_prep_job", C.byref(d), _p(self.w), self.cin, _p(self.w_tc), _p(self.w_tc_d), buf)
+        return buf.raw
 
     def tc_ok(self, d: ConvDesc) -> bool:
         return (d.dtype == BF16 and d.Cin % 64 == 0 and self.cout % 64 == 0
