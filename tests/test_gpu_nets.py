@@ -210,3 +210,28 @@ def test_specseg_padded_tensor_core_path():
     assert rel_err(got, ref) < 2e-2
     assert float(((got > 0.5) == (ref > 0.5)).double().mean()) >= 0.999
 
+
+
+def test_batched_weight_refresh_matches_per_layer_refresh():
+    """ParamStore.refresh_tc_all (one shm_conv2d_tc_prep_multi launch for the whole network) must write exactly the bf16 forward / dgrad
+    layouts that the per-layer shm_conv2d_tc_prep_weights_both writes, including the zero-padded first layers."""
+    from shmgan_b200 import nets
+    G = nets.Generator(64, True, torch.bfloat16)
+    x = dev(rand((2, 64, 64, 10), 50), torch.bfloat16)
+    mask = dev(rand((1, 64, 64, 1), 51), torch.bfloat16)
+    attn, _ = G.attention(mask)
+    y, tape = G.forward(x, attn, save=True)
+    G.backward(tape, torch.ones_like(y), [torch.zeros_like(a) for a in attn], attn_nb=1)      # registers the dgrad users too
+    convs = list(G.store.tc_convs)
+    assert len(convs) > 20
+    p2 = _params(O.generator_param_specs(64, True), 77)
+    G.store.load(p2)                                                   # version bump: every bf16 copy is stale
+    G.store.refresh_tc_all()
+    batched = [(c.w_tc.clone(), c.w_tc_d.clone()) for c in convs]
+    assert all(c.tc_version == G.store.version for c in convs)
+    for c in convs:
+        c.tc_version = -1
+        c.w_tc.zero_(); c.w_tc_d.zero_()
+        c.refresh_tc(G.store.version)
+    for c, (a, b) in zip(convs, batched):
+        assert torch.equal(c.w_tc, a) and torch.equal(c.w_tc_d, b), c.name
