@@ -176,6 +176,10 @@ def run_ours(a):
     host_in = [t.cpu().pin_memory() for t in dev_in]
     stage = [torch.empty_like(t) for t in dev_in]
 
+    def trace(msg):
+        if os.environ.get("BENCH_TRACE"):
+            print("[bench rank %d] %s" % (rank, msg), file=sys.stderr, flush=True)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -229,7 +233,9 @@ def run_ours(a):
     if rank == 0:
         clocks.start()
     l0 = _lib.launches()
+    trace("warm-up done")
     ms = timed(step_resident, a.steps)
+    trace("timed steps done")
     launches = (_lib.launches() - l0) // a.steps
     clk = clocks.stop() if rank == 0 else None
     value = world * B * a.steps / (ms * 1e-3)
@@ -238,6 +244,7 @@ def run_ours(a):
     issue_copy(0)
     step_e2e()
     ms_e2e = timed(step_e2e, a.steps)
+    trace("e2e done")
     e2e = {"value": world * B * a.steps / (ms_e2e * 1e-3), "unit": UNIT,
            "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_in), "d2h_bytes_per_step": net.table.buf.numel() * 4}
 
@@ -268,15 +275,22 @@ def run_ours(a):
             torch.cuda.empty_cache()
         except Exception as ex:                              # report, do not hide
             line["inference_replicas"] = {"error": str(ex)[:200]}
+        trace("inference replicas done")
 
-    if rank == 0 and not a.no_extras:
-        # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions), CUDA events per launch
-        ops.PROF = []
+    if not a.no_extras:
+        # ---- two profiled steps for the per-kernel roofline.  EVERY rank steps (the data-parallel gradient all-reduce needs all of
+        # them -- a rank-0-only step would wait for its peers forever); only rank 0 records the per-launch CUDA events.
+        if rank == 0:
+            ops.PROF = []
         net.overlap = False                                  # per-launch events need the kernels of one step serialised on one stream
         for _ in range(2):
             step_resident()
         torch.cuda.synchronize()
         net.overlap = True
+        trace("profiled steps done")
+
+    if rank == 0 and not a.no_extras:
+        # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM convolutions), CUDA events per launch
         rows = [(fam, kind, name, fl, nb, e0.elapsed_time(e1)) for fam, kind, name, fl, nb, e0, e1 in ops.PROF]
         ops.PROF = None
         step_ms = ms / a.steps
@@ -358,9 +372,11 @@ def run_ours(a):
         del big
 
         # ---- inference img/s (BASELINE.json metric, configs[3] / configs[4] shapes): SpecSeg mask + generator forward + yuv->rgb
-        # (test.py:218-250) through inference_step; inputs resident, CUDA events, >= L2-sized tensors
+        # (test.py:218-250) through inference_step; inputs resident, CUDA events, >= L2-sized tensors.
+        # The rank-0-only legs from here on (inference sweep, fp32 parity mode, CPU baseline) run at N = 1 only; at N > 1 the
+        # all-rank `inference_replicas` leg above carries the inference number.
         inf = {}
-        for tag, (ib, isz) in {"b64_512": (64, 512), "b8_1024": (8, 1024), "b64_256": (64, 256)}.items():
+        for tag, (ib, isz) in ({"b64_512": (64, 512), "b8_1024": (8, 1024), "b64_256": (64, 256)} if world == 1 else {}).items():
             try:
                 inet = M.ShmGANwithSSpecSeg(M.default_args(image_size=isz, batch_size=ib), dtype=a.dtype).build()
                 img = torch.rand((ib, isz, isz, 3), device="cuda")
@@ -392,10 +408,11 @@ def run_ours(a):
                 torch.cuda.empty_cache()
             except Exception as ex:                          # report, do not hide
                 inf[tag] = {"error": str(ex)[:200]}
-        line["inference"] = inf
+        if world == 1:
+            line["inference"] = inf
 
         # ---- configs[1] literally: the fp32 parity mode on the same batch (2 steps)
-        if a.dtype == "bf16":
+        if a.dtype == "bf16" and world == 1:
             del net
             torch.cuda.empty_cache()
             net32 = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B), dtype="fp32").build()
@@ -410,17 +427,20 @@ def run_ours(a):
             del net32
             torch.cuda.empty_cache()
 
-        # ---- CPU baseline beside it: one sample of the same step through the oracle port on the host cores
-        fn, cores = cpu_train_step_fn(S)
-        t0 = time.perf_counter()
-        fn()
-        dt = time.perf_counter() - t0
-        line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "1 train step of ONE sample (B=1) at %dx%d, float32, PyTorch-CPU oracle port of the reference step "
-                                          "(TensorFlow not installable), %d host threads, %.1f s" % (S, S, cores, dt)}
+        # ---- CPU baseline beside it (rank 0, N = 1 only): one sample of the same step through the oracle port on the host cores
+        if world == 1:
+            fn, cores = cpu_train_step_fn(S)
+            t0 = time.perf_counter()
+            fn()
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "1 train step of ONE sample (B=1) at %dx%d, float32, PyTorch-CPU oracle port of the reference step "
+                                              "(TensorFlow not installable), %d host threads, %.1f s" % (S, S, cores, dt)}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    trace("printing / leaving")
     if world > 1:
+        dist.barrier()                                       # leave together: rank 0's bookkeeping above has no collective in it
         dist.destroy_process_group()
 
 
