@@ -6,12 +6,14 @@
 // flight per SM, and measured 3.3-4.7 TB/s of the 6.5 TB/s copy peak.  Here the in-flight loads live in shared memory:
 // every thread owns a private ring of S slots per input stream and fills it with `cp.async.cg` (LDGSTS: global -> shared
 // without a destination register); it only ever reads back what it wrote itself, so the pipeline needs no block barrier,
-// only `cp.async.wait_group`.  Registers hold the coefficients and ONE pixel -> 4+ blocks per SM x 256 threads x S x 16 B
-// x streams = 128+ KB in flight per SM.
+// only `cp.async.wait_group`.  Registers hold the coefficients and ONE pixel -> 4 blocks per SM x 256 threads x S x 16 B x streams
+// in flight per SM; ring depth S = 4 (about 64 KB per SM) measured best -- deeper rings LOSE bandwidth.
 //
-// Work split: the tensor is ONE pixel range [0, N*HW) cut into gridDim.x equal contiguous pieces (grid = SMs x resident
-// blocks: exactly one balanced wave, no tail); a block walks its piece image by image (coefficients reloaded at an image
-// boundary, fp32 partial sums flushed to the fp64 atomics at least every SEG_MAX values).  HW % TY == 0 is required so that the
+// Work split: the tensor is ONE pixel range [0, N*HW) cut into gridDim.x equal contiguous pieces; a block walks its piece image by
+// image (coefficients reloaded at an image boundary, fp32 partial sums flushed to the fp64 atomics at least every SEG_MAX values).
+// The grid is sized by bytes per block (range_grid below: ~128 KB of the primary stream, ~512 KB for the statistics kernels whose
+// blocks end in atomics), not by the SM count: several short waves beat one long balanced wave because the pipeline-fill and
+// flush phases of different blocks then overlap (sweep: profiles/r01_norm_pipe_sweep.txt).  HW % TY == 0 is required so that the
 // TY pixel lanes of one iteration lie in one image (the host falls back to the *8 kernels otherwise).
 
 __device__ __forceinline__ void cp16(uint32_t saddr, const void* g) {
