@@ -55,28 +55,50 @@ class PolarimetricLoader:
         assert len(n) == 1, "the five folders must hold the same number of images (tf.data.Dataset.zip truncates silently)"
         self.length_dataset = n.pop()                      # datasetLoader.py:165
         self.image_size, self.batch_size, self.flip, self.repeat = image_size, batch_size, (not random_flip), repeat
-        self._pinned: Optional[torch.Tensor] = None
+        self._pinned = {}
+        self._copy_stream = None
 
     def __len__(self) -> int:
         return self.repeat * ((self.length_dataset + self.batch_size - 1) // self.batch_size)
 
-    def _stage(self, imgs: List[np.ndarray]) -> torch.Tensor:
-        arr = np.stack(imgs)
-        if self._pinned is None or self._pinned.shape != arr.shape:
-            self._pinned = torch.empty(arr.shape, dtype=torch.uint8, pin_memory=True)
-        self._pinned.copy_(torch.from_numpy(arr))
-        return self._pinned.cuda(non_blocking=True)
+    def _load_batch(self, i: int, slot: int):
+        """Stages batch i (five uint8 stacks) through pinned buffer set `slot` and runs the resize / scale / flip kernels on the copy
+        stream; returns (tensors, event recorded when they are ready)."""
+        stream = self._copy_stream
+        out, raw = [], []
+        with torch.cuda.stream(stream):
+            for k, s in enumerate(self.streams):
+                arr = np.stack(s[i:i + self.batch_size])
+                pin = self._pinned.get((slot, k))
+                if pin is None or pin.shape != arr.shape:
+                    pin = torch.empty(arr.shape, dtype=torch.uint8, pin_memory=True)
+                    self._pinned[(slot, k)] = pin
+                pin.copy_(torch.from_numpy(arr))
+                dev = pin.cuda(non_blocking=True)
+                out.append(ops.load_u8_images(dev, self.image_size, self.flip))
+                if self.est_diffuse:
+                    raw.append(dev)
+            if self.est_diffuse:
+                out.append(ops.load_u8_images(ops.pseudo_diffuse_min4(*raw), self.image_size, self.flip))
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return tuple(out), ev
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, ...]]:
-        for _ in range(self.repeat):
-            for i in range(0, self.length_dataset, self.batch_size):
-                out, raw = [], []
-                for s in self.streams:
-                    dev = self._stage(s[i:i + self.batch_size])
-                    out.append(ops.load_u8_images(dev, self.image_size, self.flip))
-                    torch.cuda.current_stream().synchronize()        # the pinned staging buffer is reused by the next stream
-                    if self.est_diffuse:
-                        raw.append(dev)
-                if self.est_diffuse:
-                    out.append(ops.load_u8_images(ops.pseudo_diffuse_min4(*raw), self.image_size, self.flip))
-                yield tuple(out)
+        """Double-buffered: while the consumer trains on batch i, batch i + 1 is copied and resized on a side stream (two pinned
+        buffer sets; a set is rewritten only after the copies that read it have completed)."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream()
+            self._pinned = {}
+        starts = [i for _ in range(self.repeat) for i in range(0, self.length_dataset, self.batch_size)]
+        pending = None
+        for n, i in enumerate(starts):
+            if pending is None:
+                pending = self._load_batch(i, n & 1)
+            batch, ev = pending
+            ev.synchronize()                                 # the pinned set of this batch may now be reused two batches later
+            pending = self._load_batch(starts[n + 1], (n + 1) & 1) if n + 1 < len(starts) else None
+            torch.cuda.current_stream().wait_event(ev)
+            for t in batch:
+                t.record_stream(torch.cuda.current_stream())
+            yield batch
