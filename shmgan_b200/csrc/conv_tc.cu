@@ -1799,8 +1799,10 @@ int tc_check(const shm_conv_desc* d) {
     SHM_REQUIRE(d != nullptr, "conv desc is NULL");
     if (d->dtype != SHM_BF16) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: needs dtype bf16");
     if (d->Cin % 64 != 0 || d->Cout % 64 != 0) {
-        // thin layers: the forward pass (K = Cin, N = Cout) of a stride-1 3x3 conv goes through the halo kernel with narrow pixel rows
-        const bool thin = !d->transposed && thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride);
+        // thin layers: the forward pass (K = Cin, N = Cout) or the dgrad (K = Cout, N = Cin) of a stride-1 3x3 conv goes through the
+        // halo kernel with narrow pixel rows / few accumulator columns
+        const bool thin = !d->transposed && (thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride) ||
+                                             thin_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, d->stride));
         if (!thin) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: Cin=%d / Cout=%d must be multiples of 64 (or a thin 3x3 stride-1 layer)", d->Cin, d->Cout);
     }
     if (d->ldx % 8 != 0 || d->ldy % 8 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: ld must be a multiple of 8");
@@ -1926,7 +1928,8 @@ extern "C" int shm_conv2d_tc_prep_weights_padded(const shm_conv_desc* d, const f
 
 extern "C" int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad) {
     if (tc_check(d) != SHM_OK) return 0;
-    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) return for_dgrad ? 0 : 1;      // thin layer (tc_check admitted it): forward only
+    if (d->Cin % 64 != 0 || d->Cout % 64 != 0)                                // thin layer (tc_check admitted one orientation)
+        return for_dgrad ? thin_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, d->stride) : thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, d->stride);
     int Ho, Wo; out_dims(d, Ho, Wo);
     int BW, BH, BI;
     // in every form the lattice is the SMALL image: Ho x Wo of a strided conv, H x W of a transposed conv
@@ -1956,7 +1959,7 @@ extern "C" int shm_conv2d_tc_route(const shm_conv_desc* d, int pass) {
     }
     if (d->transposed) return 0;
     if (s == 1) {
-        if (halo_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s)) return 1;
+        if (halo_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s) || thin_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s)) return 1;
         if (big_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s)) return 2;
         return 0;
     }
@@ -2034,7 +2037,8 @@ static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, 
 extern "C" int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const void* w_tc, void* dx, void* stream) {
     if (int rc = tc_check(d)) return rc;
     SHM_REQUIRE(dy && w_tc && dx, "shm_conv2d_tc_dgrad: NULL buffer");
-    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc dgrad: thin layers (%d -> %d) are forward-only", d->Cin, d->Cout);
+    if ((d->Cin % 64 != 0 || d->Cout % 64 != 0) && !thin_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, d->stride))
+        SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc dgrad: thin layer %d -> %d not servable (needs K = Cout in {16, 32, 64}, N = Cin in {16, 32, 64, 128})", d->Cin, d->Cout);
     cudaStream_t st = (cudaStream_t)stream;
     int Ho, Wo; out_dims(d, Ho, Wo);
     const int s = d->stride;
@@ -2076,7 +2080,7 @@ extern "C" int shm_conv2d_tc_dgrad(const shm_conv_desc* d, const void* dy, const
                 }
             }
             if (nt == 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: parity class without taps");
-            if (halo_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s))
+            if (halo_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s) || thin_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s))
                 return launch_halo(d->N, d->H, d->W, d->Cout, d->Cin, dy, d->ldy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, d->ldx, tdy, tdx, twr, st);
             if (big_ok(d->H, d->W, d->Cout, d->Cin, d->kh, d->kw, s))
                 return launch_big(d->N, d->H, d->W, d->Cout, d->Cin, dy, d->ldy, w_tc, wrows, nullptr, SHM_ACT_NONE, dx, d->ldx, tdy, tdx, twr, st);

@@ -138,6 +138,8 @@ class Conv:
         self.w_tc = self.w_tc_d = None                      # bf16 [tap][n][k] copies for the tensor-core path
         self.tc_version = -1
         self.store = None                                   # the ParamStore this layer is bound to (batched weight refresh)
+        self.w_tc_d16 = None                                # dgrad layout of a zero-padded first layer at 16 input channels (thin kernel)
+        self.tc16_version = -1
         self.cin_pad = None                                 # 64 when the layer reads a zero-padded input on the tensor cores
         self.dw_pad = None                                  # fp32 [kh,kw,cin_pad,cout] weight-gradient scratch of the padded layer
 
@@ -245,10 +247,34 @@ class Conv:
         ho, wo = self.out_hw(h, w)
         return esize * n * (h * w * self.cin + ho * wo * self.cout)
 
+    def thin_dgrad(self, dy: torch.Tensor, x_shape, version: int):
+        """dgrad of a zero-padded first layer through the thin halo kernel: dx comes out 16 channels wide (the real ones first)
+        instead of cin_pad = 64 -- a quarter of the MMAs and of the bytes.  Returns None when the shape is not servable."""
+        n, h, w, _ = x_shape
+        if self.cin > 16 or self.transposed or self.stride != 1 or self.kh != 3 or self.cout % 64 != 0:
+            return None
+        d = ConvDesc(n, h, w, 16, self.cout, 3, 3, 1, 0, ACT_NONE, 16, ld(dy), BF16, 0)
+        if dy.dtype != torch.bfloat16 or not call("shm_conv2d_tc_supported", C.byref(d), 1):
+            return None
+        if self.w_tc_d16 is None:
+            self.w_tc_d16 = new((9 * 16 * self.cout,), torch.bfloat16)
+            self.tc16_version = -1
+        if self.tc16_version != version:
+            call("shm_conv2d_tc_prep_weights", C.byref(d), _p(self.w), self.cin, _p(self.w_tc_d16), 1, _stream())
+            self.tc16_version = version
+        dx = new((n, h, w, 16), dy.dtype)
+        fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, dy.element_size())
+        _prof(_route(d, 1), "dgrad", self.name, fl, nb, lambda: call("shm_conv2d_tc_dgrad", C.byref(d), _p(dy), _p(self.w_tc_d16), _p(dx), _stream()))
+        return dx
+
     def dgrad(self, dy: torch.Tensor, x_shape, dx: Optional[torch.Tensor] = None, tc: bool = True, version: int = 0):
         """dx from dy = dL/d(pre-activation)."""
         n, h, w, cx = x_shape
         pad = self.padded(cx)
+        if pad and tc and dx is None:
+            thin = self.thin_dgrad(dy, x_shape, version)
+            if thin is not None:
+                return thin
         if dx is None:
             dx = new((n, h, w, cx if pad else self.cin), dy.dtype)
         d = self.desc(n, h, w, ld(dx), ld(dy), dt(dy), ACT_NONE, cin=self.cin_pad if pad else None)

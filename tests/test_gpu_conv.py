@@ -298,3 +298,23 @@ def test_conv_transpose_partial_column_store(cin, cout, k):
     c.fwd(xd, cat[..., :cout], True, 1)
     assert rel_err(cat[..., :cout], want) < BF16_TOL
     assert float((cat[..., cout:].float() - 3.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(2, 32, 32), (3, 64, 16), (1, 16, 8)])
+def test_conv_tc_thin_dgrad_of_padded_first_layer(shape):
+    """The zero-padded first layer (10 -> 64): its dgrad through the thin halo kernel (K = 64 output channels, N = 16 input columns)
+    against the oracle; channels 10..15 of dx belong to weights that do not exist and must be exactly zero."""
+    from shmgan_b200 import ops
+    N, H, W = shape
+    cin, cout = 10, 64
+    x = bf16_round(randn((N, H, W, cin), 61))
+    w = bf16_round(randn((3, 3, cin, cout), 62, 0.1))
+    xr = x.clone().requires_grad_()
+    pre = oracle_conv(xr, w, None, 1, False, 0)
+    dy = bf16_round(randn(tuple(pre.shape), 63))
+    gx, = torch.autograd.grad((pre * dy).sum(), [xr])
+    c = _mk_conv(cin, cout, 3, 1, False, 1, False, w, None).enable_pad()
+    dx = c.dgrad(dev(dy, torch.bfloat16), (N, H, W, 64), None, True, 1)
+    assert dx.shape == (N, H, W, 16)
+    assert rel_err(dx[..., :cin], gx) < BF16_TOL
+    assert float(dx[..., cin:].float().abs().max()) == 0.0
