@@ -1739,7 +1739,9 @@ int launch_wgrad_halo(const shm_conv_desc* d, const void* x, const void* dy, flo
     p.tiles_per_split = cdiv(p.total_tiles, best_s);
     p.splits = cdiv(p.total_tiles, p.tiles_per_split);
     CUtensorMap tmX, tmDY;
-    if (int rc = encode_act_box(&tmX, x, d->Cin, d->W, d->H, d->N, d->ldx, HALO_W, mode ? 16 : 18)) return rc;
+    // ldx < Cin: the tensor holds only ldx channels per pixel (a first layer's input padded to 16 instead of 64); the 64-channel TMA box
+    // then runs past the channel extent and the out-of-bounds part is zero-filled in shared memory -- the padding costs no HBM bytes
+    if (int rc = encode_act_box(&tmX, x, d->ldx < d->Cin ? d->ldx : d->Cin, d->W, d->H, d->N, d->ldx, HALO_W, mode ? 16 : 18)) return rc;
     if (int rc = encode_act_box(&tmDY, dy, d->Cout, d->W, d->H, d->N, d->ldy, 8, 16)) return rc;
     return mode ? launch_wgrad_halo_t<1>(tmX, tmDY, p, st) : launch_wgrad_halo_t<0>(tmX, tmDY, p, st);
 }
@@ -2128,6 +2130,7 @@ extern "C" int shm_conv2d_tc_wgrad(const shm_conv_desc* d, const void* x, const 
             }
     }
     if (wgrad_halo_ok(d)) return launch_wgrad_halo(d, x, dy, dw, st);
+    if (d->ldx < d->Cin) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc wgrad: a channel-truncated input (ldx=%d < Cin=%d) is served by the halo wgrad kernel only", d->ldx, d->Cin);
     if (wgrad_s2_ok(d)) return launch_wgrad_s2(d, x, dy, dw, st);
     if (!pick_box64(d->N, p.Qh, p.Qw, p.BW, p.BH, p.BI)) SHM_FAIL(SHM_EUNSUPPORTED, "wgrad_tc: lattice %dx%d does not tile into 64-point boxes", p.Qh, p.Qw);
     p.tiles_x = p.Qw / p.BW; p.tiles_y = p.Qh / p.BH;

@@ -290,11 +290,13 @@ class Generator:
 
     # -- helpers -----------------------------------------------------------------------------------
     def in_channels(self, n, h, w, infer: bool = False) -> int:
-        """Channel count of the input buffer forward() wants for an [n,h,w] batch: 16 (thin first layer, forward-only passes),
-        64 (zero-padded, tensor-core first layer) when that form can serve the shape, else the plain 10."""
-        if infer and "enc1a" in self.thin and self.thin["enc1a"].servable(n, h, w):
+        """Channel count of the input buffer forward() wants for an [n,h,w] batch: 16 (thin first layer: forward and dgrad on the thin
+        halo kernel, weight gradient through a zero-filling TMA box), 64 (zero-padded first layer) when only that form can serve the
+        shape, else the plain 10."""
+        c = self.enc[0][0].conv
+        if "enc1a" in self.thin and self.thin["enc1a"].servable(n, h, w) and (infer or (c.can_pad(n, h, w) and h % 16 == 0 and w % 8 == 0)):
             return 16
-        return 64 if (self.pad_in and self.enc[0][0].conv.can_pad(n, h, w)) else 10
+        return 64 if (self.pad_in and c.can_pad(n, h, w)) else 10
 
     def _conv(self, c: Conv, x, y=None):
         return c.fwd(x, y, self.tc, self.store.version)
@@ -337,9 +339,13 @@ class Generator:
         """x [B,S,S,10] (self.dtype; or already zero-padded to [B,S,S,64] in tensor-core mode) -> y [B,S,S,1].
         attn: per-level features [Ba,...] broadcast as n % Ba."""
         B, S = x.shape[0], x.shape[1]
-        if x.shape[-1] == 10 and self.in_channels(B, S, x.shape[2]) == 64:
-            x = ops.pad64(x)
-        assert x.shape[-1] != 16 or (not save and "enc1a" in self.thin), "the 16-channel input form is forward-only"
+        if x.shape[-1] == 10:
+            want = self.in_channels(B, S, x.shape[2])
+            if want == 64:
+                x = ops.pad64(x)
+            elif want == 16:
+                x = ops.pad_channels(x, 16)
+        assert x.shape[-1] != 16 or "enc1a" in self.thin, "the 16-channel input form needs the thin first layer"
         tape = {"x": x, "enc": [], "dec": [], "bott": []} if save else None
         h, cats = x, []
         for lvl in range(4):

@@ -271,10 +271,12 @@ class Conv:
         """dx from dy = dL/d(pre-activation)."""
         n, h, w, cx = x_shape
         pad = self.padded(cx)
-        if pad and tc and dx is None:
+        if (pad or (self.cin_pad is not None and cx == 16)) and tc and dx is None:
             thin = self.thin_dgrad(dy, x_shape, version)
             if thin is not None:
                 return thin
+            if not pad:
+                raise L.ShmError("%s: the 16-channel input form needs the thin dgrad kernel" % self.name)
         if dx is None:
             dx = new((n, h, w, cx if pad else self.cin), dy.dtype)
         d = self.desc(n, h, w, ld(dx), ld(dy), dt(dy), ACT_NONE, cin=self.cin_pad if pad else None)
@@ -294,7 +296,9 @@ class Conv:
         """dw += , db += (gradients accumulate: weights are shared by several passes).
         bias_done: db was already accumulated by the kernel that produced dy (inorm_bwd / act_bwd with dbias=)."""
         n, h, w, cx = x.shape
-        pad = self.padded(cx)
+        # a zero-padded first layer may be given its input 16 channels wide (dense): the halo wgrad kernel's 64-channel TMA box then
+        # runs past the channel extent and is zero-filled on the way into shared memory (ldx = 16 < Cin = 64 in the descriptor)
+        pad = self.padded(cx) or (self.cin_pad is not None and cx == 16 and x.is_contiguous())
         d = self.desc(n, h, w, ld(x), ld(dy), dt(x), ACT_NONE, cin=self.cin_pad if pad else None)
         fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, x.element_size())
         if pad and not (tc and self.tc_ok(d)):

@@ -318,3 +318,25 @@ def test_conv_tc_thin_dgrad_of_padded_first_layer(shape):
     assert dx.shape == (N, H, W, 16)
     assert rel_err(dx[..., :cin], gx) < BF16_TOL
     assert float(dx[..., cin:].float().abs().max()) == 0.0
+
+
+def test_conv_tc_wgrad_of_first_layer_from_16_channel_input():
+    """Weight gradient of the zero-padded first layer (10 -> 64) read from a DENSE 16-channel input: the 64-channel TMA box of the halo
+    wgrad kernel runs past the channel extent and is zero-filled, so the result equals the one from the 64-channel padded tensor."""
+    from shmgan_b200 import ops
+    N, H, W, cin, cout = 3, 32, 32, 10, 64
+    x = bf16_round(randn((N, H, W, cin), 71))
+    w = bf16_round(randn((3, 3, cin, cout), 72, 0.1))
+    wr = w.clone().requires_grad_()
+    pre = oracle_conv(x, wr, None, 1, False, 0)
+    dy = bf16_round(randn(tuple(pre.shape), 73))
+    gw, = torch.autograd.grad((pre * dy).sum(), [wr])
+    got = []
+    for cpad in (16, 64):
+        c = _mk_conv(cin, cout, 3, 1, False, 1, False, w, None).enable_pad()
+        c.wgrad(ops.pad_channels(dev(x, torch.bfloat16), cpad), dev(dy, torch.bfloat16), tc=True)
+        c.fold_pad_grad()
+        assert rel_err(c.dw, gw) < BF16_TOL
+        assert float(c.dw_pad[:, :, cin:].abs().max()) == 0.0
+        got.append(c.dw.clone())
+    assert float((got[0] - got[1]).abs().max()) <= 1e-5 * float(got[1].abs().max())       # fp32 atomics order only

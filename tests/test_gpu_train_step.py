@@ -183,7 +183,7 @@ def test_inference_step_full_width_thin_first_layers():
             Sp[k] = Sp[k].abs() + 0.5
     Gp, Sp = (OrderedDict((k, bf16_round(v)) for k, v in d.items()) for d in (Gp, Sp))
     net.G.net.store.load(Gp); net.SpecSeg.load(Sp)
-    assert net.G.net.in_channels(B, S, S, infer=True) == 16 and net.G.net.in_channels(B, S, S) == 64
+    assert net.G.net.in_channels(B, S, S, infer=True) == 16 and net.G.net.in_channels(B, S, S) == 16
     rgb = rand((B, S, S, 3), 31)
     want = O.inference_step(Gp, Sp, rgb)
     got = net.inference_step(dev(rgb)).clone()
