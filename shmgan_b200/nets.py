@@ -310,12 +310,14 @@ class Generator:
             if lvl > 0:
                 pooled = ops.maxpool(pooled, 2)
             ca, cb = self.attn[lvl]
-            thin = self.thin.get("attn%da" % (lvl + 1)) if infer else None
-            if thin is not None and thin.servable(*pooled.shape[:3]):
-                a1 = thin.fwd(ops.pad_channels(pooled, 16), None, True, self.store.version)
+            thin = self.thin.get("attn%da" % (lvl + 1))
+            if thin is not None and thin.servable(*pooled.shape[:3]) and (infer or ca.can_pad(*pooled.shape[:3])):
+                # 16-channel mask input: thin forward; the weight gradient (training) reads the same tensor through a zero-filling TMA box
+                pin = ops.pad_channels(pooled, 16)
+                a1 = thin.fwd(pin, None, True, self.store.version)
                 a2 = self._conv(cb, a1)
                 feats.append(a2)
-                saved.append((None, a1, a2))
+                saved.append((pin, a1, a2))
                 continue
             pin = ops.pad64(pooled) if (self.pad_in and ca.can_pad(*pooled.shape[:3])) else pooled
             a1 = self._conv(ca, pin)
