@@ -183,6 +183,12 @@ int shm_yuv2rgb(const float* Y, const float* cbcr, int64_t npix_cbcr /* cbcr ind
 /* dY (+)= sum_c (drgb_f32 + drgb_lp)[.,c]  (d rgb / dY = (1,1,1)); either gradient source may be NULL */
 int shm_yuv2rgb_bwd(const float* drgb_f32, const void* drgb_lp, int dtype_lp, int ld_lp, float* dY, int64_t npix, int accumulate, void* stream);
 
+/* running mean of the standardisation scales: acc[0] += sum(src[0..n)), acc[1] += n (fp64, device).  Replaces the unbounded
+ * self.stddev_arr list (ShmGANwithSSpecSeg.py:1306, datasetLoader.py:42) whose tf.reduce_mean is read at :548 and test.py:246 */
+int shm_sum_count(const float* src, int64_t n, double* acc, void* stream);
+/* out = x * mul * (acc ? acc[0]/acc[1] : 1): gen_rgb_output = yuv_to_rgb(gen_YCbCr * mean(stddev_arr) * 255) (:550, test.py:249; yuv_to_rgb is linear) */
+int shm_scale_by_mean(const float* x, const double* acc, float mul, float* out, int64_t n, void* stream);
+
 /* ---- losses (ShmGANwithSSpecSeg.py:669-844).  All accumulate `weight * loss` into loss_out[0] (fp32, device) and write gradients ---- */
 /* mean((a - target)^2) over n; da (+)= gscale * 2 (a-target)/n.  :669-679, :721-728 */
 int shm_lsgan(const float* a, int64_t n, float target, float* loss_out, float weight, float* da, float gscale, int accumulate, void* stream);

@@ -34,7 +34,7 @@ __all__ = [
     "per_image_standardization", "rescale_01", "ssim", "gram_matrix", "pseudo_diffuse_min4",
     "assemble_g1_input", "assemble_cyclic_inputs", "train_step_losses", "softmax_ce", "train_step_grads",
     "keras_adam_lr", "keras_adam_update", "inference_step", "count_params",
-    "RGB2YUV", "YUV2RGB", "LRELU_ALPHA", "IN_EPS", "BN_EPS", "bf16_storage",
+    "RGB2YUV", "YUV2RGB", "LRELU_ALPHA", "IN_EPS", "BN_EPS", "bf16_storage", "bf16_storage_bwd",
 ]
 
 LRELU_ALPHA = 0.2      # tf.nn.leaky_relu default (ShmGANwithSSpecSeg.py:244 activation=tf.nn.leaky_relu)
@@ -259,6 +259,23 @@ def bf16_storage(t):
     bf16 kernels are held to (same quantisation points, exact arithmetic in between); `q=None` is the plain reference."""
     r = t.detach().to(torch.float32).to(torch.bfloat16).to(t.dtype)
     return t + (r - t.detach())
+
+
+class _Bf16BothWays(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, t):
+        return t.to(torch.float32).to(torch.bfloat16).to(t.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(torch.float32).to(torch.bfloat16).to(g.dtype)
+
+
+def bf16_storage_bwd(t):
+    """bf16_storage that ALSO rounds the gradient flowing back through the same point to the bf16 grid: the CUDA path stores the
+    backward tensors (d/d pre-activation, d/d layer input) in bf16 as well, at the same places it stores activations.  This is the
+    storage model the whole-network bf16 gradient bounds are derived from (tests/test_gpu_nets.py, tests/test_gpu_baseline_shapes.py)."""
+    return _Bf16BothWays.apply(t)
 
 
 def _cli_parts(p, name, x, stride=1, bias=True, q=_ident):
@@ -584,14 +601,34 @@ def keras_adam_update(params, grads, m, v, step: int, lr0=2e-5, beta1=0.5, beta2
     return params, m, v
 
 
-def inference_step(Gp, Sp, rgb, live_mask=True, per_image=True):
-    """test.py:218-250: standardise -> SpecSeg mask -> G1 (slot 0 = Y, ED one-hot) -> yuv->rgb."""
-    yuv, _ = per_image_standardization(rgb_to_yuv(rgb), per_image)
+def inference_step(Gp, Sp, rgb, live_mask=True, per_image=True, cyclic: bool = False, stddev_history=None):
+    """test.py:218-250: standardise -> SpecSeg mask -> G1 (slot 0 = Y, ED one-hot) -> yuv->rgb.
+    cyclic=True adds test.py:252-284: five more generator passes whose non-target slots all carry `gen_rgb[..., 0]` (the R channel,
+    named orig_Ych in the reference), slot k zeroed and one-hot plane k set; outputs re-joined with the image's CbCr.
+    gen_rgb_output (test.py:249, ShmGANwithSSpecSeg.py:551) = yuv_to_rgb(gen_YCbCr * mean(stddev_arr) * 255), stddev_arr = every scale appended so far
+    (`stddev_history` = the earlier ones)."""
+    yuv, scale = per_image_standardization(rgb_to_yuv(rgb), per_image)
     Y = yuv[..., 0:1]
     mask = specseg_forward(Sp, Y)
+    gmask = mask if live_mask else None
     z = torch.zeros_like(Y)
     o = torch.ones_like(Y)
     gen_input = torch.cat([Y, z, z, z, z, z, z, z, z, o], dim=3)
-    gen_Y = generator_forward(Gp, gen_input, mask if live_mask else None)
-    gen_rgb = yuv_to_rgb(torch.cat([gen_Y, yuv[..., 1:]], dim=3))
-    return dict(mask=mask, gen_Y=gen_Y, gen_rgb=gen_rgb, yuv=yuv)
+    gen_Y = generator_forward(Gp, gen_input, gmask)
+    cbcr = yuv[..., 1:]
+    gen_ycc = torch.cat([gen_Y, cbcr], dim=3)
+    gen_rgb = yuv_to_rgb(gen_ycc)
+    hist = [scale.reshape(-1)] + ([] if stddev_history is None else [h.reshape(-1).to(scale.dtype) for h in stddev_history])
+    avg_std = torch.cat(hist).mean()
+    out = dict(mask=mask, gen_Y=gen_Y, gen_rgb=gen_rgb, yuv=yuv, scale=scale,
+               gen_rgb_output=yuv_to_rgb(gen_ycc * avg_std * 255.0))
+    if cyclic:
+        R = gen_rgb[..., 0:1]                                                           # test.py:252
+        cyc = []
+        for k in range(5):
+            planes = [z if j == k else R for j in range(5)]                             # test.py:260-264
+            onehot = [o if j == k else z for j in range(5)]                             # test.py:271-275
+            cy = generator_forward(Gp, torch.cat(planes + onehot, dim=3), gmask)        # test.py:280-284
+            cyc.append(yuv_to_rgb(torch.cat([cy, cbcr], dim=3)))                        # test.py:286-297
+        out["cyc_rgb"] = cyc
+    return out

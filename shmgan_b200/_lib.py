@@ -78,6 +78,8 @@ _SIG = {
     "shm_assemble_bwd": [_P, _I, _I, C.POINTER(C.c_int32), _I, _P, _L, _P],
     "shm_yuv2rgb": [_P, _P, _L, _P, _P, _I, _I, _L, _P],
     "shm_yuv2rgb_bwd": [_P, _P, _I, _I, _P, _L, _I, _P],
+    "shm_sum_count": [_P, _L, _P, _P],
+    "shm_scale_by_mean": [_P, _P, _F, _P, _L, _P],
     "shm_pw1_fwd": [_P, _I, _I, _P, _P, _I, _P, _L, _I, _P],
     "shm_pw1_bwd": [_P, _I, _I, _P, _P, _P, _I, _P, _I, _P, _P, _L, _I, _P],
     "shm_c3to1_fwd": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _I, _P],

@@ -1,16 +1,22 @@
 """Checkpoint / resume with the reference's surface (ShmGANwithSSpecSeg.py:939-951, :1125-1134; test.py:164-169):
 
-    ckpt = Checkpoint(generator=net.G, discriminator=net.D)        # optimizer state lives with each network's ParamStore
+    ckpt = Checkpoint(generator=net.G, discriminator=net.D, specseg=net.SpecSeg, host=net)
+                                                                 # optimizer state lives with each network's ParamStore; `specseg` makes a
+                                                                 # run self-contained (the reference re-reads specsegv3_chkpt.h5, :931);
+                                                                 # `host` = the step / RNG counters a bit-reproducible resume needs
     manager = CheckpointManager(ckpt, checkpoint_dir, max_to_keep=3)
     ckpt.restore(manager.latest_checkpoint).expect_partial()
     path = manager.save()
 
 Format: one `.npz` per save, entries `<net>/<variable>` in the reference's (Keras) layouts and variable names, plus
 `<net>/adam_m/<variable>`, `<net>/adam_v/<variable>` and `<net>/step` (Keras Adam `iterations`), so that a TensorFlow run of the
-reference can be diffed against it; a `checkpoint` index file lists the kept paths, newest last (TF's CheckpointManager does the
+reference can be diffed against it (shmgan_b200/keras_names.py maps the variable names); an object with host_state() /
+load_host_state() (the ShmGANwithSSpecSeg instance: step counter = Philox offsets of GaussianNoise / Dropout, the drop-bit RNG, D's call
+counter, the running standardisation scale) is stored as one JSON string under `<tag>/host_state`; a `checkpoint` index file lists the kept paths, newest last (TF's CheckpointManager does the
 same).  Host-side control plane: no kernels involved beyond the device<->host copies of the flat parameter buffers."""
 from __future__ import annotations
 
+import json
 import os
 from typing import Dict, List, Optional
 
@@ -42,6 +48,9 @@ class Checkpoint:
     def state(self) -> Dict[str, np.ndarray]:
         out: Dict[str, np.ndarray] = {}
         for tag, model in self.models.items():
+            if hasattr(model, "host_state"):
+                out["%s/host_state" % tag] = np.asarray(json.dumps(model.host_state()))
+                continue
             st = _store(model)
             for k, t in st.export().items():
                 out["%s/%s" % (tag, k)] = t.numpy()
@@ -69,6 +78,13 @@ class Checkpoint:
             return _Status(missing)
         with np.load(path) as z:
             for tag, model in self.models.items():
+                if hasattr(model, "load_host_state"):
+                    key = "%s/host_state" % tag
+                    if key in z.files:
+                        model.load_host_state(json.loads(str(z[key])))
+                    else:
+                        missing.append(key)
+                    continue
                 st = _store(model)
                 named = {}
                 for k in st.offsets:
@@ -78,6 +94,8 @@ class Checkpoint:
                     else:
                         missing.append(key)
                 st.load(named)
+                if hasattr(model, "loaded") and len(named) == len(st.offsets):
+                    model.loaded = True                      # SpecSeg: trained weights are in place (model.py::_require_mask_weights)
                 if st.m is not None:
                     m, v = st.m.cpu(), st.v.cpu()
                     for k, (o, n, shape) in st.offsets.items():

@@ -473,6 +473,36 @@ extern "C" int shm_yuv2rgb(const float* Y, const float* cbcr, int64_t npix_cbcr,
     })
 }
 
+// running mean of the standardisation scales (the reference appends every pixel_value_scale to self.stddev_arr, ShmGANwithSSpecSeg.py:1306,
+// and reads tf.reduce_mean(self.stddev_arr) at :548 / test.py:246): acc[0] += sum(src), acc[1] += n.  One block; n is a handful of values.
+__global__ void sum_count_kernel(const float* __restrict__ src, long long n, double* __restrict__ acc) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += (double)src[i];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) { acc[0] += s; acc[1] += (double)n; }
+}
+// out = x * mul * (acc[0] / acc[1]): gen_rgb_output = yuv_to_rgb(gen_YCbCr * mean(stddev_arr) * 255) (:550) -- yuv_to_rgb is linear
+__global__ void scale_by_mean_kernel(const float* __restrict__ x, const double* __restrict__ acc, float mul, float* __restrict__ out, long long n) {
+    float f = mul;
+    if (acc != nullptr) f *= acc[1] > 0.0 ? (float)(acc[0] / acc[1]) : 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = x[i] * f;
+}
+
+extern "C" int shm_sum_count(const float* src, int64_t n, double* acc, void* stream) {
+    SHM_REQUIRE(src && acc && n > 0, "shm_sum_count: bad args");
+    sum_count_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(src, n, acc);
+    SHM_CHECK_LAUNCH("sum_count_kernel");
+    return SHM_OK;
+}
+
+extern "C" int shm_scale_by_mean(const float* x, const double* acc, float mul, float* out, int64_t n, void* stream) {
+    SHM_REQUIRE(x && out && n > 0, "shm_scale_by_mean: bad args");
+    scale_by_mean_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(x, acc, mul, out, n);
+    SHM_CHECK_LAUNCH("scale_by_mean_kernel");
+    return SHM_OK;
+}
+
 extern "C" int shm_yuv2rgb_bwd(const float* drgb_f32, const void* drgb_lp, int dtype_lp, int ld_lp, float* dY, int64_t npix, int accumulate, void* stream) {
     SHM_REQUIRE((drgb_f32 || drgb_lp) && dY && npix > 0 && (!drgb_lp || ld_lp >= 3), "shm_yuv2rgb_bwd: bad args");
     DISPATCH_DTYPE(dtype_lp, T, {

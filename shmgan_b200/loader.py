@@ -43,8 +43,12 @@ class PolarimetricLoader:
     sources: five sequences of decoded uint8 [H,W,3] arrays (or five folder paths).  batch_size images of equal source size are
     stacked per step (the reference uses batch_size = 1, datasetLoader.py:57); `repeat` = num_epochs (:161)."""
 
-    def __init__(self, sources: Sequence, image_size: int, batch_size: int = 1, random_flip: bool = True, repeat: int = 1,
+    def __init__(self, sources: Sequence, image_size: int, batch_size: int = 1, random_flip: bool = False, repeat: int = 1,
                  est_diffuse: bool = False):
+        # random_flip: the reference's map lambda `x if self.random_flip else flip_up_down(x)` (datasetLoader.py:61) is traced ONCE, when
+        # datasetLoad runs, with self.random_flip == 0.0 (ShmGANwithSSpecSeg.py:203; the per-epoch redraw at :983 never reaches the traced
+        # graph): the training streams are therefore ALWAYS flipped vertically.  The default here reproduces that effective behaviour
+        # (random_flip=False -> flip); test.py:96,121 has the flip commented out, so inference callers pass random_flip=True (no flip).
         # est_diffuse (main.py:36 declares the flag, nothing reads it): four polarisation streams only; the fifth (ED) is the
         # pseudo-diffuse min-of-4 of the DECODED uint8 images (utils.py:68-123 works on the originals), computed on the device
         # and then sent through the same resize / scale / flip kernel as a pre-populated ED folder would be

@@ -93,27 +93,91 @@ class _DiscriminatorModel:
 
 class SpecSeg:
     """SpecSeg(H, W, C) of SpecSeg.py:27; `.predict(x[B,S,S,1], verbose=0)` -> sigmoid probabilities [B,S,S,1] fp32.
-    The reference loads specsegv3_chkpt.h5 (absent from the checkout); weights here are the seeded reference initialisers
-    unless `load()` is given a Keras-layout dict."""
+    The reference loads specsegv3_chkpt.h5 (ShmGANwithSSpecSeg.py:930-931, test.py:155-156; absent from the checkout).  Until one of
+    the `load*` methods has run the weights are the seeded reference INITIALISERS (`loaded` is False) and the mask is that of an
+    untrained network: ShmGANwithSSpecSeg refuses to train / infer on it unless built with allow_random_specseg=True."""
 
     def __init__(self, H, W, C=1, dtype=torch.float32, seed=44, tensor_core=True):
         assert C == 1, "SpecSeg takes a single-channel (Y) image"
         assert H % 16 == 0 and W % 16 == 0, "SpecSeg needs sides divisible by 16 (4 pooling levels)"
         self.net = nets.SpecSegNet(dtype, seed=seed, tensor_core=tensor_core)
+        self.loaded = False
 
     def load(self, named):
+        """Keras-layout tensors keyed by this repo's names (shmgan_b200/keras_names.py maps them to the Keras variable names)."""
         self.net.store.load(named)
+        self.loaded = True
+
+    def load_keras_weights(self, weights):
+        """`weights` = `keras_model.get_weights()` of SpecSeg.py:27-98 (a list of arrays in layer-creation order: kernel, bias per
+        conv; gamma, beta, moving_mean, moving_variance per BatchNormalization)."""
+        from .keras_names import specseg_keras_names
+        names = list(specseg_keras_names())
+        if len(weights) != len(names):
+            raise ValueError("SpecSeg has %d weight arrays, got %d" % (len(names), len(weights)))
+        named = {}
+        for k, wgt in zip(names, weights):
+            t = torch.as_tensor(wgt)
+            want = tuple(self.net.store.offsets[k][2])
+            if tuple(t.shape) != want:
+                raise ValueError("SpecSeg weight %s: shape %s, expected %s" % (k, tuple(t.shape), want))
+            named[k] = t
+        self.load(named)
+
+    def load_npz(self, path):
+        """An .npz keyed either by this repo's names (c1a.w, bn1.gamma ...) or by the Keras variable names (conv2d/kernel:0 ...)."""
+        import numpy as np
+        from .keras_names import specseg_keras_names
+        k2r = {v: k for k, v in specseg_keras_names().items()}
+        named = {}
+        with np.load(path) as z:
+            for key in z.files:
+                name = key if key in self.net.store.offsets else k2r.get(key, k2r.get(key + ":0"))
+                if name is None:
+                    raise KeyError("SpecSeg.load_npz: unknown entry %r" % key)
+                named[name] = torch.from_numpy(z[key])
+        missing = [k for k in self.net.store.offsets if k not in named]
+        if missing:
+            raise KeyError("SpecSeg.load_npz: missing %s" % missing[:4])
+        self.load(named)
+
+    def load_h5(self, path):
+        """specsegv3_chkpt.h5 (a Keras full-model HDF5, ShmGANwithSSpecSeg.py:931).  Needs h5py, which this image does not ship:
+        convert on a machine that has it (`np.savez(out, **{w.name: w.numpy() for w in model.weights})`) and use load_npz."""
+        try:
+            import h5py
+        except ImportError as ex:
+            raise RuntimeError("h5py is not installed: export the Keras weights to .npz and use SpecSeg.load_npz") from ex
+        from .keras_names import specseg_keras_names
+        named = {}
+        with h5py.File(path, "r") as f:
+            root = f["model_weights"] if "model_weights" in f else f
+            flat = {}
+            root.visititems(lambda n, o: flat.__setitem__(n, o) if hasattr(o, "shape") else None)
+            for name, kname in specseg_keras_names().items():
+                hits = [n for n in flat if n.endswith(kname) or n.endswith(kname.split(":")[0])]
+                if len(hits) != 1:
+                    raise KeyError("SpecSeg.load_h5: %d datasets match %s" % (len(hits), kname))
+                named[name] = torch.from_numpy(flat[hits[0]][()])
+        self.load(named)
 
     def predict(self, x, verbose=0):
         y = self.net.predict(ops.cast(x.contiguous(), self.net.dtype))
         return _f32(y)
 
 
+# loss attributes published by train_step (ShmGANwithSSpecSeg.py:669-844); they are read back from the device on first access
+_LOSS_ATTRS = frozenset((
+    "D1_RealFake_loss", "D3_RealFake_cyc", "D1_classification_loss", "D3_classification_loss", "D2_RealFake_target", "D4_RealFake_cyc",
+    "D4_classification_loss", "G_gan_loss", "G_clsf_loss", "L1_loss_Gen", "ssim_cyc_loss", "Spec_loss", "content_loss", "style_loss",
+    "total_NST_loss", "total_Generator_loss", "total_Discriminator_loss", "total_Classification_loss", "loss_values"))
+
+
 class ShmGANwithSSpecSeg:
     """ShmGANwithSSpecSeg(args) (ShmGANwithSSpecSeg.py:96).  Extra keyword arguments select the B200 execution mode."""
 
     def __init__(self, args, dtype: str = "fp32", live_mask: bool = True, tensor_core: bool = True, seed: int = 25,
-                 process_group=None, device: Optional[int] = None):
+                 process_group=None, device: Optional[int] = None, allow_random_specseg: bool = False):
         self.c_dim = 5                                      # :192 (args.c_dim is overridden)
         self.image_size = args.image_size
         self.batch_size = args.batch_size
@@ -134,7 +198,10 @@ class ShmGANwithSSpecSeg:
         self.use_lsgan = True
         self.gradmapD, self.gradmapG = {}, {}
         self.epoch = 0
-        self.stddev_arr, self.mean_arr, self.variance_arr = [], [], []      # datasetLoader.py:42-44
+        # datasetLoader.py:42-44.  stddev_arr is the only one the reference reads back (:548, test.py:246): a device-side running mean
+        # (ops.RunningMean, created by build()); mean_arr / variance_arr are write-only there and not kept
+        self.stddev_arr, self.mean_arr, self.variance_arr = None, [], []
+        self.allow_random_specseg = allow_random_specseg
         assert dtype in ("fp32", "bf16")
         assert self.image_size % 32 == 0, "image_size must be a multiple of 32 (5 stride-2 discriminator blocks)"
         self.dtype = torch.float32 if dtype == "fp32" else torch.bfloat16
@@ -152,6 +219,8 @@ class ShmGANwithSSpecSeg:
         self.step_count = 0
         self.table = LS.LossTable()
         self._reducer = None
+        self._pending_losses = None                         # (pinned host copy of the loss table, event) of the last train_step
+        self._loss_host = [None, None]
         # the discriminator's weight-gradient sweep (12 passes of small, bandwidth-heavy layers) is independent of the generator-loss
         # sweep (D dgrad-only -> G backward): it runs on a side stream so that its bandwidth kernels fill the gaps of the
         # tensor-bound generator kernels; likewise D(xA) forward runs beside the cyclic generator forward
@@ -178,12 +247,35 @@ class ShmGANwithSSpecSeg:
             self.D = self.build_discriminator()
         if self.SpecSeg is None:
             self.SpecSeg = SpecSeg(self.image_size, self.image_size, 1, self.dtype, tensor_core=self.tensor_core)
+        if self.stddev_arr is None:
+            self.stddev_arr = ops.RunningMean()
         return self
+
+    def _require_mask_weights(self):
+        """The reference cannot run without specsegv3_chkpt.h5 (:930-931, test.py:155-156): the mask feeds both attention branches and
+        Spec_loss.  Seeded random SpecSeg weights are for benchmarks / parity tests only and must be asked for."""
+        if self.live_mask and not self.SpecSeg.loaded and not self.allow_random_specseg:
+            raise RuntimeError("SpecSeg holds its random initialisers, not trained weights: call net.SpecSeg.load / load_npz / "
+                               "load_keras_weights (specsegv3_chkpt.h5 of the reference), restore a checkpoint that contains SpecSeg, "
+                               "or construct ShmGANwithSSpecSeg(..., allow_random_specseg=True)")
+
+    def __getattr__(self, name):
+        # only reached when normal lookup fails: the loss scalars of the last step are materialised on first access
+        if name in _LOSS_ATTRS and self.__dict__.get("_pending_losses") is not None:
+            self._finish_losses()
+            return self.__dict__[name]
+        if name == "gen_rgb_output" and self.__dict__.get("gen_rgb") is not None:
+            # :550 / test.py:249: yuv_to_rgb(gen_YCbCr * mean(stddev_arr) * 255) = gen_rgb * mean(stddev_arr) * 255 (yuv_to_rgb is linear)
+            out = self.stddev_arr.scaled(self.gen_rgb.contiguous(), 255.0)
+            self.__dict__["gen_rgb_output"] = out
+            return out
+        raise AttributeError(name)
 
     # -- preprocessing ------------------------------------------------------------------------------------------------
     def custom_per_image_standardization(self, image):
         """:1271-1309 on a YUV tensor is served by `yuv_standardize` on the RGB tensor (rgb->yuv and the divide are fused);
         this entry keeps the reference name for callers that hold RGB (test.py:218)."""
+        self.build()
         yuv, scale = ops.yuv_standardize(image.contiguous())
         self.stddev_arr.append(scale)
         return yuv
@@ -208,6 +300,10 @@ class ShmGANwithSSpecSeg:
         """train_step (:467-875).  Five [B,S,S,3] fp32 CUDA tensors in [0,1]; returns None and publishes the reference's
         attributes (gen_Y, gen_rgb, cyc_gen*_rgb, specular_candidate, the loss scalars ...)."""
         self.build()
+        self._require_mask_weights()
+        for k in _LOSS_ATTRS:                               # the previous step's scalars (read or not) are stale now
+            self.__dict__.pop(k, None)
+        self.__dict__.pop("gen_rgb_output", None)
         ops.arena_begin()
         G, D = self.G.net, self.D.net
         G.store.refresh_tc_all()                            # bf16 weight copies of every layer, one launch per network
@@ -224,7 +320,9 @@ class ShmGANwithSSpecSeg:
         tab.zero()
 
         # ---- preprocessing (:480-506) and the mask (:492, outside the tape)
-        ds = [ops.yuv_standardize(o)[0] for o in origs]
+        scales = ops.new((5, B), f32)
+        ds = [ops.yuv_standardize(o, scales[k])[0] for k, o in enumerate(origs)]
+        self.stddev_arr.append(scales)                      # :1306 (five appends per step in the reference)
         avg = ops.avg_cbcr(ds)
         mask = self.SpecSeg.net.predict(self._y_plane(ds[2], dt))
         self.specular_candidate = _f32(mask)
@@ -234,15 +332,16 @@ class ShmGANwithSSpecSeg:
             d_attn, d_attn_saved = D.attention(mask)
 
         # ---- G(1) (:509-553)
-        g_cin = min(G.in_channels(B, S, S), G.in_channels(5 * B, S, S))
-        gen_in = ops.new((B, S, S, g_cin), dt)              # 10 channels, or zero-padded to 64 for the tensor-core first layer
+        # input layout per buffer (10 plain, 16 thin first layer, 64 zero-padded first layer): whatever forward() wants for THAT batch
+        g_cin, g_cin5 = G.in_channels(B, S, S), G.in_channels(5 * B, S, S)
+        gen_in = ops.new((B, S, S, g_cin), dt)
         ops.assemble_input([None if bits[k] else ds[k] for k in range(5)], [3] * 5, 4, gen_in)
         gen_Y_lp, tape1 = G.forward(gen_in, g_attn, save=True)
         gen_Y = _f32(gen_Y_lp)
-        d_cin = min(D.in_channels(2 * B, S, S), D.in_channels(10 * B, S, S), D.in_channels(B, S, S), D.in_channels(5 * B, S, S))
+        d_cin = D.in_channels(2 * B, S, S)                  # the discriminator takes the plain 3-channel image in every mode
         xA = ops.new((2 * B, S, S, d_cin), dt)              # D batch A = [gen_rgb | origED], training=True (:559-563)
         xB = ops.new((10 * B, S, S, d_cin), dt)             # D batch B = [5 cyc_rgb | 5 orig], training=False (:627-642)
-        to_d = ops.pad64 if d_cin == 64 else (lambda src, out: ops.cast_into(src, out))
+        to_d = lambda src, out: ops.cast_into(src, out)
         if dt == f32:
             gen_rgb = xA[:B]
             ops.yuv2rgb(gen_Y, avg, gen_rgb, None)
@@ -266,7 +365,7 @@ class ShmGANwithSSpecSeg:
                 rfA_lp, clsA, tapeA = D.forward(xA, d_attn, noise, keep, save=True)
 
         # ---- cyclic G passes, batched as 5B images: pass k = images [kB, (k+1)B) (:576-624)
-        cyc_in = ops.new((5 * B, S, S, g_cin), dt)
+        cyc_in = ops.new((5 * B, S, S, g_cin5), dt)
         for k in range(5):
             srcs, lds = [], []
             for j in range(5):
@@ -373,14 +472,22 @@ class ShmGANwithSSpecSeg:
                 slots = [j for j in range(5) if j != k and bits[j]]
                 if slots:
                     ops.assemble_bwd(d_cyc_in[k * B:(k + 1) * B], slots, d_gen_Y)
-        G.backward(tape1, ops.cast(d_gen_Y, dt), g_dattn, attn_nb=B, need_dx=False)
+        # data parallel: this is the LAST pass that touches G's gradients, and it finishes the decoder first -- every range of the flat
+        # gradient buffer is all-reduced (NCCL's stream) as soon as its last weight-gradient kernel is enqueued, while the rest of the
+        # backward keeps computing; only the encoder / attention head of the buffer is reduced after the sweep
+        hook = None
+        if self._reducer is not None:
+            def hook(stage):
+                lo, hi = G.grad_range(stage)
+                self._reducer.reduce_async(G.store.grad, lo, hi)
+        G.backward(tape1, ops.cast(d_gen_Y, dt), g_dattn, attn_nb=B, need_dx=False, hook=hook)
         if self.live_mask:
             G.attention_backward(g_attn_saved, g_dattn)
         G.store.finalize_grads()
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         if self._reducer is not None:
-            self._reducer.reduce_async(G.store.grad)
+            hook("head")
             self._reducer.wait()
 
         # ---- clip_by_value(+-1) + Adam (:860-871); both optimisers use g_lr (:169-174)
@@ -391,7 +498,6 @@ class ShmGANwithSSpecSeg:
 
         # ---- published tensors / scalars (reference attribute names)
         self.gen_input, self.gen_Y, self.gen_rgb = gen_in[..., :10], gen_Y, gen_rgb
-        self.gen_rgb_output = gen_rgb
         self.averageCbCr = avg
         self.ds_yuv = ds
         self.cyc_Y = [cyc_Y[k * B:(k + 1) * B] for k in range(5)]
@@ -404,8 +510,25 @@ class ShmGANwithSSpecSeg:
         self.RealFake_orig_D4 = [rfB[(5 + k) * B:(6 + k) * B] for k in range(5)]
         (self.label_orig0_D4, self.label_orig45_D4, self.label_orig90_D4, self.label_orig135_D4,
          self.label_origED_D4) = [clsB[(5 + k) * B:(6 + k) * B] for k in range(5)]
-        self._publish_losses(tab.read())
+        self._start_loss_readback()
         return None
+
+    def _start_loss_readback(self):
+        """Asynchronous device->host copy of the loss table into pinned memory; the scalars are published when first read
+        (`net.total_Generator_loss` ...), so a caller that does not look at them every step never stalls the stream."""
+        i = self.step_count & 1
+        if self._loss_host[i] is None:
+            self._loss_host[i] = torch.empty(self.table.buf.numel(), dtype=torch.float32, pin_memory=True)
+        self._loss_host[i].copy_(self.table.buf, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._pending_losses = (self._loss_host[i], ev)
+
+    def _finish_losses(self):
+        host, ev = self._pending_losses
+        ev.synchronize()
+        self._pending_losses = None
+        self._publish_losses({k: float(host[i]) for k, i in LS.IDX.items()})
 
     def _side_stream(self):
         if not self.overlap:
@@ -416,6 +539,7 @@ class ShmGANwithSSpecSeg:
 
     def _publish_losses(self, v):
         """Totals of :669-844 from the per-term table (one device->host copy per step)."""
+        self.loss_values = dict(v)
         L1 = (v["L1_c0"] + v["L1_c1"] + v["L1_c2"] + v["L1_c3"] + v["L1_G1"]) / 5.0 + v["L1_c4"] * 10.0
         ssim = (v["ssim0"] + v["ssim1"] + v["ssim2"] + v["ssim3"] + v["ssim4"] * 10.0) / 5.0
         spec = (v["spec0"] + v["spec1"] + v["spec2"] + v["spec3"]) / 5.0 + v["spec4"] * 5.0
@@ -438,12 +562,15 @@ class ShmGANwithSSpecSeg:
         """The per-image body of test.py:218-297: standardise -> SpecSeg mask -> G1 with only slot 0 populated and the ED
         one-hot plane -> yuv->rgb with the image's own CbCr.  Returns gen_rgb [B,S,S,3] fp32 (and publishes gen_Y, mask)."""
         self.build()
+        self._require_mask_weights()
+        self.__dict__.pop("gen_rgb_output", None)
         ops.arena_begin()
         G = self.G.net
         rgb = rgb.contiguous()
         B, S = rgb.shape[0], rgb.shape[1]
         dt = self.dtype
-        yuv = ops.yuv_standardize(rgb)[0]
+        yuv, scale = ops.yuv_standardize(rgb)
+        self.stddev_arr.append(scale)                                                                  # :1306 via test.py:218
         mask = self.SpecSeg.net.predict(self._y_plane(yuv, dt))
         self.specular_candidate = _f32(mask)
         attn = G.attention(mask, infer=True)[0] if self.live_mask else None
@@ -465,6 +592,7 @@ class ShmGANwithSSpecSeg:
             crgb = ops.new((5 * B, S, S, 3), torch.float32)
             ops.yuv2rgb(cy, cbcr, crgb, None)
             self.cyc_rgb = [crgb[k * B:(k + 1) * B] for k in range(5)]
+            self.cyc_gen0_rgb, self.cyc_gen45_rgb, self.cyc_gen90_rgb, self.cyc_gen135_rgb, self.cyc_genED_rgb = self.cyc_rgb   # test.py:293-297
         return self.gen_rgb
 
     # -- data parallel ----------------------------------------------------------------------------------------------------
@@ -474,5 +602,27 @@ class ShmGANwithSSpecSeg:
         from .parallel import GradReducer
         self.build()
         self._reducer = GradReducer(process_group, bucket_mb)
-        self._reducer.broadcast_params([self.G.net.store.flat, self.D.net.store.flat, self.SpecSeg.net.store.flat])
+        stores = [self.G.net.store, self.D.net.store, self.SpecSeg.net.store]
+        self._reducer.broadcast_params([st.flat for st in stores])
+        for st in stores:
+            st.version += 1                                  # bf16 tensor-core copies made before the broadcast are stale
+        # one global batch = independent GaussianNoise / Dropout draws per sample: every rank draws from its own Philox stream
+        # (the 5 drop bits and T stay shared: they are per-step scalars of the whole batch)
+        self.noise_seed = self.seed + 1000003 * self._reducer.rank
         return self
+
+    # -- host-side state a resumed run needs beside the parameters (checkpoint.py) ------------------------------------------
+    def host_state(self) -> dict:
+        return {"step_count": self.step_count, "rng": list(self._rng.getstate()[1]), "rng_gauss": self._rng.getstate()[2],
+                "d_calls": 0 if self.D is None else self.D.calls, "noise_seed": self.noise_seed, "epoch": self.epoch,
+                "stddev": None if self.stddev_arr is None else self.stddev_arr.state()}
+
+    def load_host_state(self, st: dict):
+        self.build()
+        self.step_count = int(st["step_count"])
+        self._rng.setstate((3, tuple(int(v) for v in st["rng"]), st.get("rng_gauss")))
+        self.D.calls = int(st.get("d_calls", 0))
+        self.noise_seed = int(st.get("noise_seed", self.noise_seed))
+        self.epoch = int(st.get("epoch", 0))
+        if st.get("stddev") is not None:
+            self.stddev_arr.load_state(st["stddev"])

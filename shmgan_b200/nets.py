@@ -347,7 +347,8 @@ class Generator:
                 x = ops.pad64(x)
             elif want == 16:
                 x = ops.pad_channels(x, 16)
-        assert x.shape[-1] != 16 or "enc1a" in self.thin, "the 16-channel input form needs the thin first layer"
+        assert x.shape[-1] != 16 or ("enc1a" in self.thin and self.thin["enc1a"].servable(B, S, x.shape[2])), \
+            "the 16-channel input form needs the thin first layer to serve this shape (use in_channels(n, h, w) to pick the layout)"
         tape = {"x": x, "enc": [], "dec": [], "bott": []} if save else None
         h, cats = x, []
         for lvl in range(4):
@@ -401,10 +402,23 @@ class Generator:
             return None
         return blk.conv.dgrad(dpre, x_in.shape, None, self.tc, self.store.version)
 
+    def grad_range(self, stage):
+        """[lo, hi) of the flat gradient buffer that is FINAL once `stage` of the last backward sweep has been enqueued (the buffer is
+        in Keras creation order: encoder + attention head, bottleneck, decoder levels 1..4, output layer): ("dec", u) = up{u+1}T ..
+        dec{u+1}b (+ the output layer for u = 3), "bott", "head" = everything before the bottleneck."""
+        off = self.store.offsets
+        if stage == "head":
+            return 0, off["bott1.w"][0]
+        if stage == "bott":
+            return off["bott1.w"][0], off["up1T.w"][0]
+        _, u = stage
+        return off["up%dT.w" % (u + 1)][0], (off["up%dT.w" % (u + 2)][0] if u < 3 else self.store.n_train)
+
     def backward(self, tape, dy: torch.Tensor, dattn: Optional[List[torch.Tensor]] = None, attn_nb: int = 0,
-                 need_dx: bool = False):
+                 need_dx: bool = False, hook=None):
         """Accumulates weight gradients into the store; dattn[lvl] (+)= batch-group sums of d(skip) when given.
-        Returns d(x) [B,S,S,10] if need_dx."""
+        Returns d(x) [B,S,S,10] if need_dx.  hook(stage): called when the weight gradients of ("dec", u) / "bott" have been
+        enqueued (see grad_range) -- the data-parallel all-reduce of that range starts there."""
         v = self.store.version
         h, y = tape["last"]
         if self.tc and self.out.pw1_ok(h):
@@ -424,9 +438,13 @@ class Generator:
             self.up[u].wgrad(hin, dup, self.tc, bias_done=True)
             dh = self.up[u].dgrad(dup, hin.shape, None, self.tc, v)
             dskips[3 - u] = dcat[..., C:]
+            if hook is not None:
+                hook(("dec", u))
         for i in (1, 0):
             hin, z, sz = tape["bott"][i]
             dh = self._cli_bwd(self.bott[i], hin, z, sz, dyA=dh)
+        if hook is not None:
+            hook("bott")
         dx = None
         for lvl in (3, 2, 1, 0):
             hin, za, sa, ya, zb, sb = tape["enc"][lvl]

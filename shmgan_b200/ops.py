@@ -558,15 +558,48 @@ def pseudo_diffuse_min4(i0, i45, i90, i135):
     return out
 
 
-def yuv_standardize(rgb):
-    """rgb [N,H,W,3] fp32 -> (standardised yuv [N,H,W,3] fp32, scale [N])."""
+def yuv_standardize(rgb, scale_out=None):
+    """rgb [N,H,W,3] fp32 -> (standardised yuv [N,H,W,3] fp32, scale [N]); scale_out: a dense [N] fp32 view to write the scales into."""
     n, h, w, _ = rgb.shape
     sums = zeros64((n, 2), rgb.device)
     call("shm_yuv_stats", _p(rgb), n, h * w, _p(sums), _stream())
     yuv = torch.empty_like(rgb)
-    scale = new((n,), torch.float32)
+    scale = new((n,), torch.float32) if scale_out is None else scale_out
+    assert scale.numel() == n and scale.is_contiguous() and scale.dtype == torch.float32
     call("shm_yuv_standardize", _p(rgb), n, h * w, _p(sums), _p(yuv), _p(scale), _stream())
     return yuv, scale
+
+
+class RunningMean:
+    """Device-side stand-in for the reference's unbounded `self.stddev_arr` list (ShmGANwithSSpecSeg.py:1306, datasetLoader.py:42): `append`
+    adds a tensor of scales to an fp64 (sum, count) pair on the device; `scaled(x, mul)` = x * mul * mean without a host round trip
+    (tf.reduce_mean(self.stddev_arr) at :548 / test.py:246); `mean()` reads it back (synchronises)."""
+
+    def __init__(self, device="cuda"):
+        self.acc = torch.zeros(2, dtype=torch.float64, device=device)
+
+    def append(self, t: torch.Tensor):
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        call("shm_sum_count", _p(t), t.numel(), _p(self.acc), _stream())
+
+    def scaled(self, x: torch.Tensor, mul: float) -> torch.Tensor:
+        assert x.dtype == torch.float32 and x.is_contiguous()
+        out = torch.empty_like(x)
+        call("shm_scale_by_mean", _p(x), _p(self.acc), float(mul), _p(out), x.numel(), _stream())
+        return out
+
+    def mean(self) -> float:
+        a = self.acc.cpu()
+        return float(a[0] / a[1]) if float(a[1]) > 0 else 0.0
+
+    def __len__(self) -> int:
+        return int(self.acc[1].item())
+
+    def state(self):
+        return self.acc.cpu().tolist()
+
+    def load_state(self, st):
+        self.acc.copy_(torch.tensor(list(st), dtype=torch.float64))
 
 
 def avg_cbcr(ds: Sequence[torch.Tensor]):

@@ -18,7 +18,7 @@ def rand(shape, seed):
     return torch.rand(shape, generator=gen(seed), dtype=F64)
 
 
-def rel_err(got, want):
+def max_err(got, want):
     """max |got - want| / max |want| (both brought to fp64 on the host)."""
     g = got.detach().to("cpu", F64)
     w = want.detach().to("cpu", F64)
@@ -27,9 +27,56 @@ def rel_err(got, want):
 
 
 def rms_err(got, want):
+    """rms(got - want) / rms(want)."""
     g = got.detach().to("cpu", F64)
     w = want.detach().to("cpu", F64)
+    assert g.shape == w.shape, (g.shape, w.shape)
     return float(((g - w) ** 2).mean().sqrt() / ((w ** 2).mean().sqrt() + 1e-30))
+
+
+def rel_err(got, want):
+    """The relative error every parity assertion uses: the LARGER of the max-norm reading (max |d| / max |want|) and the rms reading
+    (rms d / rms want), so that a tolerance holds under both (VERDICT r01 weak #3: max-norm alone is the most forgiving reading)."""
+    return max(max_err(got, want), rms_err(got, want))
+
+
+def cos_sim(got, want):
+    g, w = got.detach().to("cpu", F64).reshape(-1), want.detach().to("cpu", F64).reshape(-1)
+    return float((g @ w) / (g.norm() * w.norm() + 1e-300))
+
+
+BF16_FACTOR = 1.5        # device error (vs the plain oracle) allowed as a multiple of what bf16 storage costs the oracle itself
+BF16_FLOOR = 2e-2        # north_star's bf16 tolerance: tensors that bf16 storage barely moves are held to it directly
+BF16_REPORT = {}         # test name -> rows (tensor, e_store, e_dev, cos_store, cos_dev), dumped to gpurun_out/ for DESIGN.md
+
+
+def derived_bf16_grad_check(what, got: dict, plain: dict, stored: dict):
+    """got / plain / stored: name -> gradient tensor from the device, the plain fp64 oracle and the fp64 oracle with bf16 storage points."""
+    keys = [k for k, w in plain.items() if float(w.abs().max()) > 0]
+    e_store = {k: rms_err(stored[k], plain[k]) for k in keys}
+    med = sorted(e_store.values())[len(keys) // 2]
+    rows, bad = [], []
+    for k in keys:
+        e_dev, c_dev, c_st = rms_err(got[k], plain[k]), cos_sim(got[k], plain[k]), cos_sim(stored[k], plain[k])
+        rows.append((k, e_store[k], e_dev, c_st, c_dev))
+        if e_dev > BF16_FACTOR * max(e_store[k], med) + BF16_FLOOR or (1 - c_dev) > BF16_FACTOR ** 2 * (1 - c_st) + 1e-3:
+            bad.append(rows[-1])
+    BF16_REPORT[what] = rows
+    _dump_report()
+    assert not bad, (what, "(tensor, e_store, e_dev, cos_store, cos_dev)", bad)
+    return rows
+
+
+def _dump_report():
+    import json, os
+    try:
+        d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, "bf16_grad_bounds.json"), "w") as fh:
+            json.dump({k: [{"tensor": r[0], "e_store": r[1], "e_dev": r[2], "cos_store": r[3], "cos_dev": r[4]} for r in v]
+                       for k, v in BF16_REPORT.items()}, fh, indent=1)
+    except OSError:
+        pass
 
 
 def dev(t, dtype=torch.float32):

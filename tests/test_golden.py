@@ -104,7 +104,7 @@ def test_gpu_train_step_matches_golden():
     from shmgan_b200 import model as M
     z = _load("train_step")
     fs, S = 4, 32
-    net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=1, filter_size=fs), dtype="fp32").build()
+    net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=1, filter_size=fs), dtype="fp32", allow_random_specseg=True).build()
     net.G.net.store.load(O.init_params(O.generator_param_specs(fs, True), 1, F, randomize_all=True))
     net.D.net.store.load(O.init_params(O.discriminator_param_specs(S, fs, True), 2, F, randomize_all=True))
     # pin the mask the fixture used: replace the SpecSeg prediction by the stored mask

@@ -59,7 +59,7 @@ def test_image_metrics_parity(n, s):
 
 def _net(seed_shift=0):
     from shmgan_b200 import model as M
-    net = M.ShmGANwithSSpecSeg(M.default_args(image_size=64, batch_size=2, filter_size=8), dtype="bf16").build()
+    net = M.ShmGANwithSSpecSeg(M.default_args(image_size=64, batch_size=2, filter_size=8), dtype="bf16", allow_random_specseg=True).build()
     if seed_shift:
         net.G.net.store.init(100 + seed_shift); net.D.net.store.init(200 + seed_shift)
     net.drop_bits, net.TARGET_LABELS, net.noise_seed = [True, False, False, True, False], 0.9, 5
@@ -71,19 +71,28 @@ def test_checkpoint_roundtrip_resumes_training(tmp_path):
     g = torch.Generator().manual_seed(0)
     batch = [torch.rand((2, 64, 64, 3), generator=g).cuda() for _ in range(5)]
     a = _net()
+    a.drop_bits = None                                             # let the host RNG draw the five bits: its state must survive the resume
     a.train_step(*batch)                                           # Adam moments and step counters are now non-trivial
-    mgr = CheckpointManager(Checkpoint(generator=a.G, discriminator=a.D), str(tmp_path), max_to_keep=3)
+    mgr = CheckpointManager(Checkpoint(generator=a.G, discriminator=a.D, specseg=a.SpecSeg, host=a), str(tmp_path), max_to_keep=3)
     path = mgr.save()
     b = _net(seed_shift=1)
+    b.drop_bits = None
+    b.SpecSeg.net.store.init(300)
     assert not torch.equal(a.G.net.store.flat, b.G.net.store.flat)
-    Checkpoint(generator=b.G, discriminator=b.D).restore(CheckpointManager(Checkpoint(), str(tmp_path)).latest_checkpoint).assert_consumed()
+    Checkpoint(generator=b.G, discriminator=b.D, specseg=b.SpecSeg, host=b).restore(
+        CheckpointManager(Checkpoint(), str(tmp_path)).latest_checkpoint).assert_consumed()
+    # SpecSeg travels with the checkpoint (the reference re-reads specsegv3_chkpt.h5 instead, :931) and counts as loaded weights
+    assert torch.equal(a.SpecSeg.net.store.flat, b.SpecSeg.net.store.flat) and b.SpecSeg.loaded
+    # host-side state of a bit-reproducible resume: Philox step counter, drop-bit RNG, D call counter, running standardisation scale
+    assert b.step_count == a.step_count == 1 and b._rng.getstate() == a._rng.getstate() and b.D.calls == a.D.calls
+    assert b.stddev_arr.state() == a.stddev_arr.state() and b.noise_seed == a.noise_seed
     assert path == mgr.latest_checkpoint
     for x, y in ((a.G, b.G), (a.D, b.D)):
         sx, sy = x.net.store, y.net.store
         assert torch.equal(sx.flat, sy.flat) and torch.equal(sx.m, sy.m) and torch.equal(sx.v, sy.v) and sx.step == sy.step == 1
     for net in (a, b):
-        net.drop_bits, net.noise_seed, net.step_count = [False, True, False, False, False], 9, 1
-        net.train_step(*batch)
+        net.train_step(*batch)                                     # bits, noise and dropout now come from the restored RNG state
+    assert a.last_drop_bits == b.last_drop_bits
     assert a.total_Generator_loss == pytest.approx(b.total_Generator_loss, rel=1e-5)
     assert a.total_Discriminator_loss == pytest.approx(b.total_Discriminator_loss, rel=1e-5)
     d = (a.G.net.store.flat - b.G.net.store.flat).abs().max()

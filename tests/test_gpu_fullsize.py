@@ -135,7 +135,7 @@ def test_train_step_full_size_batch_independence_and_repeatability():
     from shmgan_b200 import model as M
 
     def fresh(B):
-        net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B), dtype="bf16").build()
+        net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B), dtype="bf16", allow_random_specseg=True).build()
         net.drop_bits, net.TARGET_LABELS, net.noise_seed = [True, False, True, False, False], 0.9, 3
         return net
     g = torch.Generator().manual_seed(15)

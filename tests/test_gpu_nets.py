@@ -6,16 +6,20 @@ Tolerances (BASELINE.json north_star; every number is max|got-want| / max|want| 
     meet 2e-2 in any implementation: the random-init network amplifies a perturbation ~2x per conv block (measured in fp32
     as well: 5e-8 -> 2e-6 over the encoder), so bf16 storage noise reaches ~0.6 % at the output and flips the LeakyReLU branch
     of ~1 % of the pre-activations per layer, each flip changing a local derivative 5x (tools/diag_bf16.py).
-    Every bf16 kernel by itself IS inside 2e-2 on identical inputs (tests/test_gpu_conv.py TC cases, test_gpu_ops.py); here
-    the whole-network bf16 gradients are held to the oracle run with the same storage quantisation points
-    (oracle.bf16_storage) by L2 error and direction (cosine), with the bounds written below."""
+    Every bf16 kernel by itself IS inside 2e-2 on identical inputs (tests/test_gpu_conv.py TC cases, test_gpu_ops.py).  The
+    whole-network bound is therefore DERIVED IN THE TEST, per gradient tensor, from the oracle itself:
+        e_store = rms error of the fp64 oracle run with the device's bf16 storage points (activations AND gradients rounded to bf16,
+                  oracle.bf16_storage_bwd) against the plain fp64 oracle  = what bf16 storage alone costs, in exact arithmetic;
+        device bound:  rms_err(device, plain oracle) <= 1.5 * max(e_store, median e_store) + 2e-2,
+                       1 - cos(device, plain)        <= 2.25 * (1 - cos(stored oracle, plain)) + 1e-3.
+    (Measured: e_store is 0.10-0.35 at these shapes; the old fixed bounds were L2 <= 0.40 / cos >= 0.90.)"""
 from collections import OrderedDict
 
 import pytest
 import torch
 
 import oracle as O
-from _util import F64, bf16_round, dev, rand, randn, rel_err, rms_err
+from _util import F64, bf16_round, derived_bf16_grad_check, dev, rand, randn, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -42,27 +46,21 @@ def _check_fp32_grads(errs: dict, tol):
     assert len(over) <= 2 and all(e <= 2e-2 for e in over.values()), over
 
 
-BF16_GRAD_L2 = 0.40      # L2-relative bound on whole-network bf16 gradients vs the bf16-storage oracle (see module docstring)
-BF16_GRAD_COS = 0.90
-
-
-def _cos(got, want):
-    g, w = got.detach().double().cpu().reshape(-1), want.detach().double().reshape(-1)
-    return float((g @ w) / (g.norm() * w.norm() + 1e-300))
-
-
-def _check_bf16_grads(got: dict, want: dict, dx, dx_want):
-    rows = [("d/dx", rms_err(dx, dx_want), _cos(dx, dx_want))]
-    rows += [(k, rms_err(got[k], w), _cos(got[k], w)) for k, w in want.items() if float(w.abs().max()) > 0]
-    bad = [r for r in rows if r[1] > BF16_GRAD_L2 or r[2] < BF16_GRAD_COS]
-    assert not bad, bad
-    return rows
+def _oracle_grads(fwd, params, x, seeds, q):
+    """fwd(params, x, q) -> tuple of outputs; returns ({name: grad}, d/dx) of sum_i <out_i, seed_i>."""
+    pr = OrderedDict((k, v.clone().requires_grad_(not k.endswith(("in_gamma", "in_beta")))) for k, v in params.items())
+    xr = x.clone().requires_grad_()
+    outs = fwd(pr, xr, q)
+    names = [k for k, v in pr.items() if v.requires_grad]
+    grads = torch.autograd.grad(sum((o * sd).sum() for o, sd in zip(outs, seeds)), [pr[k] for k in names] + [xr])
+    g = dict(zip(names, grads[:-1]))
+    g["d/dx"] = grads[-1]
+    return g
 
 
 def _run_generator(dtype, fs, B, S, tol, tc):
     from shmgan_b200 import nets
     bf = dtype == torch.bfloat16
-    q = O.bf16_storage if bf else None
     p = _params(O.generator_param_specs(fs, True), 1)
     if bf:
         p = OrderedDict((k, bf16_round(v)) for k, v in p.items())
@@ -71,12 +69,9 @@ def _run_generator(dtype, fs, B, S, tol, tc):
     dy = randn((B, S, S, 1), 4)
     if dtype == torch.bfloat16:
         x, mask, dy = bf16_round(x), bf16_round(mask), bf16_round(dy)
-    pr = OrderedDict((k, v.clone().requires_grad_(not k.endswith(("in_gamma", "in_beta")))) for k, v in p.items())
-    xr = x.clone().requires_grad_()
-    y = O.generator_forward(pr, xr, mask.expand(B, S, S, 1), q=q)
-    names = [k for k, v in pr.items() if v.requires_grad]
-    grads = torch.autograd.grad((y * dy).sum(), [pr[k] for k in names] + [xr])
-    want = dict(zip(names, grads[:-1]))
+    fwd = lambda pr, xr, qq: (O.generator_forward(pr, xr, mask.expand(B, S, S, 1), q=qq),)
+    want = _oracle_grads(fwd, p, x, (dy,), None)                       # plain fp64 oracle: the truth in both modes
+    stored = _oracle_grads(fwd, p, x, (dy,), O.bf16_storage_bwd) if bf else None
 
     G = nets.Generator(fs, True, dtype, tensor_core=tc)
     G.store.load(p)
@@ -90,11 +85,13 @@ def _run_generator(dtype, fs, B, S, tol, tc):
     dattn = [torch.zeros_like(f) for f in feats]
     dx = G.backward(tape, dev(dy, dtype), dattn, attn_nb=1, need_dx=True)[..., :10]   # (zero-padded to 64 in tensor-core mode)
     G.attention_backward(saved, dattn)
+    got = dict(G.store.export_grads())
+    got["d/dx"] = dx
     if bf:
-        _check_bf16_grads(G.store.export_grads(), want, dx, grads[-1])
+        derived_bf16_grad_check("generator B=%d S=%d fs=%d" % (B, S, fs), got, want, stored)
         return
-    assert rel_err(dx, grads[-1]) < 2e-2, "generator d/dx"
-    _check_fp32_grads(_grad_errs(G.store.export_grads(), want), tol)
+    assert rel_err(dx, want["d/dx"]) < 2e-2, "generator d/dx"
+    _check_fp32_grads(_grad_errs(got, {k: v for k, v in want.items() if k != "d/dx"}), tol)
 
 
 def test_generator_fp32_parity():
@@ -112,7 +109,6 @@ def test_generator_bf16_tensor_core():
 def _run_discriminator(dtype, fs, B, S, tol, tc):
     from shmgan_b200 import nets
     bf = dtype == torch.bfloat16
-    q = O.bf16_storage if bf else None
     p = _params(O.discriminator_param_specs(S, fs, True), 5)
     if bf:
         p = OrderedDict((k, bf16_round(v)) for k, v in p.items())
@@ -123,12 +119,9 @@ def _run_discriminator(dtype, fs, B, S, tol, tc):
     d_rf, d_cls = randn((B, S // 32, S // 32, 1), 10), randn((B, 5), 11)
     if dtype == torch.bfloat16:
         x, mask, noise = bf16_round(x), bf16_round(mask), bf16_round(noise)
-    pr = OrderedDict((k, v.clone().requires_grad_(not k.endswith(("in_gamma", "in_beta")))) for k, v in p.items())
-    xr = x.clone().requires_grad_()
-    rf, cls = O.discriminator_forward(pr, xr, mask.expand(B, S, S, 1), True, noise, keep, q=q)
-    names = [k for k, v in pr.items() if v.requires_grad]
-    grads = torch.autograd.grad((rf * d_rf).sum() + (cls * d_cls).sum(), [pr[k] for k in names] + [xr])
-    want = dict(zip(names, grads[:-1]))
+    fwd = lambda pr, xr, qq: O.discriminator_forward(pr, xr, mask.expand(B, S, S, 1), True, noise, keep, q=qq)
+    want = _oracle_grads(fwd, p, x, (d_rf, d_cls), None)
+    stored = _oracle_grads(fwd, p, x, (d_rf, d_cls), O.bf16_storage_bwd) if bf else None
 
     D = nets.Discriminator(S, fs, True, dtype, tensor_core=tc)
     D.store.load(p)
@@ -143,16 +136,18 @@ def _run_discriminator(dtype, fs, B, S, tol, tc):
     dattn = torch.zeros_like(attn)
     dx = D.backward(tape, dev(d_rf), dev(d_cls), need_dx=True, dattn=dattn, attn_nb=1)[..., :3]
     D.attention_backward(saved, dattn)
+    got = dict(D.store.export_grads())
+    got["d/dx"] = dx
     if bf:
-        _check_bf16_grads(D.store.export_grads(), want, dx, grads[-1])
+        derived_bf16_grad_check("discriminator B=%d S=%d fs=%d" % (B, S, fs), got, want, stored)
         return
-    assert rel_err(dx, grads[-1]) < 2e-2, "discriminator d/dx"
-    _check_fp32_grads(_grad_errs(D.store.export_grads(), want), tol)
+    assert rel_err(dx, want["d/dx"]) < 2e-2, "discriminator d/dx"
+    _check_fp32_grads(_grad_errs(got, {k: v for k, v in want.items() if k != "d/dx"}), tol)
     # dgrad-only sweep on a sub-batch (the generator-loss path): same d/dx, no weight gradients touched
     before = D.store.grad.clone()
     dx2 = D.backward(tape, dev(d_rf[:1]), dev(d_cls[:1]), n=1, wgrad=False, need_dx=True)
     assert torch.equal(before, D.store.grad)
-    assert rel_err(dx2, grads[-1][:1]) < 2e-2
+    assert rel_err(dx2, want["d/dx"][:1]) < 2e-2
 
 
 def test_discriminator_fp32_parity():

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 import oracle as O
-from _util import F64, bf16_round, dev, rand, randn, rel_err, rms_err
+from _util import F64, bf16_round, derived_bf16_grad_check, dev, rand, randn, rel_err, rms_err
 
 pytestmark = pytest.mark.gpu
 
@@ -134,19 +134,23 @@ def test_train_step_as_written_no_mask():
 
 
 def test_train_step_bf16_runs_and_tracks_oracle():
-    """bf16 / tcgen05 mode: forward quantities within 2e-2 of the plain oracle, loss scalars within 5 %; gradients are checked
-    per kernel elsewhere (see tests/test_gpu_nets.py for why whole-network bf16 gradients get a looser, L2 bound)."""
+    """bf16 / tcgen05 mode: forward quantities within 2e-2 of the plain oracle, loss scalars within 5 %, and EVERY gradient tensor of both
+    networks inside the bound derived in-test from what bf16 storage costs the oracle itself (tests/_util.py::derived_bf16_grad_check)."""
     B, S, fs, bits = 8, 64, 64, [True, False, True, False, False]
     net, Gp, Dp, Sp, origs, noise, keep = _setup("bf16", fs, B, S, bits)
     ds = [O.per_image_standardization(O.rgb_to_yuv(o), True)[0] for o in origs]
     mask = O.specseg_forward(Sp, bf16_round(ds[2][..., 0:1]))
-    L = O.train_step_losses(Gp, Dp, origs, mask, bits, 0.93, (noise[:B], noise[B:]), (keep[:B], keep[B:]), True, True)
+    args = (Gp, Dp, origs, mask, bits, 0.93, (noise[:B], noise[B:]), (keep[:B], keep[B:]), True, True)
+    L, gG, gD = O.train_step_grads(*args, clip=False)
+    _, sG, sD = O.train_step_grads(*args, clip=False, q=O.bf16_storage_bwd)
     net.train_step(*[dev(o) for o in origs])
     assert rel_err(net.specular_candidate, mask) < 2e-2
     assert rel_err(net.gen_Y, L["gen_Y"]) < 2e-2 and rel_err(net.gen_rgb, L["gen_rgb"]) < 2e-2
     for name in SCALARS:
         assert getattr(net, name) == pytest.approx(float(L[name]), rel=5e-2, abs=1e-4), name
     assert torch.isfinite(net.G.net.store.flat).all() and torch.isfinite(net.D.net.store.flat).all()
+    derived_bf16_grad_check("train_step G grads B=%d S=%d fs=%d" % (B, S, fs), net.G.net.store.export_grads(), gG, sG)
+    derived_bf16_grad_check("train_step D grads B=%d S=%d fs=%d" % (B, S, fs), net.D.net.store.export_grads(), gD, sD)
 
 
 def test_inference_step_matches_oracle():
@@ -194,3 +198,80 @@ def test_inference_step_full_width_thin_first_layers():
     ref = net.inference_step(dev(rgb))
     net.G.net.thin = thin
     assert rel_err(got, ref.double().cpu()) < 1e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-3), ("bf16", 2e-2)])
+def test_inference_step_cyclic_matches_restated_test_py(dtype, tol):
+    """inference_step(cyclic=True) = test.py:252-297: five more generator passes whose non-target slots carry the R channel of gen_rgb
+    (Q11), re-joined with the image's own CbCr; and gen_rgb_output (test.py:246-249) scales by the running mean of EVERY standardisation
+    scale seen so far (self.stddev_arr is never cleared), checked over two consecutive calls."""
+    from shmgan_b200 import model as M
+    B, S, fs = 2, 64, 16
+    net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B, filter_size=fs), dtype=dtype).build()
+    Gp = O.init_params(O.generator_param_specs(fs, True), 1, F64, randomize_all=True)
+    Sp = O.init_params(O.specseg_param_specs(), 3, F64, randomize_all=True)
+    for k in Sp:
+        if k.endswith(".var"):
+            Sp[k] = Sp[k].abs() + 0.5
+    if dtype == "bf16":
+        Gp, Sp = (OrderedDict((k, bf16_round(v)) for k, v in d.items()) for d in (Gp, Sp))
+    net.G.net.store.load(Gp); net.SpecSeg.load(Sp)
+    history = []
+    for call, seed in enumerate((32, 33)):
+        rgb = rand((B, S, S, 3), seed) * (1.0 if call == 0 else 0.4)      # a darker second batch: its scales differ from the first
+        want = O.inference_step(Gp, Sp, rgb, cyclic=True, stddev_history=history)
+        history.append(want["scale"])
+        got = net.inference_step(dev(rgb), cyclic=True)
+        assert rel_err(got, want["gen_rgb"]) < tol
+        names = ["cyc_gen0_rgb", "cyc_gen45_rgb", "cyc_gen90_rgb", "cyc_gen135_rgb", "cyc_genED_rgb"]
+        for k in range(5):
+            assert rel_err(getattr(net, names[k]), want["cyc_rgb"][k]) < tol, names[k]
+            assert rel_err(net.cyc_rgb[k], want["cyc_rgb"][k]) < tol
+        assert rel_err(net.gen_rgb_output, want["gen_rgb_output"]) < tol
+        assert net.stddev_arr.mean() == pytest.approx(float(torch.cat([h.reshape(-1) for h in history]).mean()), rel=1e-5)
+
+
+def test_train_step_publishes_gen_rgb_output_and_lazy_losses():
+    """gen_rgb_output (:548-551) = yuv_to_rgb(gen_YCbCr * mean(stddev_arr) * 255) over the five per-image scales of every step so far; the loss
+    scalars are read back on first access (no host synchronisation inside train_step) and a step's scalars replace the previous step's."""
+    B, S, fs, bits = 2, 64, 8, [False, True, False, False, False]
+    net, Gp, Dp, Sp, origs, noise, keep = _setup("fp32", fs, B, S, bits)
+    scales = torch.stack([O.per_image_standardization(O.rgb_to_yuv(o), True)[1].reshape(-1) for o in origs])
+    net.train_step(*[dev(o) for o in origs])
+    assert net._pending_losses is not None and "total_Generator_loss" not in net.__dict__      # not read back yet
+    want = net.gen_rgb.double().cpu() * float(scales.mean()) * 255.0
+    assert rel_err(net.gen_rgb_output, want) < 1e-5
+    first = net.total_Generator_loss
+    assert net._pending_losses is None and first == net.__dict__["total_Generator_loss"]
+    net.train_step(*[dev(o) for o in origs])
+    assert "total_Generator_loss" not in net.__dict__ and net.total_Generator_loss != first    # weights moved: a new value
+    assert len(net.stddev_arr) == 10 * B                                                       # 5 images x B samples x 2 steps
+
+
+def test_random_specseg_weights_must_be_asked_for():
+    """The reference cannot run without specsegv3_chkpt.h5 (:930-931): a live-mask step on SpecSeg's random initialisers is refused unless the
+    caller opts in; loading weights (any of the importers) or a checkpoint that holds SpecSeg lifts the refusal."""
+    from shmgan_b200 import model as M
+    from shmgan_b200.keras_names import specseg_keras_names
+    B, S, fs = 1, 64, 8
+    rgb = dev(rand((B, S, S, 3), 40))
+    net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B, filter_size=fs), dtype="fp32").build()
+    with pytest.raises(RuntimeError, match="SpecSeg"):
+        net.inference_step(rgb)
+    with pytest.raises(RuntimeError, match="SpecSeg"):
+        net.train_step(rgb, rgb, rgb, rgb, rgb)
+    M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B, filter_size=fs), dtype="fp32", live_mask=False).build().inference_step(rgb)
+    M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B, filter_size=fs), dtype="fp32", allow_random_specseg=True).build().inference_step(rgb)
+    # Keras get_weights() order -> named parameters
+    Sp = O.init_params(O.specseg_param_specs(), 3, F64, randomize_all=True)
+    for k in Sp:
+        if k.endswith(".var"):
+            Sp[k] = Sp[k].abs() + 0.5
+    assert list(Sp) == list(specseg_keras_names())
+    net.SpecSeg.load_keras_weights([v.numpy() for v in Sp.values()])
+    assert net.SpecSeg.loaded
+    got = net.inference_step(rgb)
+    Gp = {k: v.double() for k, v in net.G.net.store.export().items()}
+    assert rel_err(got, O.inference_step(Gp, Sp, rgb.double().cpu())["gen_rgb"]) < 1e-3
+    with pytest.raises(ValueError):
+        net.SpecSeg.load_keras_weights([v.numpy() for v in Sp.values()][:-1])

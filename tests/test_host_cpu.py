@@ -148,3 +148,66 @@ def test_data_parallel_average_equals_global_batch_gloo_world2():
         assert p.exitcode == 0
     got = dict(q.get() for _ in range(2))
     assert got == {0: True, 1: True}
+
+
+def _range_worker(rank, world, port, out):
+    """The generator's gradient buffer is reduced range by range while the backward runs (decoder levels, bottleneck, then the head):
+    the ranges must tile the buffer and the result must equal one whole-buffer reduction."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from shmgan_b200.parallel import GradReducer
+        g = torch.Generator().manual_seed(rank)
+        flat = torch.randn(10_000, generator=g, dtype=torch.float64)
+        mine = flat.clone()
+        red = GradReducer(None, bucket_mb=0.004)                       # 1048-element buckets: several per range
+        for lo, hi in ((7000, 10_000), (5200, 7000), (4000, 5200), (0, 4000)):
+            red.reduce_async(flat, lo, hi)
+        red.wait()
+        both = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(both, mine)
+        out.put((rank, bool(torch.equal(flat, both[0] + both[1])) and red.bytes_reduced == 8 * 10_000))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ranged_bucket_reduce_covers_buffer_gloo_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_range_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    assert dict(q.get() for _ in range(2)) == {0: True, 1: True}
+
+
+def test_generator_grad_ranges_tile_the_flat_buffer():
+    """Generator.grad_range (the ranges the overlapped all-reduce uses) from the parameter inventory alone: decoder levels 3..0, bottleneck,
+    head -- contiguous, disjoint, covering exactly the trainable prefix, each range holding exactly the layers whose gradients are final."""
+    from shmgan_b200 import nets
+
+    class _Store:                                                      # ParamStore's offset rule without device buffers
+        def __init__(self, specs):
+            order = [s for s in specs if nets._is_trainable(s[0])] + [s for s in specs if not nets._is_trainable(s[0])]
+            self.offsets, off = {}, 0
+            for name, shape, _ in order:
+                n = math.prod(shape)
+                self.offsets[name] = (off, n, shape)
+                off += (n + 3) // 4 * 4
+                if nets._is_trainable(name):
+                    self.n_train = off
+
+    import math
+    fake = type("G", (), {"store": _Store(nets.generator_specs(64, True)), "grad_range": nets.Generator.grad_range})()
+    ranges = [fake.grad_range(("dec", u)) for u in (3, 2, 1, 0)] + [fake.grad_range("bott"), fake.grad_range("head")]
+    assert ranges[0][1] == fake.store.n_train and ranges[-1][0] == 0
+    for (lo, hi), (lo2, hi2) in zip(ranges[1:], ranges[:-1]):
+        assert hi == lo2 and lo < hi                                   # each range ends where the previous (later-layer) one starts
+    off = fake.store.offsets
+    lo, hi = fake.grad_range(("dec", 3))
+    assert lo == off["up4T.w"][0] and off["out.b"][0] + 4 == hi        # the output layer rides with the last decoder level
+    lo, hi = fake.grad_range("head")
+    assert all(lo <= off[k][0] < hi for k in ("enc1a.w", "attn4b.b", "enc4b.b")) and off["bott1.w"][0] == hi

@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 import torch
 from shmgan_b200 import model as M, _lib
 B, S = 16, 256
-net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B), dtype="bf16").build()
+net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B), dtype="bf16", allow_random_specseg=True).build()
 g = torch.Generator(device="cuda").manual_seed(1)
 pol = [torch.rand((B, S, S, 3), generator=g, device="cuda") for _ in range(4)]
 inp = pol + [net.calculate_estimate_diffuse(*pol)]
