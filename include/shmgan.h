@@ -60,6 +60,12 @@ int shm_conv2d_tc_supported(const shm_conv_desc* d, int for_dgrad);   /* 1 if th
 /* cin_real (0 = d->Cin): the Keras kernel holds only cin_real < d->Cin input channels; the rest of the bf16 copy is zero (the layer
  * then reads a zero-padded 64-channel input, see shm_pad_channels64) */
 int shm_conv2d_tc_prep_weights(const shm_conv_desc* d, const float* w, int cin_real, void* w_tc, int for_dgrad, void* stream);
+/* Forward + instance-norm statistics in ONE kernel ("IN stats fused into the producing conv's epilogue"; the Conv -> LeakyReLU ->
+ * InstanceNormalization blocks of ShmGANwithSSpecSeg.py:244-245, :386-389): stats[n][c] = (sum, sum of squares) over the pixels of image n of
+ * the bf16 values stored to y, ADDED to the caller's zero-initialised fp64 buffer [N][Cout][2] -- exactly what shm_inorm_stats(y) returns,
+ * without reading y back.  shm_conv2d_tc_stats_supported: 1 if the kernel serving this layer has the statistics epilogue. */
+int shm_conv2d_tc_stats_supported(const shm_conv_desc* d);
+int shm_conv2d_tc_fwd_stats(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, double* stats, void* stream);
 /* which tcgen05 kernel serves the layer (accounting only): pass 0 fwd, 1 dgrad, 2 wgrad -> 0 conv_tc, 1 conv_halo, 2 conv_multi (big),
  * 3 conv_multi (stride-2 scatter), 4 wgrad_tc, 5 wgrad_halo<0>, 6 wgrad_halo<1>, 7 wgrad_s2<0>, 8 wgrad_s2<1>; -1 = not servable */
 int shm_conv2d_tc_route(const shm_conv_desc* d, int pass);

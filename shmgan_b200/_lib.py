@@ -44,6 +44,8 @@ _SIG = {
     "shm_conv2d_tc_prep_multi": [_P, _I, _I, _P],
     "shm_conv2d_tc_fwd": [_D, _P, _P, _P, _P, _P],
     "shm_conv2d_tc_fwd_cols": [_D, _P, _P, _P, _P, _I, _P],
+    "shm_conv2d_tc_fwd_stats": [_D, _P, _P, _P, _P, _P, _P],
+    "shm_conv2d_tc_stats_supported": [_D],
     "shm_conv2d_tc_dgrad": [_D, _P, _P, _P, _P],
     "shm_conv2d_tc_wgrad": [_D, _P, _P, _P, _P],
     "shm_colsum": [_P, _L, _I, _I, _I, _P, _P],
@@ -111,7 +113,7 @@ _SIG = {
 }
 _RET = {"shm_last_error": C.c_char_p, "shm_conv2d_tc_weight_elems": C.c_int64, "shm_ssim_map_elems": C.c_int64}
 # functions whose int return is a value, not a status
-_VALUE = {"shm_conv2d_tc_route", "shm_conv2d_tc_supported", "shm_version", "shm_sm_count", "shm_conv2d_tc_weight_elems", "shm_ssim_map_elems",
+_VALUE = {"shm_conv2d_tc_route", "shm_conv2d_tc_supported", "shm_conv2d_tc_stats_supported", "shm_version", "shm_sm_count", "shm_conv2d_tc_weight_elems", "shm_ssim_map_elems",
           "shm_conv2d_tc_prep_job_bytes", "shm_conv2d_tc_prep_jobs_finalize",
           "shm_last_error"}
 

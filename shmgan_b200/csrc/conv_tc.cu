@@ -263,6 +263,109 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, const float* sbias, int 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Instance-norm statistics produced by the convolution epilogue (SURVEY 2b "IN stats fused into the producing conv's epilogue").
+//
+// Every Conv -> LeakyReLU -> InstanceNorm block of the reference (ShmGANwithSSpecSeg.py:244-245, :386-389) needs sum / sum of squares per
+// (image, channel) of the tensor the epilogue is about to store; computing them here removes one full HBM read of every such tensor
+// (in_stats_p).  A thread owns one pixel row of the accumulator, so the per-channel sums are COLUMN sums over the 32 lanes of a warp:
+// a recursive-halving butterfly (lanes trade the half they do not keep: 16 + 8 + 4 + 2 + 1 = 31 shuffles per 32 x 32 block) leaves
+// column L's total in lane L -- shuffles use the lane crossbar only and do not compete with the tensor core for shared-memory banks.
+// The statistics are taken from the bf16-ROUNDED values (exactly what in_stats_p would read back), accumulated in fp32 registers over
+// the consecutive tiles a CTA handles of one image (the tile order of a statistics launch is contiguous per CTA for that reason) and
+// flushed with one fp64 atomic per (image, channel, moment) when the image or the column block changes.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int h = 16; h >= 1; h >>= 1) {
+        const bool up = (lane & h) != 0;
+#pragma unroll
+        for (int j = 0; j < h; ++j) {
+            const float send = up ? v[j] : v[j + h];
+            const float keep = up ? v[j + h] : v[j];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, h);
+        }
+    }
+    return v[0];
+}
+
+template <int NC>                      // 32-column chunks of one accumulator row
+struct EpiStats {
+    float s[NC], q[NC];
+    int img, col0;                     // owner of the running sums: image and first column (-1: none)
+    __device__ __forceinline__ void init() {
+        img = -1; col0 = 0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) { s[c] = 0.f; q[c] = 0.f; }
+    }
+    __device__ __forceinline__ void flush(double* __restrict__ stats, int Nn, int lane) {
+        if (img >= 0) {
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                double* d = stats + ((long long)img * Nn + col0 + c * 32 + lane) * 2;
+                atomicAdd(d, (double)s[c]);
+                atomicAdd(d + 1, (double)q[c]);
+                s[c] = 0.f; q[c] = 0.f;
+            }
+        }
+    }
+    // warp-uniform: makes (image, column block) the owner of the running sums
+    __device__ __forceinline__ void own(double* __restrict__ stats, int Nn, int nimg, int ncol0, int lane) {
+        if (nimg != img || ncol0 != col0) { flush(stats, Nn, lane); img = nimg; col0 = ncol0; }
+    }
+    // pk: the 32 packed bf16 this lane is about to store for chunk c (ok = the lane's pixel exists)
+    template <int NV = 32>
+    __device__ __forceinline__ void add(int c, const uint4* pk, bool ok, int lane) {
+        float v[32], w[32];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (i * 8 < NV) {
+                const uint32_t u[4] = {pk[i].x, pk[i].y, pk[i].z, pk[i].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[i * 8 + 2 * k] = ok ? __uint_as_float(u[k] << 16) : 0.f;
+                    v[i * 8 + 2 * k + 1] = ok ? __uint_as_float(u[k] & 0xffff0000u) : 0.f;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[i * 8 + k] = 0.f;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = v[j] * v[j];
+        s[c] += warp_colsum32(v, lane);
+        q[c] += warp_colsum32(w, lane);
+    }
+};
+
+// epi_row with optional statistics: the same TMEM -> bias -> activation -> bf16 -> global pipeline, through the packed form
+template <int NC>
+__device__ __forceinline__ void epi_row_stats(uint32_t taddr, const float* sbias, int act, bf16* __restrict__ dst, bool ok, EpiStats<NC>& st, int lane) {
+    uint32_t r[2][32];
+    tmem_ld32_nw(taddr, r[0]);
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        tmem_wait_ld32(r[c & 1]);
+        if (c + 1 < NC) tmem_ld32_nw(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
+        uint4 pk[4];
+        epi_pack<32>(r[c & 1], sbias ? sbias + c * 32 : nullptr, act, pk);
+        if (ok) {
+            uint4* g = reinterpret_cast<uint4*>(dst + c * 32);
+            g[0] = pk[0]; g[1] = pk[1]; g[2] = pk[2]; g[3] = pk[3];
+        }
+        st.add(c, pk, ok, lane);
+    }
+}
+
+// contiguous share of `total` work items for this CTA (statistics launches), or the strided order (everything else)
+__device__ __forceinline__ void tile_walk(int total, bool contig, int& first, int& end, int& step) {
+    if (contig) {
+        first = (int)((long long)total * blockIdx.x / gridDim.x);
+        end = (int)((long long)total * (blockIdx.x + 1) / gridDim.x);
+        step = 1;
+    } else { first = blockIdx.x; end = total; step = gridDim.x; }
+}
+
 // copies the layer's bias vector into shared memory (all threads of the CTA; call before the first __syncthreads)
 __device__ __forceinline__ void stage_bias(float* sbias, const float* __restrict__ bias, int n) {
     if (bias != nullptr)
@@ -283,7 +386,7 @@ struct TcParams {
     int Hout, Wout, OS, py, px, ldout, Nn;
     const float* bias; int act;
     bf16* out;
-    float* stats;                // optional [Nimg][Nn][2] fp32 (sum, sumsq) of the stored activations
+    double* stats;               // optional [Nimg][Nn][2] fp64 (sum, sum of squares) of the stored activations: instance-norm statistics
 };
 
 constexpr int TC_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
@@ -317,6 +420,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int niter = p.ntaps * p.kchunks;
+    int tile_first, tile_end, tile_step;
+    tile_walk(total_tiles, p.stats != nullptr, tile_first, tile_end, tile_step);
     stage_bias(sbias, p.bias, p.Nn);
 
     if (warp == 0 && lane == 0) {
@@ -335,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== TMA producer (warp-uniform loop, one elected lane issues) =====
         {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
                 const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
                 const int per_img = p.tiles_x * p.tiles_y;
                 int img0, qy0, qx0;
@@ -361,7 +466,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
         int stage = 0; uint32_t phase = 0;
         int local = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        for (int tile = tile_first; tile < tile_end; tile += tile_step, ++local) {
             const int as = local & 1;
             mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -387,8 +492,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== epilogue: TMEM -> registers -> bias + activation -> bf16 -> global =====
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;             // accumulator row = lattice point within the tile
+        EpiStats<BN / 32> st;
+        st.init();
         int local = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+        for (int tile = tile_first; tile < tile_end; tile += tile_step, ++local) {
             const int as = local & 1;
             const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
             const int per_img = p.tiles_x * p.tiles_y;
@@ -403,11 +510,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bf16* dst = p.out + ((long long)(img * p.Hout + oy) * p.Wout + ox) * p.ldout + nt * BN;
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
-            epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN), p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+            if (p.stats != nullptr) {
+                // the host only asks for statistics when the 32 rows of a warp lie in ONE image (BW * BH a multiple of 32)
+                st.own(p.stats, p.Nn, __shfl_sync(0xffffffffu, img, 0), nt * BN, lane);
+                epi_row_stats<BN / 32>(taddr, p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok, st, lane);
+            } else {
+                epi_row<BN / 32>(taddr, p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
         }
+        if (p.stats != nullptr) st.flush(p.stats, p.Nn, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -438,6 +553,7 @@ struct HaloParams {
     int H, W, ldout, Nn;
     const float* bias; int act;
     bf16* out;
+    double* stats;                   // optional instance-norm statistics [N][Nn][2] (see EpiStats)
 };
 
 // CPX = bytes of one pixel row of the A operand = 2 x (reduction channels per k-chunk): 128 (64 channels, SWIZZLE_128B) for the
@@ -503,6 +619,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_img = p.tiles_x * p.tiles_y;
+    int tile_first, tile_end, tile_step;
+    tile_walk(p.total_tiles, p.stats != nullptr, tile_first, tile_end, tile_step);
     stage_bias(sbias, p.bias, BN);
 
     if (warp == 0 && lane == 0) {
@@ -530,7 +648,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             __syncwarp();
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int tile = tile_first; tile < tile_end; tile += tile_step) {
                 const int img = tile / per_img; const int r = tile - img * per_img;
                 const int y0 = (r / p.tiles_x) * (16 * T) + p.oy, x0 = (r % p.tiles_x) * 8 + p.ox;
                 for (int kc = 0; kc < KC; ++kc) {
@@ -549,7 +667,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(wbar, 0);
         int stage = 0; uint32_t phase = 0;
         int local = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        for (int tile = tile_first; tile < tile_end; tile += tile_step, ++local) {
             const int as = local & 1;
             mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
             tc_fence_after();
@@ -584,7 +702,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ty = row >> 3, tx = row & 7;
         int local = 0;
         uint32_t nstore = 0;                              // sub-tiles this epilogue group has handed to the TMA engine
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+        constexpr int SNC = BN >= 32 ? BN / 32 : 1;       // statistics (BN >= 32 only: every layer followed by an instance norm has >= 64 columns)
+        EpiStats<SNC> st;
+        st.init();
+        for (int tile = tile_first; tile < tile_end; tile += tile_step, ++local) {
             const int as = local & 1;
             const int img = tile / per_img; const int r = tile - img * per_img;
             const int y0t = (r / p.tiles_x) * (16 * T), x0t = (r % p.tiles_x) * 8;
@@ -643,6 +764,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     ++nstore;
                 }
+                if constexpr (BN >= 32) {
+                    if (p.stats != nullptr) {
+                        st.own(p.stats, BN, img, 0, lane);
+#pragma unroll
+                        for (int jj = 0; jj < TJ; ++jj)
+#pragma unroll
+                            for (int c = 0; c < SNC; ++c) st.add(c, pk[jj] + c * 4, true, lane);
+                    }
+                }
             } else {
                 const int oy = y0t + ty, ox = x0t + tx;
                 bf16* dst = p.out + ((long long)(img * p.H + oy) * p.W + ox) * p.ldout;
@@ -681,14 +811,27 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int c = 0; c < NC; ++c) tmem_ld32_nw(taddr + (uint32_t)(c * 32), r[c]);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) tmem_wait_ld32(r[c]);
+                    if (p.stats != nullptr) {
+                        st.own(p.stats, BN, img, 0, lane);
 #pragma unroll
-                    for (int c = 0; c < NC; ++c) epi_store32(r[c], p.bias ? sbias + c * 32 : nullptr, p.act, dst + c * 32, true);
+                        for (int c = 0; c < NC; ++c) {
+                            uint4 pk4[4];
+                            epi_pack<32>(r[c], p.bias ? sbias + c * 32 : nullptr, p.act, pk4);
+                            uint4* g = reinterpret_cast<uint4*>(dst + c * 32);
+                            g[0] = pk4[0]; g[1] = pk4[1]; g[2] = pk4[2]; g[3] = pk4[3];
+                            st.add(c, pk4, true, lane);
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < NC; ++c) epi_store32(r[c], p.bias ? sbias + c * 32 : nullptr, p.act, dst + c * 32, true);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty[as]);
             }
         }
+        if (p.stats != nullptr) st.flush(p.stats, BN, lane);
         if (Cfg::TSTORE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every bulk store of this thread has completed
         (void)nstore; (void)ty; (void)tx;
     }
@@ -727,6 +870,7 @@ struct MultiParams {
     int nstore;                               // output channels that exist in `out` (<= Nn; the rest are zero-padding columns)
     const float* bias; int act;
     bf16* out;
+    double* stats;                            // optional instance-norm statistics [N][n_tiles * BN][2] ("big" configuration only)
 };
 
 template <int BN, int NBUF, int NPAIR>
@@ -751,6 +895,8 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int total = p.m_tiles * p.n_tiles;
     const int per_img = p.tiles_x * p.tiles_y;
     const int set_cols = p.nacc * BN;
+    int item_first, item_end, item_step;
+    tile_walk(total, p.stats != nullptr, item_first, item_end, item_step);
     stage_bias(sbias, p.bias, p.n_tiles * BN);
 
     if (warp == 0 && lane == 0) {
@@ -769,7 +915,7 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 0) {
         {
             int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
-            for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            for (int item = item_first; item < item_end; item += item_step) {
                 const int nt = item % p.n_tiles, mt = item / p.n_tiles;
                 const int img = mt / per_img; const int r = mt - img * per_img;
                 const int y0 = (r / p.tiles_x) * p.TH + p.hy, x0 = (r % p.tiles_x) * 8 + p.hx;
@@ -797,7 +943,7 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
         int local = 0;
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++local) {
+        for (int item = item_first; item < item_end; item += item_step, ++local) {
             const int as = local % NBUF;
             mbar_wait(&tempty[as], ((local / NBUF) & 1) ^ 1);
             tc_fence_after();
@@ -841,8 +987,10 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int ty = row >> 3, tx = row & 7;
+        EpiStats<BN / 32> st;
+        st.init();
         int local = 0;
-        for (int item = blockIdx.x; item < total; item += gridDim.x, ++local) {
+        for (int item = item_first; item < item_end; item += item_step, ++local) {
             const int as = local % NBUF;
             const int nt = item % p.n_tiles, mt = item / p.n_tiles;
             const int img = mt / per_img; const int r = mt - img * per_img;
@@ -854,13 +1002,19 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int oy = (qy + p.row_dy[a]) * p.OS + p.py[a], ox = qx * p.OS + p.px[a];
                 const bool ok = oy < p.Hout && ox < p.Wout;
                 bf16* dst = p.out + ((long long)(img * p.Hout + oy) * p.Wout + ox) * p.ldout + nt * BN;
-                epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN), p.bias ? sbias + nt * BN : nullptr,
-                                 p.act, dst, ok, p.nstore - nt * BN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN);
+                if (p.stats != nullptr) {
+                    st.own(p.stats, p.n_tiles * BN, img, nt * BN, lane);
+                    epi_row_stats<BN / 32>(taddr, p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok, st, lane);
+                } else {
+                    epi_row<BN / 32>(taddr, p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok, p.nstore - nt * BN);
+                }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
         }
+        if (p.stats != nullptr) st.flush(p.stats, p.n_tiles * BN, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -942,9 +1096,11 @@ struct Geometry {
 };
 
 int launch_tc(const Geometry& g, int N, const void* in, const void* w_tc, int wrows_total, const float* bias, int act, void* out,
-              const int* tdy, const int* tdx, const int* twrow, int ntaps, int py, int px, cudaStream_t st) {
+              const int* tdy, const int* tdx, const int* twrow, int ntaps, int py, int px, cudaStream_t st, double* stats = nullptr) {
     TcParams p{};
     if (!pick_box(N, g.Qh, g.Qw, p.BW, p.BH, p.BI)) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: lattice %dx%d (N=%d) does not tile into 128-point boxes", g.Qh, g.Qw, N);
+    if (stats != nullptr && !(p.BI == 1 || (p.BW * p.BH) % 32 == 0))
+        SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: fused statistics need >= 32 lattice points per image (%dx%d)", g.Qh, g.Qw);
     p.ntaps = ntaps;
     for (int t = 0; t < ntaps; ++t) { p.dy[t] = tdy[t]; p.dx[t] = tdx[t]; p.wrow[t] = twrow[t]; }
     p.kchunks = g.K / 64;
@@ -954,7 +1110,7 @@ int launch_tc(const Geometry& g, int N, const void* in, const void* w_tc, int wr
     const int BN = (g.Nn % 128 == 0) ? 128 : 64;
     p.n_tiles = g.Nn / BN;
     p.Hout = g.Hout; p.Wout = g.Wout; p.OS = g.OS; p.py = py; p.px = px; p.ldout = g.ldout; p.Nn = g.Nn;
-    p.bias = bias; p.act = act; p.out = (bf16*)out; p.stats = nullptr;
+    p.bias = bias; p.act = act; p.out = (bf16*)out; p.stats = stats;
     CUtensorMap tmA, tmB;
     if (int rc = encode_act(&tmA, in, g.K, g.Win, g.Hin, N, g.ldin, p.BW, p.BH, p.BI, g.IS)) return rc;
     if (int rc = encode_w(&tmB, w_tc, g.K, wrows_total, BN)) return rc;
@@ -1014,7 +1170,7 @@ bool big_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
 }
 
 int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
-               void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st) {
+               void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st, double* stats = nullptr) {
     MultiParams p{};
     int miny = 9, minx = 9;
     for (int t = 0; t < 9; ++t) { if (tdy[t] < miny) miny = tdy[t]; if (tdx[t] < minx) minx = tdx[t]; }
@@ -1033,7 +1189,7 @@ int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, con
     p.tiles_x = W / 8; p.tiles_y = H / 32;
     p.m_tiles = N * p.tiles_x * p.tiles_y; p.n_tiles = Nn / 128;
     p.nstore = Nn;
-    p.Hout = H; p.Wout = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
+    p.Hout = H; p.Wout = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out; p.stats = stats;
     CUtensorMap tmA, tmB;
     if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, BIG_H)) return rc;
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 128)) return rc;
@@ -1117,9 +1273,18 @@ int launch_thin(const CUtensorMap& tmA1, const CUtensorMap& tmAT, const CUtensor
 }
 
 // in: [N,H,W,K] (ld ldin), out: [N,H,W,Nn] (ld ldout); taps (tdy, tdx) in {-1,0,1} with weight rows twrow
+// which halo-kernel variants carry the statistics epilogue: every one with >= 32 output columns except the stacked (T = 2) 128-column thin variant
+bool halo_stats_ok(int H, int K, int Nn) {
+    if (Nn < 32) return false;
+    if (K < 64 && Nn == 128 && H % 32 == 0) return false;
+    return true;
+}
+
 int launch_halo(int N, int H, int W, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
-                void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st) {
+                void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st, double* stats = nullptr) {
     HaloParams p{};
+    if (stats != nullptr && !halo_stats_ok(H, K, Nn)) SHM_FAIL(SHM_EUNSUPPORTED, "conv_halo: this variant (K=%d, Nn=%d) has no statistics epilogue", K, Nn);
+    p.stats = stats;
     int miny = 9, minx = 9;
     for (int t = 0; t < 9; ++t) { if (tdy[t] < miny) miny = tdy[t]; if (tdx[t] < minx) minx = tdx[t]; }
     for (int t = 0; t < 9; ++t) {
@@ -1969,15 +2134,35 @@ extern "C" int shm_conv2d_tc_route(const shm_conv_desc* d, int pass) {
 }
 
 // forward: Conv2D (gather form) or Conv2DTranspose (scatter-by-parity form, 4 launches)
-static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream);
+static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream, double* stats = nullptr);
 extern "C" int shm_conv2d_tc_fwd(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, void* stream) {
     return tc_fwd_impl(d, x, w_tc, bias, y, 0, stream);
+}
+// forward + instance-norm statistics of the stored output in the same kernel: stats[n][c] = (sum, sum of squares) over the pixels of image n,
+// ADDED to the caller's (zeroed) fp64 buffer -- what shm_inorm_stats would compute from y, without reading y back
+extern "C" int shm_conv2d_tc_fwd_stats(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, double* stats, void* stream) {
+    SHM_REQUIRE(stats != nullptr, "shm_conv2d_tc_fwd_stats: stats is NULL");
+    if (!shm_conv2d_tc_stats_supported(d)) SHM_FAIL(SHM_EUNSUPPORTED, "shm_conv2d_tc_fwd_stats: no statistics epilogue for this layer (ask shm_conv2d_tc_stats_supported)");
+    return tc_fwd_impl(d, x, w_tc, bias, y, 0, stream, stats);
+}
+extern "C" int shm_conv2d_tc_stats_supported(const shm_conv_desc* d) {
+    if (tc_check(d) != SHM_OK || d->transposed) return 0;
+    if (!shm_conv2d_tc_supported(d, 0)) return 0;
+    const int s = d->stride;
+    if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s) || thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
+        return halo_stats_ok(d->H, d->Cin, d->Cout) ? 1 : 0;
+    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) return 0;
+    if (big_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s)) return 1;
+    int Ho, Wo; out_dims(d, Ho, Wo);
+    int BW, BH, BI;
+    if (!pick_box(d->N, Ho, Wo, BW, BH, BI)) return 0;
+    return (BI == 1 || (BW * BH) % 32 == 0) ? 1 : 0;
 }
 extern "C" int shm_conv2d_tc_fwd_cols(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream) {
     SHM_REQUIRE(d && nstore > 0 && nstore <= d->Cout && nstore % 8 == 0, "shm_conv2d_tc_fwd_cols: nstore must be a multiple of 8 in (0, Cout]");
     return tc_fwd_impl(d, x, w_tc, bias, y, nstore, stream);
 }
-static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream) {
+static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream, double* stats) {
     if (int rc = tc_check(d)) return rc;
     SHM_REQUIRE(x && w_tc && y, "shm_conv2d_tc_fwd: NULL buffer");
     if (nstore > 0 && nstore < d->Cout && !(d->transposed && d->stride == 2 && scatter_ok(d->H, d->W, d->Cin, d->Cout)))
@@ -1994,13 +2179,14 @@ static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, 
         for (int ky = 0; ky < d->kh; ++ky)
             for (int kx = 0; kx < d->kw; ++kx) { tdy[nt] = ky - pby; tdx[nt] = kx - pbx; twr[nt] = (ky * d->kw + kx) * d->Cout; ++nt; }
         if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s) || thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
-            return launch_halo(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st);
+            return launch_halo(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st, stats);
         if (d->Cin % 64 != 0 || d->Cout % 64 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc fwd: thin layer %d -> %d not servable", d->Cin, d->Cout);
         if (big_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
-            return launch_big(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st);
+            return launch_big(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st, stats);
         Geometry g{d->H, d->W, d->ldx, d->Cin, Ho, Wo, s, Ho, Wo, d->ldy, d->Cout, 1};
-        return launch_tc(g, d->N, x, w_tc, wrows, bias, d->act, y, tdy, tdx, twr, nt, 0, 0, st);
+        return launch_tc(g, d->N, x, w_tc, wrows, bias, d->act, y, tdy, tdx, twr, nt, 0, 0, st, stats);
     }
+    if (stats != nullptr) SHM_FAIL(SHM_EUNSUPPORTED, "shm_conv2d_tc_fwd_stats: transposed convolutions have no statistics epilogue");
     // transposed: out[p] = sum_{o,k: s*o + k - pb = p} x[o] W[k];  p = s*q + r
     const int pby = same_pad_before(Ho, d->kh, s), pbx = same_pad_before(Wo, d->kw, s);
     if (s == 2 && scatter_ok(d->H, d->W, d->Cin, d->Cout)) {

@@ -214,12 +214,18 @@ class ParamStore:
         self.grad.zero_()
         for c in self.padded_convs:
             c.zero_pad_grad()
+        self._finalized = False
 
     def finalize_grads(self):
-        """Copies the weight gradients of the zero-padded first layers from their 64-channel scratch into the flat buffer
-        (idempotent; call once the backward sweeps are done, before the all-reduce / clip / Adam)."""
+        """Copies the weight gradients of the zero-padded first layers from their 64-channel scratch into the flat buffer.  Runs ONCE per
+        zero_grad(): call it when the backward sweeps are done, before the all-reduce / clip / Adam.  (A second fold after the data-parallel
+        all-reduce would overwrite the reduced gradients of those layers with the rank-local ones: the ranks' first layers drifted apart in
+        round 1 -- caught by tests/test_gpu_data_parallel.py.)"""
+        if getattr(self, "_finalized", False):
+            return
         for c in self.padded_convs:
             c.fold_pad_grad()
+        self._finalized = True
 
     def adam_step(self, lr0=2e-5, beta1=0.5, beta2=0.99, eps=1e-7, clip=1.0, gscale=1.0,
                   decay_steps=10000.0, decay_rate=0.95):
@@ -298,8 +304,8 @@ class Generator:
             return 16
         return 64 if (self.pad_in and c.can_pad(n, h, w)) else 10
 
-    def _conv(self, c: Conv, x, y=None):
-        return c.fwd(x, y, self.tc, self.store.version)
+    def _conv(self, c: Conv, x, y=None, stats=False):
+        return c.fwd(x, y, self.tc, self.store.version, want_stats=stats)
 
     def attention(self, mask: torch.Tensor, infer: bool = False):
         """attention_layer on a live mask: level 1 un-pooled, then MaxPool2 chain; 2 x [Conv3x3 + LeakyReLU] per level.
@@ -354,14 +360,13 @@ class Generator:
         for lvl in range(4):
             a, b = self.enc[lvl]
             C = a.conv.cout
+            # instance-norm statistics come out of the convolution's epilogue (no separate read of z)
             if lvl == 0 and x.shape[-1] == 16:
-                za = self.thin["enc1a"].fwd(h, None, True, self.store.version)
+                za, sa = self.thin["enc1a"].fwd(h, None, True, self.store.version, want_stats=True)
             else:
-                za = self._conv(a.conv, h)
-            sa = ops.inorm_stats(za)
+                za, sa = self._conv(a.conv, h, stats=True)
             ya, _ = ops.inorm_apply(za, sa, a.gamma, a.beta)
-            zb = self._conv(b.conv, ya)
-            sb = ops.inorm_stats(zb)
+            zb, sb = self._conv(b.conv, ya, stats=True)
             cat = ops.new((B, zb.shape[1], zb.shape[2], 2 * C), self.dtype)
             _, pool = ops.inorm_apply(zb, sb, b.gamma, b.beta, add=None if attn is None else attn[lvl], out=cat[..., C:], pooled=True)
             cats.append(cat)
@@ -369,8 +374,7 @@ class Generator:
                 tape["enc"].append((h, za, sa, ya, zb, sb))
             h = pool
         for bl in self.bott:
-            z = self._conv(bl.conv, h)
-            sz = ops.inorm_stats(z)
+            z, sz = self._conv(bl.conv, h, stats=True)
             y, _ = ops.inorm_apply(z, sz, bl.gamma, bl.beta)
             if save:
                 tape["bott"].append((h, z, sz))
@@ -380,11 +384,9 @@ class Generator:
             C = cat.shape[3] // 2
             self._conv(self.up[u], h, cat[..., :C])
             a, b = self.dec[u]
-            za = self._conv(a.conv, cat)
-            sa = ops.inorm_stats(za)
+            za, sa = self._conv(a.conv, cat, stats=True)
             ya, _ = ops.inorm_apply(za, sa, a.gamma, a.beta)
-            zb = self._conv(b.conv, ya)
-            sb = ops.inorm_stats(zb)
+            zb, sb = self._conv(b.conv, ya, stats=True)
             yb, _ = ops.inorm_apply(zb, sb, b.gamma, b.beta)
             if save:
                 tape["dec"].append((h, cat, za, sa, ya, zb, sb))
@@ -524,8 +526,7 @@ class Discriminator:
         tape = {"layers": [], "col": col, "hw": (x.shape[1], x.shape[2])} if save else None
         for i, bl in enumerate(self.blocks):
             conv = self.d1_col if (i == 0 and col) else bl.conv
-            z = conv.fwd(h, None, self.tc, v)
-            sz = ops.inorm_stats(z)
+            z, sz = conv.fwd(h, None, self.tc, v, want_stats=True)
             y, _ = ops.inorm_apply(z, sz, bl.gamma, bl.beta, add=attn if i == 3 else None)
             if save:
                 tape["layers"].append((h, z, sz))

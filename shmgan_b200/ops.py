@@ -18,6 +18,11 @@ BN_EPS = 1e-3       # Keras BatchNormalization default (SpecSeg.py:37)
 # (family, pass, layer, flops, bytes, ev0, ev1); bench.py uses it for the per-kernel roofline (never on in the timed value).
 PROF = None
 
+# Instance-norm statistics from the producing convolution's epilogue (shm_conv2d_tc_fwd_stats) instead of a separate read of the tensor
+# (shm_inorm_stats).  Off = the round-1 two-kernel form (kept switchable for A/B measurements and the equivalence test).
+import os as _os
+FUSE_STATS = _os.environ.get("SHM_FUSE_STATS", "1") != "0"
+
 
 TC_KERNELS = ("conv_tc_kernel", "conv_halo_kernel", "conv_multi_kernel (big)", "conv_multi_kernel (scatter)", "wgrad_tc_kernel",
               "wgrad_halo_kernel<0>", "wgrad_halo_kernel<1>", "wgrad_s2_kernel<0>", "wgrad_s2_kernel<1>")
@@ -212,7 +217,9 @@ class Conv:
                 and bool(call("shm_conv2d_tc_supported", C.byref(d), 0)))
 
     # -- forward / backward ------------------------------------------------------------------------
-    def fwd(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, tc: bool = True, version: int = 0):
+    def fwd(self, x: torch.Tensor, y: Optional[torch.Tensor] = None, tc: bool = True, version: int = 0, want_stats: bool = False):
+        """want_stats: also return the instance-norm statistics of y ([n, cout, 2] fp64 sums / sums of squares per image and channel) --
+        from the convolution's own epilogue when the serving kernel has one, else from a separate pass over y."""
         n, h, w, _ = x.shape
         ho, wo = self.out_hw(h, w)
         if y is None:
@@ -222,6 +229,16 @@ class Conv:
         fl, nb = self.flops(n, h, w), self.io_bytes(n, h, w, x.element_size())
         if pad and not (tc and self.tc_ok(d)):
             raise L.ShmError("%s: zero-padded input needs the tensor-core path (shape %s)" % (self.name, tuple(x.shape)))
+        if want_stats:
+            sums = None
+            if tc and FUSE_STATS and not self.c3to1_ok(x) and not self.pw1_ok(x) and self.tc_ok(d) and call("shm_conv2d_tc_stats_supported", C.byref(d)):
+                self.refresh_tc(version)
+                sums = zeros64((n, self.cout, 2), x.device)
+                _prof(_route(d, 0), "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd_stats", C.byref(d), _p(x), _p(self.w_tc), _p(self.b), _p(y), _p(sums), _stream()))
+            else:
+                self.fwd(x, y, tc, version)
+                sums = inorm_stats(y)
+            return y, sums
         if tc and self.c3to1_ok(x):
             _prof("bw", "fwd", self.name, fl, nb, lambda: call("shm_c3to1_fwd", _p(x), n, h, w, self.cin, ld(x), _p(self.w), _p(self.b), self.act,
                                                               _p(y), dt(x), _stream()))
@@ -376,7 +393,7 @@ class PaddedConv(Conv):
     def servable(self, n, h, w) -> bool:
         return bool(call("shm_conv2d_tc_supported", C.byref(self.dev_desc(n, h, w, self.cin_dev, self.cout_dev)), 0))
 
-    def fwd(self, x, y=None, tc=True, version=0):
+    def fwd(self, x, y=None, tc=True, version=0, want_stats=False):
         """x [n,h,w,cin_dev] bf16 (zero-padded segments) -> y [n,ho,wo,cout_dev] bf16 (channels cout.. are zero)."""
         n, h, w, cx = x.shape
         assert tc and x.dtype == torch.bfloat16 and cx == self.cin_dev, (self.name, tuple(x.shape))
@@ -388,6 +405,14 @@ class PaddedConv(Conv):
         self.refresh_tc(version)
         d = self.dev_desc(n, h, w, ld(x), ld(y))
         fl, nb = self.flops(n, h, w), x.element_size() * n * (h * w * self.cin_dev + ho * wo * nst)
+        if want_stats:
+            assert nst == self.cout_dev == self.cout, "statistics are for layers whose device columns are all real channels"
+            if FUSE_STATS and call("shm_conv2d_tc_stats_supported", C.byref(d)):
+                sums = zeros64((n, self.cout, 2), x.device)
+                _prof(_route(d, 0), "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd_stats", C.byref(d), _p(x), _p(self.w_tc), _p(self.b_dev), _p(y), _p(sums), _stream()))
+                return y, sums
+            self.fwd(x, y, tc, version)
+            return y, inorm_stats(y)
         if nst != self.cout_dev:
             _prof(_route(d, 0), "fwd", self.name, fl, nb, lambda: call("shm_conv2d_tc_fwd_cols", C.byref(d), _p(x), _p(self.w_tc), _p(self.b_dev), _p(y), nst, _stream()))
         else:
