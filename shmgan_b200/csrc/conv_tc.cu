@@ -13,6 +13,7 @@
 #include <string.h>
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
 
@@ -267,15 +268,18 @@ __device__ __forceinline__ void epi_row(uint32_t taddr, const float* sbias, int 
 // Instance-norm statistics produced by the convolution epilogue (SURVEY 2b "IN stats fused into the producing conv's epilogue").
 //
 // Every Conv -> LeakyReLU -> InstanceNorm block of the reference (ShmGANwithSSpecSeg.py:244-245, :386-389) needs sum / sum of squares per
-// (image, channel) of the tensor the epilogue is about to store; computing them here removes one full HBM read of every such tensor
-// (in_stats_p).  A thread owns one pixel row of the accumulator, so the per-channel sums are COLUMN sums over the 32 lanes of a warp:
-// a recursive-halving butterfly (lanes trade the half they do not keep: 16 + 8 + 4 + 2 + 1 = 31 shuffles per 32 x 32 block) leaves
-// column L's total in lane L -- shuffles use the lane crossbar only and do not compete with the tensor core for shared-memory banks.
-// The statistics are taken from the bf16-ROUNDED values (exactly what in_stats_p would read back), accumulated in fp32 registers over
-// the consecutive tiles a CTA handles of one image (the tile order of a statistics launch is contiguous per CTA for that reason) and
-// flushed with one fp64 atomic per (image, channel, moment) when the image or the column block changes.
+// (image, channel) of the tensor the epilogue is about to store; computing them here removes one full HBM read of that tensor (in_stats_p).
+// A thread owns one pixel ROW of the accumulator, so per-channel sums are COLUMN sums across the lanes of a warp.  Reducing across lanes per
+// tile (a recursive-halving shuffle butterfly, 31 shuffles + ~90 ALU instructions per 32 x 32 block and moment) made every epilogue the
+// bottleneck of its kernel: measured +0.85 ms on the halo kernels, +0.78 ms on the big-halo kernel, +0.37 ms on the generic kernel per training
+// step against 1.65 ms of in_stats_p saved (profiles/r02_fused_stats_ab.txt) -- a net loss.  What does pay: every thread keeps PRIVATE fp32
+// running sums of its own pixel row over the consecutive tiles its CTA handles of one image (the tile order of a statistics launch is
+// contiguous per CTA for that reason; 2 FMA-class instructions per value), and the cross-lane butterfly + one fp64 atomic per (image, channel,
+// moment) run only when the image changes -- two or three times per CTA.  That costs 2 x BN registers per thread, so it exists for the
+// 64-column halo variants only (the full-resolution 64-channel tensors: the largest share of the statistics traffic); every other layer keeps
+// the separate pass.  The statistics are taken from the bf16-ROUNDED values, exactly what in_stats_p would read back.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+__device__ __forceinline__ float warp_colsum32(float* v, int lane) {
 #pragma unroll
     for (int h = 16; h >= 1; h >>= 1) {
         const bool up = (lane & h) != 0;
@@ -289,73 +293,56 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
     return v[0];
 }
 
-template <int NC>                      // 32-column chunks of one accumulator row
+template <int BN>                      // accumulator columns of one pixel row (a multiple of 32)
 struct EpiStats {
-    float s[NC], q[NC];
-    int img, col0;                     // owner of the running sums: image and first column (-1: none)
+    float s[BN], q[BN];                // this thread's running sum / sum of squares per column, over the tiles of image `img`
+    int img;
     __device__ __forceinline__ void init() {
-        img = -1; col0 = 0;
+        img = -1;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) { s[c] = 0.f; q[c] = 0.f; }
+        for (int c = 0; c < BN; ++c) { s[c] = 0.f; q[c] = 0.f; }
     }
-    __device__ __forceinline__ void flush(double* __restrict__ stats, int Nn, int lane) {
+    // cross-lane column sums of the running totals -> lane L owns columns L, 32 + L, ...; one fp64 atomic per column and moment
+    __device__ __forceinline__ void flush(double* __restrict__ stats, int lane) {
         if (img >= 0) {
 #pragma unroll
-            for (int c = 0; c < NC; ++c) {
-                double* d = stats + ((long long)img * Nn + col0 + c * 32 + lane) * 2;
-                atomicAdd(d, (double)s[c]);
-                atomicAdd(d + 1, (double)q[c]);
-                s[c] = 0.f; q[c] = 0.f;
+            for (int c = 0; c < BN / 32; ++c) {
+                const float ts = warp_colsum32(s + c * 32, lane);
+                const float tq = warp_colsum32(q + c * 32, lane);
+                double* d = stats + ((long long)img * BN + c * 32 + lane) * 2;
+                atomicAdd(d, (double)ts);
+                atomicAdd(d + 1, (double)tq);
             }
+#pragma unroll
+            for (int c = 0; c < BN; ++c) { s[c] = 0.f; q[c] = 0.f; }
         }
     }
-    // warp-uniform: makes (image, column block) the owner of the running sums
-    __device__ __forceinline__ void own(double* __restrict__ stats, int Nn, int nimg, int ncol0, int lane) {
-        if (nimg != img || ncol0 != col0) { flush(stats, Nn, lane); img = nimg; col0 = ncol0; }
+    // warp-uniform: the running sums now belong to image nimg
+    __device__ __forceinline__ void own(double* __restrict__ stats, int nimg, int lane) {
+        if (nimg != img) { flush(stats, lane); img = nimg; }
     }
-    // pk: the 32 packed bf16 this lane is about to store for chunk c (ok = the lane's pixel exists)
-    template <int NV = 32>
-    __device__ __forceinline__ void add(int c, const uint4* pk, bool ok, int lane) {
-        float v[32], w[32];
+    // pk: the packed bf16 of this lane's pixel row, columns [col0, col0 + 8 * NU)
+    template <int NU>
+    __device__ __forceinline__ void add(int col0, const uint4* pk) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (i * 8 < NV) {
-                const uint32_t u[4] = {pk[i].x, pk[i].y, pk[i].z, pk[i].w};
+        for (int i = 0; i < NU; ++i) {
+            const uint32_t u[4] = {pk[i].x, pk[i].y, pk[i].z, pk[i].w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    v[i * 8 + 2 * k] = ok ? __uint_as_float(u[k] << 16) : 0.f;
-                    v[i * 8 + 2 * k + 1] = ok ? __uint_as_float(u[k] & 0xffff0000u) : 0.f;
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[i * 8 + k] = 0.f;
+            for (int k = 0; k < 4; ++k) {
+                const float lo = __uint_as_float(u[k] << 16), hi = __uint_as_float(u[k] & 0xffff0000u);
+                const int c = col0 + i * 8 + 2 * k;
+                s[c] += lo; q[c] = fmaf(lo, lo, q[c]);
+                s[c + 1] += hi; q[c + 1] = fmaf(hi, hi, q[c + 1]);
             }
         }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) w[j] = v[j] * v[j];
-        s[c] += warp_colsum32(v, lane);
-        q[c] += warp_colsum32(w, lane);
     }
 };
-
-// epi_row with optional statistics: the same TMEM -> bias -> activation -> bf16 -> global pipeline, through the packed form
-template <int NC>
-__device__ __forceinline__ void epi_row_stats(uint32_t taddr, const float* sbias, int act, bf16* __restrict__ dst, bool ok, EpiStats<NC>& st, int lane) {
-    uint32_t r[2][32];
-    tmem_ld32_nw(taddr, r[0]);
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        tmem_wait_ld32(r[c & 1]);
-        if (c + 1 < NC) tmem_ld32_nw(taddr + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);
-        uint4 pk[4];
-        epi_pack<32>(r[c & 1], sbias ? sbias + c * 32 : nullptr, act, pk);
-        if (ok) {
-            uint4* g = reinterpret_cast<uint4*>(dst + c * 32);
-            g[0] = pk[0]; g[1] = pk[1]; g[2] = pk[2]; g[3] = pk[3];
-        }
-        st.add(c, pk, ok, lane);
-    }
-}
+struct NoStats {                       // stand-in for the kernel variants without a statistics epilogue (no registers)
+    __device__ __forceinline__ void init() {}
+    __device__ __forceinline__ void flush(double*, int) {}
+    __device__ __forceinline__ void own(double*, int, int) {}
+    template <int NU> __device__ __forceinline__ void add(int, const uint4*) {}
+};
 
 // contiguous share of `total` work items for this CTA (statistics launches), or the strided order (everything else)
 __device__ __forceinline__ void tile_walk(int total, bool contig, int& first, int& end, int& step) {
@@ -386,7 +373,6 @@ struct TcParams {
     int Hout, Wout, OS, py, px, ldout, Nn;
     const float* bias; int act;
     bf16* out;
-    double* stats;               // optional [Nimg][Nn][2] fp64 (sum, sum of squares) of the stored activations: instance-norm statistics
 };
 
 constexpr int TC_THREADS = 192;          // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..5: epilogue
@@ -421,7 +407,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int total_tiles = p.m_tiles * p.n_tiles;
     const int niter = p.ntaps * p.kchunks;
     int tile_first, tile_end, tile_step;
-    tile_walk(total_tiles, p.stats != nullptr, tile_first, tile_end, tile_step);
+    tile_walk(total_tiles, false, tile_first, tile_end, tile_step);
     stage_bias(sbias, p.bias, p.Nn);
 
     if (warp == 0 && lane == 0) {
@@ -492,8 +478,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ===== epilogue: TMEM -> registers -> bias + activation -> bf16 -> global =====
         const int quad = warp & 3;                    // TMEM lane quadrant this warp may access
         const int row = quad * 32 + lane;             // accumulator row = lattice point within the tile
-        EpiStats<BN / 32> st;
-        st.init();
         int local = 0;
         for (int tile = tile_first; tile < tile_end; tile += tile_step, ++local) {
             const int as = local & 1;
@@ -510,19 +494,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             bf16* dst = p.out + ((long long)(img * p.Hout + oy) * p.Wout + ox) * p.ldout + nt * BN;
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
-            if (p.stats != nullptr) {
-                // the host only asks for statistics when the 32 rows of a warp lie in ONE image (BW * BH a multiple of 32)
-                st.own(p.stats, p.Nn, __shfl_sync(0xffffffffu, img, 0), nt * BN, lane);
-                epi_row_stats<BN / 32>(taddr, p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok, st, lane);
-            } else {
-                epi_row<BN / 32>(taddr, p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok);
-            }
+            epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN), p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
         }
-        if (p.stats != nullptr) st.flush(p.stats, p.Nn, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -620,7 +596,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int per_img = p.tiles_x * p.tiles_y;
     int tile_first, tile_end, tile_step;
-    tile_walk(p.total_tiles, p.stats != nullptr, tile_first, tile_end, tile_step);
+    tile_walk(p.total_tiles, BN == 64 && T == 1 && p.stats != nullptr, tile_first, tile_end, tile_step);
     stage_bias(sbias, p.bias, BN);
 
     if (warp == 0 && lane == 0) {
@@ -702,8 +678,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ty = row >> 3, tx = row & 7;
         int local = 0;
         uint32_t nstore = 0;                              // sub-tiles this epilogue group has handed to the TMA engine
-        constexpr int SNC = BN >= 32 ? BN / 32 : 1;       // statistics (BN >= 32 only: every layer followed by an instance norm has >= 64 columns)
-        EpiStats<SNC> st;
+        constexpr bool STATS = BN == 64 && T == 1;        // see EpiStats: private running sums cost 2 x BN registers per thread
+        typename std::conditional<STATS, EpiStats<64>, NoStats>::type st;
         st.init();
         for (int tile = tile_first; tile < tile_end; tile += tile_step, ++local) {
             const int as = local & 1;
@@ -764,13 +740,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                     ++nstore;
                 }
-                if constexpr (BN >= 32) {
+                if constexpr (STATS) {
                     if (p.stats != nullptr) {
-                        st.own(p.stats, BN, img, 0, lane);
-#pragma unroll
-                        for (int jj = 0; jj < TJ; ++jj)
-#pragma unroll
-                            for (int c = 0; c < SNC; ++c) st.add(c, pk[jj] + c * 4, true, lane);
+                        st.own(p.stats, img, lane);
+                        st.template add<CH>(0, pk[0]);
                     }
                 }
             } else {
@@ -811,15 +784,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     for (int c = 0; c < NC; ++c) tmem_ld32_nw(taddr + (uint32_t)(c * 32), r[c]);
 #pragma unroll
                     for (int c = 0; c < NC; ++c) tmem_wait_ld32(r[c]);
-                    if (p.stats != nullptr) {
-                        st.own(p.stats, BN, img, 0, lane);
+                    if (STATS && p.stats != nullptr) {
+                        st.own(p.stats, img, lane);
 #pragma unroll
                         for (int c = 0; c < NC; ++c) {
                             uint4 pk4[4];
                             epi_pack<32>(r[c], p.bias ? sbias + c * 32 : nullptr, p.act, pk4);
                             uint4* g = reinterpret_cast<uint4*>(dst + c * 32);
                             g[0] = pk4[0]; g[1] = pk4[1]; g[2] = pk4[2]; g[3] = pk4[3];
-                            st.add(c, pk4, true, lane);
+                            st.template add<4>(c * 32, pk4);
                         }
                     } else {
 #pragma unroll
@@ -831,7 +804,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (lane == 0) mbar_arrive(&tempty[as]);
             }
         }
-        if (p.stats != nullptr) st.flush(p.stats, BN, lane);
+        if (STATS && p.stats != nullptr) st.flush(p.stats, lane);
         if (Cfg::TSTORE) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every bulk store of this thread has completed
         (void)nstore; (void)ty; (void)tx;
     }
@@ -870,7 +843,6 @@ struct MultiParams {
     int nstore;                               // output channels that exist in `out` (<= Nn; the rest are zero-padding columns)
     const float* bias; int act;
     bf16* out;
-    double* stats;                            // optional instance-norm statistics [N][n_tiles * BN][2] ("big" configuration only)
 };
 
 template <int BN, int NBUF, int NPAIR>
@@ -896,7 +868,7 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int per_img = p.tiles_x * p.tiles_y;
     const int set_cols = p.nacc * BN;
     int item_first, item_end, item_step;
-    tile_walk(total, p.stats != nullptr, item_first, item_end, item_step);
+    tile_walk(total, false, item_first, item_end, item_step);
     stage_bias(sbias, p.bias, p.n_tiles * BN);
 
     if (warp == 0 && lane == 0) {
@@ -987,8 +959,6 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int ty = row >> 3, tx = row & 7;
-        EpiStats<BN / 32> st;
-        st.init();
         int local = 0;
         for (int item = item_first; item < item_end; item += item_step, ++local) {
             const int as = local % NBUF;
@@ -1002,19 +972,13 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int oy = (qy + p.row_dy[a]) * p.OS + p.py[a], ox = qx * p.OS + p.px[a];
                 const bool ok = oy < p.Hout && ox < p.Wout;
                 bf16* dst = p.out + ((long long)(img * p.Hout + oy) * p.Wout + ox) * p.ldout + nt * BN;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN);
-                if (p.stats != nullptr) {
-                    st.own(p.stats, p.n_tiles * BN, img, nt * BN, lane);
-                    epi_row_stats<BN / 32>(taddr, p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok, st, lane);
-                } else {
-                    epi_row<BN / 32>(taddr, p.bias ? sbias + nt * BN : nullptr, p.act, dst, ok, p.nstore - nt * BN);
-                }
+                epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN), p.bias ? sbias + nt * BN : nullptr,
+                                 p.act, dst, ok, p.nstore - nt * BN);
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[as]);
         }
-        if (p.stats != nullptr) st.flush(p.stats, p.n_tiles * BN, lane);
     }
     tc_fence_before();
     __syncthreads();
@@ -1096,11 +1060,9 @@ struct Geometry {
 };
 
 int launch_tc(const Geometry& g, int N, const void* in, const void* w_tc, int wrows_total, const float* bias, int act, void* out,
-              const int* tdy, const int* tdx, const int* twrow, int ntaps, int py, int px, cudaStream_t st, double* stats = nullptr) {
+              const int* tdy, const int* tdx, const int* twrow, int ntaps, int py, int px, cudaStream_t st) {
     TcParams p{};
     if (!pick_box(N, g.Qh, g.Qw, p.BW, p.BH, p.BI)) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: lattice %dx%d (N=%d) does not tile into 128-point boxes", g.Qh, g.Qw, N);
-    if (stats != nullptr && !(p.BI == 1 || (p.BW * p.BH) % 32 == 0))
-        SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc: fused statistics need >= 32 lattice points per image (%dx%d)", g.Qh, g.Qw);
     p.ntaps = ntaps;
     for (int t = 0; t < ntaps; ++t) { p.dy[t] = tdy[t]; p.dx[t] = tdx[t]; p.wrow[t] = twrow[t]; }
     p.kchunks = g.K / 64;
@@ -1110,7 +1072,7 @@ int launch_tc(const Geometry& g, int N, const void* in, const void* w_tc, int wr
     const int BN = (g.Nn % 128 == 0) ? 128 : 64;
     p.n_tiles = g.Nn / BN;
     p.Hout = g.Hout; p.Wout = g.Wout; p.OS = g.OS; p.py = py; p.px = px; p.ldout = g.ldout; p.Nn = g.Nn;
-    p.bias = bias; p.act = act; p.out = (bf16*)out; p.stats = stats;
+    p.bias = bias; p.act = act; p.out = (bf16*)out;
     CUtensorMap tmA, tmB;
     if (int rc = encode_act(&tmA, in, g.K, g.Win, g.Hin, N, g.ldin, p.BW, p.BH, p.BI, g.IS)) return rc;
     if (int rc = encode_w(&tmB, w_tc, g.K, wrows_total, BN)) return rc;
@@ -1170,7 +1132,7 @@ bool big_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
 }
 
 int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
-               void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st, double* stats = nullptr) {
+               void* out, int ldout, const int* tdy, const int* tdx, const int* twrow, cudaStream_t st) {
     MultiParams p{};
     int miny = 9, minx = 9;
     for (int t = 0; t < 9; ++t) { if (tdy[t] < miny) miny = tdy[t]; if (tdx[t] < minx) minx = tdx[t]; }
@@ -1189,7 +1151,7 @@ int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, con
     p.tiles_x = W / 8; p.tiles_y = H / 32;
     p.m_tiles = N * p.tiles_x * p.tiles_y; p.n_tiles = Nn / 128;
     p.nstore = Nn;
-    p.Hout = H; p.Wout = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out; p.stats = stats;
+    p.Hout = H; p.Wout = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
     CUtensorMap tmA, tmB;
     if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, BIG_H)) return rc;
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 128)) return rc;
@@ -1233,6 +1195,36 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
     const int BN = (Nn % 128 == 0) ? 128 : 64;
     p.n_tiles = Nn / BN;
     CUtensorMap tmA, tmB;
+    if (BN == 128 && Hq % 32 == 0 && p.nstore == Nn) {
+        // 128-column layers: four parity accumulators fill TMEM (no double buffering: the tensor core idles during every epilogue) and each
+        // 16 KB weight tile feeds ONE group of 4 MMAs (64 B/clk/SM of weight traffic: the kernel ran at the L2 -> SM limit, 560-820 TFLOP/s).
+        // Instead each parity class runs as its own pass in the "big" configuration: 32 x 8 lattice tile = TWO accumulators per streamed
+        // weight tile, double-buffered in TMEM, written with output stride 2.  The small image is read once per class (from L2 mostly).
+        if (int rc = encode_act_box(&tmA, in, K, Wq, Hq, N, ldin, HALO_W, BIG_H)) return rc;
+        if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 128)) return rc;
+        for (int a = 0; a < 4; ++a) {
+            MultiParams q{};
+            q.nstore = Nn;
+            for (int t = 0; t < ntaps; ++t) {
+                const ScatterTap& tp = taps[t];
+                if (tp.ry * 2 + tp.rx != a) continue;
+                const int i = q.ntaps++;
+                q.wrow[i] = tp.wrow; q.npairs[i] = 2;
+                q.aoff[i][0] = (tp.dy + 1) * HALO_W + (tp.dx + 1); q.aoff[i][1] = q.aoff[i][0] + 16 * HALO_W;
+                q.acc[i][0] = 0; q.acc[i][1] = 1;
+                q.first[i][0] = q.first[i][1] = (i == 0);
+            }
+            q.nacc = 2; q.row_dy[0] = 0; q.row_dy[1] = 16;
+            q.py[0] = q.py[1] = a >> 1; q.px[0] = q.px[1] = a & 1;
+            q.OS = 2; q.TH = 32; q.a_bytes = BIG_H * HALO_W * 128; q.hy = -1; q.hx = -1;
+            q.kchunks = K / 64;
+            q.tiles_x = Wq / 8; q.tiles_y = Hq / 32;
+            q.m_tiles = N * q.tiles_x * q.tiles_y; q.n_tiles = Nn / 128;
+            q.Hout = Hout; q.Wout = Wout; q.ldout = ldout; q.bias = bias; q.act = act; q.out = (bf16*)out;
+            if (int rc = launch_multi_t<128, 2, 2>(tmA, tmB, q, st)) return rc;
+        }
+        return SHM_OK;
+    }
     if (int rc = encode_act_box(&tmA, in, K, Wq, Hq, N, ldin, HALO_W, HALO_H)) return rc;
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, BN)) return rc;
     if (BN == 128) return launch_multi_t<128, 1, 1>(tmA, tmB, p, st);   // 4 x 128 columns: one accumulator set
@@ -1273,11 +1265,11 @@ int launch_thin(const CUtensorMap& tmA1, const CUtensorMap& tmAT, const CUtensor
 }
 
 // in: [N,H,W,K] (ld ldin), out: [N,H,W,Nn] (ld ldout); taps (tdy, tdx) in {-1,0,1} with weight rows twrow
-// which halo-kernel variants carry the statistics epilogue: every one with >= 32 output columns except the stacked (T = 2) 128-column thin variant
+// which halo-kernel variants carry the statistics epilogue (EpiStats): the un-stacked 64-column ones -- 64 -> 64 (TMA-store epilogue) and
+// 128 -> 64 (two k-chunks, direct stores)
 bool halo_stats_ok(int H, int K, int Nn) {
-    if (Nn < 32) return false;
-    if (K < 64 && Nn == 128 && H % 32 == 0) return false;
-    return true;
+    (void)H;
+    return Nn == 64 && (K == 64 || K == 128);
 }
 
 int launch_halo(int N, int H, int W, int K, int Nn, const void* in, int ldin, const void* w_tc, int wrows_total, const float* bias, int act,
@@ -2151,12 +2143,7 @@ extern "C" int shm_conv2d_tc_stats_supported(const shm_conv_desc* d) {
     const int s = d->stride;
     if (halo_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s) || thin_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
         return halo_stats_ok(d->H, d->Cin, d->Cout) ? 1 : 0;
-    if (d->Cin % 64 != 0 || d->Cout % 64 != 0) return 0;
-    if (big_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s)) return 1;
-    int Ho, Wo; out_dims(d, Ho, Wo);
-    int BW, BH, BI;
-    if (!pick_box(d->N, Ho, Wo, BW, BH, BI)) return 0;
-    return (BI == 1 || (BW * BH) % 32 == 0) ? 1 : 0;
+    return 0;                                          // big-halo / generic kernels: the separate pass is cheaper (see EpiStats)
 }
 extern "C" int shm_conv2d_tc_fwd_cols(const shm_conv_desc* d, const void* x, const void* w_tc, const float* bias, void* y, int nstore, void* stream) {
     SHM_REQUIRE(d && nstore > 0 && nstore <= d->Cout && nstore % 8 == 0, "shm_conv2d_tc_fwd_cols: nstore must be a multiple of 8 in (0, Cout]");
@@ -2182,9 +2169,9 @@ static int tc_fwd_impl(const shm_conv_desc* d, const void* x, const void* w_tc, 
             return launch_halo(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st, stats);
         if (d->Cin % 64 != 0 || d->Cout % 64 != 0) SHM_FAIL(SHM_EUNSUPPORTED, "conv_tc fwd: thin layer %d -> %d not servable", d->Cin, d->Cout);
         if (big_ok(d->H, d->W, d->Cin, d->Cout, d->kh, d->kw, s))
-            return launch_big(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st, stats);
+            return launch_big(d->N, d->H, d->W, d->Cin, d->Cout, x, d->ldx, w_tc, wrows, bias, d->act, y, d->ldy, tdy, tdx, twr, st);
         Geometry g{d->H, d->W, d->ldx, d->Cin, Ho, Wo, s, Ho, Wo, d->ldy, d->Cout, 1};
-        return launch_tc(g, d->N, x, w_tc, wrows, bias, d->act, y, tdy, tdx, twr, nt, 0, 0, st, stats);
+        return launch_tc(g, d->N, x, w_tc, wrows, bias, d->act, y, tdy, tdx, twr, nt, 0, 0, st);
     }
     if (stats != nullptr) SHM_FAIL(SHM_EUNSUPPORTED, "shm_conv2d_tc_fwd_stats: transposed convolutions have no statistics epilogue");
     // transposed: out[p] = sum_{o,k: s*o + k - pb = p} x[o] W[k];  p = s*q + r

@@ -343,35 +343,33 @@ def test_conv_tc_wgrad_of_first_layer_from_16_channel_input():
 
 
 # ---- instance-norm statistics from the convolution epilogue (shm_conv2d_tc_fwd_stats) ----------------------------------------
-# (N, H, W, Cin, Cout, k, stride, act, bias, kernel that serves it)
+# (N, H, W, Cin, Cout, k, stride, act, bias, fused?, kernel that serves it)
 STATS_CASES = [
-    (3, 32, 32, 64, 64, 3, 1, 1, True, "halo, TMA-store epilogue (64 -> 64)"),
-    (2, 48, 16, 128, 64, 3, 1, 1, True, "halo, two k-chunks (dec4a class), direct-store epilogue"),
-    (3, 16, 16, 64, 128, 3, 1, 1, True, "halo BN = 128 (enc2a class)"),
-    (5, 32, 32, 128, 128, 3, 1, 1, True, "big halo kernel, one n-tile"),
-    (2, 64, 16, 256, 256, 3, 1, 1, True, "big halo kernel, two n-tiles: the column block changes every item"),
-    (10, 64, 64, 128, 256, 3, 1, 1, True, "big halo kernel, 320 items: contiguous ranges over several images per CTA"),
-    (4, 64, 64, 64, 128, 3, 2, 1, False, "generic kernel, stride 2 (discriminator block)"),
-    (2, 16, 16, 512, 512, 1, 1, 1, True, "generic kernel, 1 x 1 bottleneck, four n-tiles"),
-    (8, 16, 16, 256, 512, 3, 2, 1, False, "generic kernel, 8 x 8 lattice: two images per tile (64 points each)"),
-    (200, 32, 32, 64, 64, 3, 1, 1, True, "halo, 1600 tiles: many flushes per CTA"),
+    (3, 32, 32, 64, 64, 3, 1, 1, True, True, "halo, TMA-store epilogue (64 -> 64)"),
+    (2, 48, 16, 128, 64, 3, 1, 1, True, True, "halo, two k-chunks (dec4a class), direct-store epilogue"),
+    (200, 32, 32, 64, 64, 3, 1, 1, True, True, "halo, 1600 tiles: several images and flushes per CTA"),
+    (7, 16, 8, 64, 64, 3, 1, 0, False, True, "halo, 7 tiles: fewer tiles than CTAs, no bias, no activation"),
+    (3, 16, 16, 64, 128, 3, 1, 1, True, False, "halo BN = 128 (enc2a class): separate pass"),
+    (5, 32, 32, 128, 128, 3, 1, 1, True, False, "big halo kernel: separate pass"),
+    (4, 64, 64, 64, 128, 3, 2, 1, False, False, "generic kernel, stride 2 (discriminator block): separate pass"),
 ]
 
 
 @pytest.mark.parametrize("case", STATS_CASES, ids=[c[-1] for c in STATS_CASES])
 def test_conv_tc_fwd_stats_matches_separate_pass(case):
-    """The statistics epilogue must return what shm_inorm_stats computes from the stored tensor (sums of the bf16-rounded outputs), and the
-    stored tensor itself must be bit-identical to the plain forward (the tile order of a statistics launch differs, the arithmetic does not)."""
+    """Conv.fwd(want_stats=True) must return what shm_inorm_stats computes from the stored tensor (sums of the bf16-rounded outputs) whether the
+    statistics come from the convolution's epilogue (64-column halo variants) or from the separate pass, and the stored tensor itself must be
+    bit-identical to the plain forward (the tile order of a statistics launch differs, the arithmetic does not)."""
     from shmgan_b200 import ops
     import ctypes as C
-    N, H, W, Cin, Cout, k, s, act, bias, _ = case
+    N, H, W, Cin, Cout, k, s, act, bias, fused, _ = case
     g = torch.Generator(device="cuda").manual_seed(5)
     x = (torch.randn((N, H, W, Cin), device="cuda", generator=g) * 0.7 + 0.1).bfloat16()
     c = ops.Conv("t", k, k, Cin, Cout, stride=s, act=act, bias=bias)
     c.w = (torch.randn((k, k, Cin, Cout), device="cuda", generator=g) * 0.05).bfloat16().float()
     c.b = torch.randn(Cout, device="cuda", generator=g) * 0.3 if bias else None
     d = c.desc(N, H, W, Cin, Cout, ops.BF16)
-    assert c.tc_ok(d) and ops.call("shm_conv2d_tc_stats_supported", C.byref(d)) == 1
+    assert c.tc_ok(d) and ops.call("shm_conv2d_tc_stats_supported", C.byref(d)) == int(fused)
     y0 = c.fwd(x, tc=True, version=1)
     want = ops.inorm_stats(y0)
     y1, got = c.fwd(x, tc=True, version=1, want_stats=True)
@@ -379,38 +377,14 @@ def test_conv_tc_fwd_stats_matches_separate_pass(case):
     yf = y0.double()
     ref = torch.stack([yf.sum(dim=(1, 2)), (yf * yf).sum(dim=(1, 2))], dim=-1)          # [N, C, 2] from the stored values, fp64
     scale = ref.abs().amax(dim=(0, 1), keepdim=True)
-    assert float(((got - ref).abs() / scale).max()) < 2e-6                                # fp32 partial sums per CTA, fp64 across CTAs
-    assert float(((got - want).abs() / scale).max()) < 4e-6
+    assert float(((got - ref).abs() / scale).max()) < 1e-5                                # fp32 running sums per thread, fp64 across threads
+    assert float(((got - want).abs() / scale).max()) < 1e-5
     # a channel-slice destination (the decoder's concat buffer) changes nothing
     wide = torch.zeros((N, y0.shape[1], y0.shape[2], Cout + 64), dtype=torch.bfloat16, device="cuda")
     _, got2 = c.fwd(x, wide[..., 64:], tc=True, version=1, want_stats=True)
-    assert torch.equal(wide[..., 64:], y0) and float(((got2 - ref).abs() / scale).max()) < 2e-6
+    assert torch.equal(wide[..., 64:], y0) and float(((got2 - ref).abs() / scale).max()) < 1e-5
+    if not fused:
+        with pytest.raises(ops.L.ShmError):
+            ops.call("shm_conv2d_tc_fwd_stats", C.byref(d), ops._p(x), ops._p(c.w_tc), ops._p(c.b), ops._p(y1), ops._p(got), ops._stream())
 
 
-def test_conv_tc_fwd_stats_thin_first_layer_and_unsupported_shapes():
-    from shmgan_b200 import ops
-    import ctypes as C
-    # enc1a on the thin kernel: 10 -> 64 channels from a 16-channel input, stacked sub-tiles (T = 4), TMA-store epilogue
-    N, H, W = 3, 64, 32
-    g = torch.Generator(device="cuda").manual_seed(6)
-    c = ops.PaddedConv("enc1a", 3, 3, 10, 64, 10, 1, act=1, seg_pad=16, cout_dev=64)
-    c.w = (torch.randn((3, 3, 10, 64), device="cuda", generator=g) * 0.1).bfloat16().float()
-    c.b = torch.randn(64, device="cuda", generator=g) * 0.2
-    x = ops.pad_channels(torch.rand((N, H, W, 10), device="cuda", generator=g).bfloat16(), 16)
-    y0 = c.fwd(x, None, True, 1)
-    y1, got = c.fwd(x, None, True, 1, want_stats=True)
-    assert torch.equal(y0, y1)
-    yf = y0.double()
-    ref = torch.stack([yf.sum(dim=(1, 2)), (yf * yf).sum(dim=(1, 2))], dim=-1)
-    assert float(((got - ref).abs() / ref.abs().amax(dim=(0, 1), keepdim=True)).max()) < 2e-6
-    # a 4 x 4 lattice (16 points per image < one warp of accumulator rows): no statistics epilogue; Conv.fwd falls back to the separate pass
-    cc = ops.Conv("t", 3, 3, 64, 128, act=1)
-    cc.w = torch.randn((3, 3, 64, 128), device="cuda", generator=g) * 0.05
-    cc.b = torch.zeros(128, device="cuda")
-    xs = torch.randn((8, 4, 4, 64), device="cuda", generator=g).bfloat16()
-    d = cc.desc(8, 4, 4, 64, 128, ops.BF16)
-    assert cc.tc_ok(d) and ops.call("shm_conv2d_tc_stats_supported", C.byref(d)) == 0
-    y, sums = cc.fwd(xs, tc=True, version=1, want_stats=True)
-    assert float((sums - ops.inorm_stats(y)).abs().max()) == 0.0
-    with pytest.raises(ops.L.ShmError):
-        ops.call("shm_conv2d_tc_fwd_stats", C.byref(d), ops._p(xs), ops._p(cc.w_tc), ops._p(cc.b), ops._p(y), ops._p(sums), ops._stream())
