@@ -99,6 +99,51 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: a cluster of two CTAs on one TPC; the leader (cluster rank 0) issues one MMA for both ----
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared::cta pointer of this CTA) as seen in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is signalled on a barrier that may live in the PEER CTA (the leader's full barrier)
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* tm, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives (once all MMAs issued so far have completed) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp reads TMEM lane (base_lane + i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
     asm volatile(
@@ -986,6 +1031,174 @@ conv_multi_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair form of the "big" configuration: stride-1 3x3 convolutions with Nn % 128 == 0 (every 128..1024-channel generator layer, forward and
+// dgrad -- the largest single share of the training step).
+//
+// Measured on B200 (tools/umma_rate_probe.cu, profiles/r02_umma_rate_probe.txt): back-to-back M128 x N128 x K16 MMAs of one SM retire every
+// 72.9 cycles (87.8 % of the tensor peak), the M256 x N128 x K16 MMA of a CTA PAIR every 64.1 cycles (99.8 %) -- each SM of a pair reads its 128
+// rows of A plus HALF of B from its own shared memory.  (The same probe shows that N = 64 tiles gain nothing from pairing: 58.4 vs 59.6 cycles,
+// a fixed per-instruction floor, not operand bandwidth.)  Pairing also halves the weight stream per SM: the single-CTA kernel pulls a 16 KB
+// weight tile per 512 MMA cycles = 32 B/clk/SM on top of the halo tiles -- ~6 KB/clk over 148 SMs, the L2 -> SM limit.
+//
+// Structure (one cluster = two CTAs = two SMs of a TPC; each CTA is the warp-specialised CTA of conv_multi_kernel):
+//   * each CTA owns one 32 x 8-pixel tile (two 128-row accumulators, double-buffered in its own TMEM) and loads that tile's halo itself;
+//   * each CTA loads 64 of the 128 rows of every streamed weight tile (8 KB instead of 16 KB);
+//   * every TMA load signals the LEADER's full barrier (cp.async.bulk.tensor ... cta_group::2); the leader's MMA warp issues ONE
+//     tcgen05.mma.cta_group::2 per (accumulator, k-step) for both tiles; tcgen05.commit ... multicast::cluster releases the operand slots and
+//     publishes the accumulators in BOTH CTAs; the peer's epilogue warps hand the accumulator buffer back with a remote mbarrier arrive.
+// ------------------------------------------------------------------------------------------------
+constexpr int B2_ST = 64 * 128;                                // this CTA's half of a 128-row weight tile
+constexpr int B2_STAGES = 16;
+constexpr int BIG2_SMEM = BIG_A_STAGES * BIG_A_ST + B2_STAGES * B2_ST + 1024 + 512 + BIAS_SMEM;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const MultiParams p) {
+    constexpr int BN = 128;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + BIG_A_STAGES * BIG_A_ST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + B2_STAGES * B2_ST);
+    uint64_t* fullA = bars;                              // used in the leader only (both CTAs' loads land here)
+    uint64_t* emptyA = fullA + BIG_A_STAGES;
+    uint64_t* fullB = emptyA + BIG_A_STAGES;             // leader only
+    uint64_t* emptyB = fullB + B2_STAGES;
+    uint64_t* tfull = emptyB + B2_STAGES;                // [2]
+    uint64_t* tempty = tfull + 2;                        // [2] leader only: 4 epilogue warps x 2 CTAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* sbias = reinterpret_cast<float*>(sB + B2_STAGES * B2_ST + 512);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pairs_m = (p.m_tiles + 1) >> 1;
+    const int total = pairs_m * p.n_tiles;
+    const int per_img = p.tiles_x * p.tiles_y;
+    const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
+    constexpr int set_cols = 2 * BN;
+    stage_bias(sbias, p.bias, p.n_tiles * BN);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int i = 0; i < BIG_A_STAGES; ++i) { mbar_init(&fullA[i], 2); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < B2_STAGES; ++i) { mbar_init(&fullB[i], 2); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // barriers of BOTH CTAs are initialised before anyone signals across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own halo tile + own half of every weight tile, signalled on the leader's full barriers =====
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+        for (int item = cid; item < total; item += nclusters) {
+            const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
+            const int img = mt / per_img; const int r = mt - img * per_img;       // mt == m_tiles (odd tile count): img == N, zero-filled box
+            const int y0 = (r / p.tiles_x) * p.TH + p.hy, x0 = (r % p.tiles_x) * 8 + p.hx;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&emptyA[sa], pha ^ 1);
+                if (elect_one_sync()) {
+                    const uint32_t lead = map_to_cta(&fullA[sa], 0);
+                    if (rank == 0) mbar_expect_tx(&fullA[sa], 2 * p.a_bytes); else mbar_arrive_cluster(lead);
+                    tma_load_4d_2sm(sA + sa * BIG_A_ST, &tmA, lead, kc * 64, x0, y0, img);
+                }
+                __syncwarp();
+                if (++sa == BIG_A_STAGES) { sa = 0; pha ^= 1; }
+                for (int t = 0; t < p.ntaps; ++t) {
+                    mbar_wait(&emptyB[sb], phb ^ 1);
+                    if (elect_one_sync()) {
+                        const uint32_t lead = map_to_cta(&fullB[sb], 0);
+                        if (rank == 0) mbar_expect_tx(&fullB[sb], 2 * B2_ST); else mbar_arrive_cluster(lead);
+                        tma_load_2d_2sm(sB + sb * B2_ST, &tmB, lead, kc * 64, p.wrow[t] + nt * BN + (int)rank * 64);
+                    }
+                    __syncwarp();
+                    if (++sb == B2_STAGES) { sb = 0; phb ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1 && rank == 0) {
+        // ===== MMA issuer (leader only): M = 256 over the pair =====
+        constexpr uint32_t idesc = make_idesc(256, BN, 0, 0);
+        int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
+        int local = 0;
+        for (int item = cid; item < total; item += nclusters, ++local) {
+            const int as = local & 1;
+            mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + as * set_cols;
+            for (int kc = 0; kc < p.kchunks; ++kc) {
+                mbar_wait(&fullA[sa], pha);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA + sa * BIG_A_ST);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                    if (t < p.ntaps) {
+                        mbar_wait(&fullB[sb], phb);
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+                            const uint64_t bdesc = make_desc_sw128(smem_u32(sB + sb * B2_ST), 16, 1024);
+#pragma unroll
+                            for (int j = 0; j < 2; ++j) {
+                                const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)p.aoff[t][j] * 128u, 16, HALO_W * 128);
+                                const uint32_t keep = (kc == 0 && p.first[t][j]) ? 0u : 1u;
+                                const uint32_t dcol = d0 + p.acc[t][j] * BN;
+                                umma_bf16_2sm(dcol, adesc, bdesc, idesc, keep);
+#pragma unroll
+                                for (int k = 1; k < 4; ++k)
+                                    umma_bf16_2sm(dcol, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+                            }
+                            umma_commit_2sm(&emptyB[sb]);
+                        }
+                        __syncwarp();
+                        if (++sb == B2_STAGES) { sb = 0; phb ^= 1; }
+                    }
+                }
+                if (elect_one_sync()) umma_commit_2sm(&emptyA[sa]);
+                __syncwarp();
+                if (++sa == BIG_A_STAGES) { sa = 0; pha ^= 1; }
+            }
+            if (elect_one_sync()) umma_commit_2sm(&tfull[as]);
+            __syncwarp();
+        }
+    } else if (warp >= 2) {
+        // ===== epilogue (both CTAs): own accumulators -> bias + activation -> bf16 -> global; hands the buffer back to the LEADER's MMA warp =====
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int ty = row >> 3, tx = row & 7;
+        int local = 0;
+        for (int item = cid; item < total; item += nclusters, ++local) {
+            const int as = local & 1;
+            const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
+            const bool valid = mt < p.m_tiles;
+            const int img = mt / per_img; const int r = mt - img * per_img;
+            const int qy = (r / p.tiles_x) * p.TH + ty, qx = (r % p.tiles_x) * 8 + tx;
+            mbar_wait(&tfull[as], (local >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int a = 0; a < 2; ++a) {
+                const int oy = (qy + p.row_dy[a]) * p.OS + p.py[a], ox = qx * p.OS + p.px[a];
+                const bool ok = valid && oy < p.Hout && ox < p.Wout;
+                bf16* dst = p.out + ((long long)((valid ? img : 0) * p.Hout + (ok ? oy : 0)) * p.Wout + (ok ? ox : 0)) * p.ldout + nt * BN;
+                epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN), p.bias ? sbias + nt * BN : nullptr,
+                                 p.act, dst, ok, p.nstore - nt * BN);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tempty[as]); else mbar_arrive_cluster(map_to_cta(&tempty[as], 0));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                   // no CTA leaves (or frees TMEM) while its peer may still signal it or read its operands
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1154,6 +1367,20 @@ int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, con
     p.Hout = H; p.Wout = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
     CUtensorMap tmA, tmB;
     if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, BIG_H)) return rc;
+    // CTA-pair form (conv_big2_kernel): every layer with at least one pair of tiles per pair of SMs.  SHM_BIG2=0 in the environment keeps the
+    // single-CTA kernel (A/B measurements, tests of both paths).
+    static const bool pair_on = []() { const char* e = getenv("SHM_BIG2"); return !(e && e[0] == '0'); }();
+    if (pair_on && p.m_tiles >= 2) {
+        if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 64)) return rc;
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(conv_big2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG2_SMEM); attr = true; }
+        const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+        int clusters = shm_num_sms() / 2;
+        if (clusters > pairs) clusters = pairs;
+        conv_big2_kernel<<<2 * clusters, TC_THREADS, BIG2_SMEM, st>>>(tmA, tmB, p);
+        SHM_CHECK_LAUNCH("conv_big2_kernel");
+        return SHM_OK;
+    }
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 128)) return rc;
     return launch_multi_t<128, 2, 2>(tmA, tmB, p, st);
 }
@@ -1195,36 +1422,9 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
     const int BN = (Nn % 128 == 0) ? 128 : 64;
     p.n_tiles = Nn / BN;
     CUtensorMap tmA, tmB;
-    if (BN == 128 && Hq % 32 == 0 && p.nstore == Nn) {
-        // 128-column layers: four parity accumulators fill TMEM (no double buffering: the tensor core idles during every epilogue) and each
-        // 16 KB weight tile feeds ONE group of 4 MMAs (64 B/clk/SM of weight traffic: the kernel ran at the L2 -> SM limit, 560-820 TFLOP/s).
-        // Instead each parity class runs as its own pass in the "big" configuration: 32 x 8 lattice tile = TWO accumulators per streamed
-        // weight tile, double-buffered in TMEM, written with output stride 2.  The small image is read once per class (from L2 mostly).
-        if (int rc = encode_act_box(&tmA, in, K, Wq, Hq, N, ldin, HALO_W, BIG_H)) return rc;
-        if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 128)) return rc;
-        for (int a = 0; a < 4; ++a) {
-            MultiParams q{};
-            q.nstore = Nn;
-            for (int t = 0; t < ntaps; ++t) {
-                const ScatterTap& tp = taps[t];
-                if (tp.ry * 2 + tp.rx != a) continue;
-                const int i = q.ntaps++;
-                q.wrow[i] = tp.wrow; q.npairs[i] = 2;
-                q.aoff[i][0] = (tp.dy + 1) * HALO_W + (tp.dx + 1); q.aoff[i][1] = q.aoff[i][0] + 16 * HALO_W;
-                q.acc[i][0] = 0; q.acc[i][1] = 1;
-                q.first[i][0] = q.first[i][1] = (i == 0);
-            }
-            q.nacc = 2; q.row_dy[0] = 0; q.row_dy[1] = 16;
-            q.py[0] = q.py[1] = a >> 1; q.px[0] = q.px[1] = a & 1;
-            q.OS = 2; q.TH = 32; q.a_bytes = BIG_H * HALO_W * 128; q.hy = -1; q.hx = -1;
-            q.kchunks = K / 64;
-            q.tiles_x = Wq / 8; q.tiles_y = Hq / 32;
-            q.m_tiles = N * q.tiles_x * q.tiles_y; q.n_tiles = Nn / 128;
-            q.Hout = Hout; q.Wout = Wout; q.ldout = ldout; q.bias = bias; q.act = act; q.out = (bf16*)out;
-            if (int rc = launch_multi_t<128, 2, 2>(tmA, tmB, q, st)) return rc;
-        }
-        return SHM_OK;
-    }
+    // (Tried: each parity class of a 128-column layer as its own pass in the "big" configuration -- two accumulators per streamed weight tile,
+    // double-buffered TMEM.  No gain: up3T 0.397 -> 0.363 ms but d3 dgrad 0.316 -> 0.381 ms; a class with one or two taps streams a 43 KB halo
+    // tile per 8-16 MMAs and is bound by the L2 -> SM path just like the four-accumulator form.  profiles/r02_negative_results.txt)
     if (int rc = encode_act_box(&tmA, in, K, Wq, Hq, N, ldin, HALO_W, HALO_H)) return rc;
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, BN)) return rc;
     if (BN == 128) return launch_multi_t<128, 1, 1>(tmA, tmB, p, st);   // 4 x 128 columns: one accumulator set

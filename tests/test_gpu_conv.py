@@ -126,6 +126,9 @@ TC_CASES = [
     (1, 64, 16, 256, 128, 3, 1, False, 2, True),    # big halo kernel, four k-chunks (A ring wraps), dgrad has two n-tiles
     (2, 32, 8, 64, 256, 3, 1, False, 0, True),      # big halo kernel fwd with two n-tiles, single k-chunk
     (10, 64, 64, 128, 256, 3, 1, False, 1, True),   # big halo kernel, 320 work items: persistent loop, accumulator double buffering
+    (3, 32, 8, 128, 128, 3, 1, False, 1, True),     # big halo kernel, CTA-pair form with an ODD tile count (the last pair's second tile is a dummy)
+    (150, 32, 8, 128, 128, 3, 1, False, 0, True),   # CTA-pair form, 75 pairs on 74 clusters: one cluster wraps around, operand rings wrap
+    (1, 32, 8, 192, 128, 3, 1, False, 1, True),     # single tile: falls back to the single-CTA big kernel
     (2, 16, 16, 128, 64, 3, 2, True, 1, True),      # scatter kernel: Conv2DTranspose fwd, four parity accumulators x 64 columns
     (1, 32, 16, 256, 128, 3, 2, True, 1, True),     # scatter kernel, 4 x 128 columns (single accumulator set), four k-chunks
     (3, 16, 8, 64, 128, 2, 2, True, 0, True),       # scatter kernel, k2 s2 transposed conv (SpecSeg up path)
