@@ -1079,8 +1079,13 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
-        for (int i = 0; i < BIG_A_STAGES; ++i) { mbar_init(&fullA[i], 2); mbar_init(&emptyA[i], 1); }
-        for (int i = 0; i < B2_STAGES; ++i) { mbar_init(&fullB[i], 2); mbar_init(&emptyB[i], 1); }
+        // full barriers: ONE arrival (the leader's arrive.expect_tx for the bytes of both CTAs); the peer only contributes transaction bytes.
+        // (A per-stage remote mbarrier.arrive.release.cluster from the peer's producer cost ~500 cycles per weight tile and halved the kernel's
+        // throughput: 780 instead of 1400 TFLOP/s.)  A peer's bytes can land before the leader's expect_tx of the same phase -- the transaction
+        // count goes negative for a moment while the pending arrival keeps the phase open -- but never in an earlier phase: the peer refills a
+        // slot only after the multicast commit that released it.
+        for (int i = 0; i < BIG_A_STAGES; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < B2_STAGES; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
         fence_barrier_init();
     }
@@ -1102,7 +1107,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_wait(&emptyA[sa], pha ^ 1);
                 if (elect_one_sync()) {
                     const uint32_t lead = map_to_cta(&fullA[sa], 0);
-                    if (rank == 0) mbar_expect_tx(&fullA[sa], 2 * p.a_bytes); else mbar_arrive_cluster(lead);
+                    if (rank == 0) mbar_expect_tx(&fullA[sa], 2 * p.a_bytes);
                     tma_load_4d_2sm(sA + sa * BIG_A_ST, &tmA, lead, kc * 64, x0, y0, img);
                 }
                 __syncwarp();
@@ -1111,7 +1116,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     mbar_wait(&emptyB[sb], phb ^ 1);
                     if (elect_one_sync()) {
                         const uint32_t lead = map_to_cta(&fullB[sb], 0);
-                        if (rank == 0) mbar_expect_tx(&fullB[sb], 2 * B2_ST); else mbar_arrive_cluster(lead);
+                        if (rank == 0) mbar_expect_tx(&fullB[sb], 2 * B2_ST);
                         tma_load_2d_2sm(sB + sb * B2_ST, &tmB, lead, kc * 64, p.wrow[t] + nt * BN + (int)rank * 64);
                     }
                     __syncwarp();
@@ -1375,7 +1380,21 @@ int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, con
         static bool attr = false;
         if (!attr) { cudaFuncSetAttribute(conv_big2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG2_SMEM); attr = true; }
         const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
-        int clusters = shm_num_sms() / 2;
+        // a cluster needs both SMs of one TPC; parts with odd SM counts per GPC cannot host SMs / 2 clusters at once, and a persistent kernel
+        // launched with more clusters than fit runs the excess as a second wave AFTER the first has finished all of its items
+        static int max_clusters = 0;
+        if (max_clusters == 0) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(shm_num_sms() & ~1); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = BIG2_SMEM;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, conv_big2_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = shm_num_sms() / 2; }
+            max_clusters = n < shm_num_sms() / 2 ? n : shm_num_sms() / 2;
+            if (getenv("SHM_DEBUG")) fprintf(stderr, "[shmgan] conv_big2_kernel: %d CTA pairs fit on %d SMs\n", max_clusters, shm_num_sms());
+        }
+        int clusters = max_clusters;
         if (clusters > pairs) clusters = pairs;
         conv_big2_kernel<<<2 * clusters, TC_THREADS, BIG2_SMEM, st>>>(tmA, tmB, p);
         SHM_CHECK_LAUNCH("conv_big2_kernel");
