@@ -1051,6 +1051,9 @@ constexpr int B2_ST = 64 * 128;                                // this CTA's hal
 constexpr int B2_STAGES = 16;
 constexpr int BIG2_SMEM = BIG_A_STAGES * BIG_A_ST + B2_STAGES * B2_ST + 1024 + 512 + BIAS_SMEM;
 
+// NBUF / NPAIR as in conv_multi_kernel: <2, 2> = "big" (two accumulators per weight tile, double-buffered), <1, 1> = stride-2 "scatter" with
+// 128 columns (four parity accumulators = all of TMEM; pairing halves its weight stream, which is what bounds it)
+template <int NBUF, int NPAIR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const MultiParams p) {
     constexpr int BN = 128;
@@ -1074,7 +1077,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int total = pairs_m * p.n_tiles;
     const int per_img = p.tiles_x * p.tiles_y;
     const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
-    constexpr int set_cols = 2 * BN;
+    const int set_cols = p.nacc * BN;
     stage_bias(sbias, p.bias, p.n_tiles * BN);
 
     if (warp == 0 && lane == 0) {
@@ -1130,8 +1133,8 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
         int local = 0;
         for (int item = cid; item < total; item += nclusters, ++local) {
-            const int as = local & 1;
-            mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+            const int as = local % NBUF;
+            mbar_wait(&tempty[as], ((local / NBUF) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d0 = tmem_base + as * set_cols;
             for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -1146,7 +1149,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (elect_one_sync()) {
                             const uint64_t bdesc = make_desc_sw128(smem_u32(sB + sb * B2_ST), 16, 1024);
 #pragma unroll
-                            for (int j = 0; j < 2; ++j) {
+                            for (int j = 0; j < NPAIR; ++j) {
                                 const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)p.aoff[t][j] * 128u, 16, HALO_W * 128);
                                 const uint32_t keep = (kc == 0 && p.first[t][j]) ? 0u : 1u;
                                 const uint32_t dcol = d0 + p.acc[t][j] * BN;
@@ -1175,15 +1178,15 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ty = row >> 3, tx = row & 7;
         int local = 0;
         for (int item = cid; item < total; item += nclusters, ++local) {
-            const int as = local & 1;
+            const int as = local % NBUF;
             const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
             const bool valid = mt < p.m_tiles;
             const int img = mt / per_img; const int r = mt - img * per_img;
             const int qy = (r / p.tiles_x) * p.TH + ty, qx = (r % p.tiles_x) * 8 + tx;
-            mbar_wait(&tfull[as], (local >> 1) & 1);
+            mbar_wait(&tfull[as], (local / NBUF) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int a = 0; a < 2; ++a) {
+            for (int a = 0; a < p.nacc; ++a) {
                 const int oy = (qy + p.row_dy[a]) * p.OS + p.py[a], ox = qx * p.OS + p.px[a];
                 const bool ok = valid && oy < p.Hout && ox < p.Wout;
                 bf16* dst = p.out + ((long long)((valid ? img : 0) * p.Hout + (ok ? oy : 0)) * p.Wout + (ok ? ox : 0)) * p.ldout + nt * BN;
@@ -1344,6 +1347,35 @@ int launch_multi_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const MultiPa
     return SHM_OK;
 }
 
+inline bool pair_enabled() {
+    static const bool on = []() { const char* e = getenv("SHM_BIG2"); return !(e && e[0] == '0'); }();
+    return on;
+}
+template <int NBUF, int NPAIR>
+int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const MultiParams& p, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_big2_kernel<NBUF, NPAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG2_SMEM); attr = true; }
+    // a cluster needs both SMs of one TPC; a persistent kernel launched with more clusters than fit at once would run the excess as a second
+    // wave AFTER the first has finished all of its items, so the grid is capped by what the occupancy query says (74 pairs on a 148-SM B200)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(shm_num_sms() & ~1); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = BIG2_SMEM;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_big2_kernel<NBUF, NPAIR>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = shm_num_sms() / 2; }
+        max_clusters = n < shm_num_sms() / 2 ? n : shm_num_sms() / 2;
+        if (getenv("SHM_DEBUG")) fprintf(stderr, "[shmgan] conv_big2_kernel<%d, %d>: %d CTA pairs fit on %d SMs\n", NBUF, NPAIR, max_clusters, shm_num_sms());
+    }
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = max_clusters < pairs ? max_clusters : pairs;
+    conv_big2_kernel<NBUF, NPAIR><<<2 * clusters, TC_THREADS, BIG2_SMEM, st>>>(tmA, tmB, p);
+    SHM_CHECK_LAUNCH("conv_big2_kernel");
+    return SHM_OK;
+}
+
 // stride-1 3x3 layers the "big" configuration serves
 bool big_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
     return kh == 3 && kw == 3 && stride == 1 && H % 32 == 0 && W % 8 == 0 && K % 64 == 0 && Nn % 128 == 0;
@@ -1372,33 +1404,11 @@ int launch_big(int N, int H, int W, int K, int Nn, const void* in, int ldin, con
     p.Hout = H; p.Wout = W; p.ldout = ldout; p.bias = bias; p.act = act; p.out = (bf16*)out;
     CUtensorMap tmA, tmB;
     if (int rc = encode_act_box(&tmA, in, K, W, H, N, ldin, HALO_W, BIG_H)) return rc;
-    // CTA-pair form (conv_big2_kernel): every layer with at least one pair of tiles per pair of SMs.  SHM_BIG2=0 in the environment keeps the
-    // single-CTA kernel (A/B measurements, tests of both paths).
-    static const bool pair_on = []() { const char* e = getenv("SHM_BIG2"); return !(e && e[0] == '0'); }();
-    if (pair_on && p.m_tiles >= 2) {
+    // CTA-pair form (conv_big2_kernel): every layer with at least one pair of tiles.  SHM_BIG2=0 in the environment keeps the single-CTA
+    // kernel (A/B measurements, tests of both paths).
+    if (pair_enabled() && p.m_tiles >= 2) {
         if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 64)) return rc;
-        static bool attr = false;
-        if (!attr) { cudaFuncSetAttribute(conv_big2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BIG2_SMEM); attr = true; }
-        const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
-        // a cluster needs both SMs of one TPC; parts with odd SM counts per GPC cannot host SMs / 2 clusters at once, and a persistent kernel
-        // launched with more clusters than fit runs the excess as a second wave AFTER the first has finished all of its items
-        static int max_clusters = 0;
-        if (max_clusters == 0) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(shm_num_sms() & ~1); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = BIG2_SMEM;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, conv_big2_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = shm_num_sms() / 2; }
-            max_clusters = n < shm_num_sms() / 2 ? n : shm_num_sms() / 2;
-            if (getenv("SHM_DEBUG")) fprintf(stderr, "[shmgan] conv_big2_kernel: %d CTA pairs fit on %d SMs\n", max_clusters, shm_num_sms());
-        }
-        int clusters = max_clusters;
-        if (clusters > pairs) clusters = pairs;
-        conv_big2_kernel<<<2 * clusters, TC_THREADS, BIG2_SMEM, st>>>(tmA, tmB, p);
-        SHM_CHECK_LAUNCH("conv_big2_kernel");
-        return SHM_OK;
+        return launch_pair_t<2, 2>(tmA, tmB, p, st);
     }
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 128)) return rc;
     return launch_multi_t<128, 2, 2>(tmA, tmB, p, st);
@@ -1445,6 +1455,10 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
     // double-buffered TMEM.  No gain: up3T 0.397 -> 0.363 ms but d3 dgrad 0.316 -> 0.381 ms; a class with one or two taps streams a 43 KB halo
     // tile per 8-16 MMAs and is bound by the L2 -> SM path just like the four-accumulator form.  profiles/r02_negative_results.txt)
     if (int rc = encode_act_box(&tmA, in, K, Wq, Hq, N, ldin, HALO_W, HALO_H)) return rc;
+    if (BN == 128 && pair_enabled() && p.m_tiles >= 2) {                // CTA pair: each SM streams half of every weight tile
+        if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 64)) return rc;
+        return launch_pair_t<1, 1>(tmA, tmB, p, st);
+    }
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, BN)) return rc;
     if (BN == 128) return launch_multi_t<128, 1, 1>(tmA, tmB, p, st);   // 4 x 128 columns: one accumulator set
     return launch_multi_t<64, 2, 1>(tmA, tmB, p, st);                   // 4 x 64 columns, double-buffered

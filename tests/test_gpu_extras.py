@@ -95,8 +95,10 @@ def test_checkpoint_roundtrip_resumes_training(tmp_path):
     assert a.last_drop_bits == b.last_drop_bits
     assert a.total_Generator_loss == pytest.approx(b.total_Generator_loss, rel=1e-5)
     assert a.total_Discriminator_loss == pytest.approx(b.total_Discriminator_loss, rel=1e-5)
-    d = (a.G.net.store.flat - b.G.net.store.flat).abs().max()
-    assert float(d) < 1e-6                                          # fp32 atomics order only
+    # fp32 atomics order only: the gradients agree to ~1e-6 relative, so Adam's normalised step (~2e-5 per weight) agrees except where a
+    # gradient's sign sits inside that noise
+    d = (a.G.net.store.flat - b.G.net.store.flat).abs()
+    assert float(d.max()) < 5e-5 and float((d > 1e-6).float().mean()) < 1e-3
 
 
 def test_loader_feeds_train_step():
