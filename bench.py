@@ -335,13 +335,13 @@ def run_ours(a):
         tc_fl = sum(v[0] for k, v in fam.items() if k[0] == "tc") / 2
         tc_ms = sum(v[1] for k, v in fam.items() if k[0] == "tc") / 2
         # measured DRAM traffic of single launches (ncu --set full, profiles/r0N_ncu_kernels.json), reported beside the live numbers
+        # one `ncu --set full` capture per kernel family (profiles/r02_ncu_kernels.json: tools/prof_kernels.py + tools/ncu_summary2.py; the first
+        # entry of a family is its representative 256 x 256-step layer)
+        ncu = {}
         try:
-            ncu = {}
-            for name in ("r01_ncu_kernels.json", "r02_ncu_kernels.json"):       # later rounds override / extend earlier captures
-                pth = os.path.join(ROOT, "profiles", name)
-                if os.path.exists(pth):
-                    with open(pth) as fh:
-                        ncu.update(json.load(fh))
+            with open(os.path.join(ROOT, "profiles", "r02_ncu_kernels.json")) as fh:
+                for label, d in json.load(fh).items():
+                    ncu.setdefault(d.get("family"), d)
         except Exception:
             ncu = {}
         ktab = {}
