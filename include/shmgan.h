@@ -112,11 +112,6 @@ int shm_inorm_bwd_apply(const void* x, int N, int H, int W, int C, int ldx, int 
                         const double* bsums, int act, void* dx, int lddx,
                         float* dbias /* may be NULL: dbias[c] += sum over pixels of dx = the producing conv's bias gradient */, void* stream);
 
-/* Tuning / comparison hook for the instance-norm and activation-backward streams (tools/bench_norm.py): pipe_off = 1 routes bf16 tensors
- * to the register-staged kernels instead of the cp.async-pipelined range kernels; depth in {0 = per-kernel default, 2, 4, 8} is the
- * per-thread ring depth; grid_mul = 0 launches one resident wave, k > 0 launches k blocks per SM.  Defaults: (0, 0, 0). */
-int shm_norm_tune(int pipe_off, int depth, int grid_mul);
-
 /* ---- pointwise ---- */
 /* dpre = dy * act'(y_post)   (LeakyReLU/ReLU derivative from the saved post-activation value); dbias (may be NULL) += column sums of dpre */
 int shm_act_bwd(const void* dy, int lddy, const void* y, int ldy, void* dpre, int ldd, int64_t npix, int C, int act, int dtype, float* dbias, void* stream);

@@ -32,7 +32,8 @@ def _stale(target: str, deps) -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "norm_pipe.cuh"), os.path.join(HERE, "..", "include", "shmgan.h")]
+    headers = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "norm_pipe.cuh"), os.path.join(HERE, "..", "include", "shmgan.h"),
+               os.path.join(HERE, "..", "include", "shmgan_tools.h")]
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

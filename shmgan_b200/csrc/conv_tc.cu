@@ -1852,6 +1852,127 @@ wgrad_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair form of wgrad_halo_kernel<1> (Cin % 256 == 0, Cout % 128 == 0): M = 256 input channels over the pair (each CTA loads the halo of its own
+// 128 channels), N = 128 output channels of ONE dy tile of which each CTA loads 64 -- tcgen05.mma.cta_group::2 retires an M256 x N128 x K16 MMA
+// every 64 cycles against 73 for M128 x N128 on one SM (tools/umma_rate_probe.cu), and the dy stream per SM halves.  Barrier protocol as in
+// conv_big2_kernel: all loads signal the leader's full barriers (one arrival: the leader's expect_tx for both CTAs' bytes), commits are multicast.
+// There is one accumulator set per CTA for the whole kernel (split-K over the pixel range), so no accumulator hand-back is needed.
+// ------------------------------------------------------------------------------------------------
+constexpr int WH2_A_ONE = 16 * HALO_W * 128;                   // 20480: one 64-channel halo (16 rows of 10 pixels)
+constexpr int WH2_A_ST = 2 * WH2_A_ONE;
+constexpr int WH2_B_ST = 16384;                                // this CTA's 64 output channels of the 128-pixel dy tile
+constexpr int WH2_STAGE = WH2_A_ST + WH2_B_ST;
+constexpr int WH2_STAGES = 3;
+constexpr int WH2_SMEM = WH2_STAGES * WH2_STAGE + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+wgrad_halo2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmDY, const WhParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + WH2_STAGES * WH2_A_ST;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + WH2_STAGES * WH2_STAGE);
+    uint64_t* full = bars;                                 // leader only
+    uint64_t* empty = bars + WH2_STAGES;
+    uint64_t* tfull = bars + 2 * WH2_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cid = blockIdx.x >> 1;
+    const int unit = cid % p.units, split = cid / p.units;          // p.units counts PAIRS of 128-channel ci blocks here
+    const int nb = unit % p.nblocks;
+    const int cb = 2 * ((unit / p.nblocks) % (p.cblocks >> 1)) + (int)rank;
+    const int frow = unit / (p.nblocks * (p.cblocks >> 1));
+    const int t0 = split * p.tiles_per_split;
+    int t1 = t0 + p.tiles_per_split; if (t1 > p.total_tiles) t1 = p.total_tiles;
+    const int per_img = p.tiles_x * p.tiles_y;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmX); prefetch_tmap(&tmDY);
+        for (int s = 0; s < WH2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(tfull, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int t = t0; t < t1; ++t) {
+            const int img = t / per_img; const int r = t - img * per_img;
+            const int y0 = (r / p.tiles_x) * 16, x0 = (r % p.tiles_x) * 8;
+            mbar_wait(&empty[stage], phase ^ 1);
+            if (elect_one_sync()) {
+                const uint32_t lead = map_to_cta(&full[stage], 0);
+                if (rank == 0) mbar_expect_tx(&full[stage], 2 * (WH2_A_ST + WH2_B_ST));
+                uint8_t* a = sA + stage * WH2_A_ST;
+                tma_load_4d_2sm(a, &tmX, lead, cb * 128, x0 - 1, y0 - 1 + frow, img);
+                tma_load_4d_2sm(a + WH2_A_ONE, &tmX, lead, cb * 128 + 64, x0 - 1, y0 - 1 + frow, img);
+                tma_load_4d_2sm(sB + stage * WH2_B_ST, &tmDY, lead, nb * 128 + (int)rank * 64, x0, y0, img);
+            }
+            __syncwarp();
+            if (++stage == WH2_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp == 1 && rank == 0) {
+        if (t1 > t0) {
+            constexpr uint32_t idesc = make_idesc(256, 128, 1, 1);
+            int stage = 0; uint32_t phase = 0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t a0 = smem_u32(sA + stage * WH2_A_ST);
+                    const uint32_t b0 = smem_u32(sB + stage * WH2_B_ST);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {          // 16 pixels = tile rows 2j, 2j+1 per MMA
+                        const uint64_t bdesc = make_desc_sw128(b0 + j * 2048, 16384, 1024);
+                        const uint32_t acc = (t > t0 || j > 0) ? 1u : 0u;
+#pragma unroll
+                        for (int tx = 0; tx < 3; ++tx) {
+                            const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(2 * j * HALO_W + tx) * 128u, WH2_A_ONE, HALO_W * 128);
+                            umma_bf16_2sm(tmem_base + tx * 128, adesc, bdesc, idesc, acc);
+                        }
+                    }
+                    umma_commit_2sm(&empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == WH2_STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one_sync()) umma_commit_2sm(tfull);
+            __syncwarp();
+        }
+    } else if (warp >= 2 && t1 > t0) {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        mbar_wait(tfull, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int a = 0; a < 3; ++a) {
+            const int tap = frow * 3 + a, ci = cb * 128 + row;
+            float* dst = p.dW + ((long long)tap * p.Cin + ci) * p.Cout + nb * 128;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(a * 128 + c * 32), r);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    red_add_v4(dst + c * 32 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // stride-2 halo wgrad kernel: weight gradients of Conv2DTranspose(3, s=2) and of stride-2 Conv2D(3) layers.
 //
 //   dW[ky][kx][cg][cs] += sum_o G[2*o + (ky, kx), cg] * S[o, cs]
@@ -2133,6 +2254,25 @@ int launch_wgrad_halo(const shm_conv_desc* d, const void* x, const void* dy, flo
     // then runs past the channel extent and the out-of-bounds part is zero-filled in shared memory -- the padding costs no HBM bytes
     if (int rc = encode_act_box(&tmX, x, d->ldx < d->Cin ? d->ldx : d->Cin, d->W, d->H, d->N, d->ldx, HALO_W, mode ? 16 : 18)) return rc;
     if (int rc = encode_act_box(&tmDY, dy, d->Cout, d->W, d->H, d->N, d->ldy, 8, 16)) return rc;
+    if (mode == 1 && pair_enabled() && p.cblocks % 2 == 0) {
+        // CTA pairs: a unit = TWO 128-channel ci blocks; the pixel range is split as before, over half as many (twice as wide) units
+        p.units /= 2;
+        long long bc = -1; int bs = 1;
+        for (int s = 1; s <= smax; ++s) {
+            const long long ctas = 2LL * p.units * s;
+            if (ctas > 4LL * sms && s > 1) break;
+            const long long waves = (ctas + sms - 1) / sms;
+            const long long cost = waves * (cdiv(p.total_tiles, s) + 6);
+            if (bc < 0 || cost < bc) { bc = cost; bs = s; }
+        }
+        p.tiles_per_split = cdiv(p.total_tiles, bs);
+        p.splits = cdiv(p.total_tiles, p.tiles_per_split);
+        static bool attr = false;
+        if (!attr) { cudaFuncSetAttribute(wgrad_halo2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WH2_SMEM); attr = true; }
+        wgrad_halo2_kernel<<<2 * p.units * p.splits, TC_THREADS, WH2_SMEM, st>>>(tmX, tmDY, p);
+        SHM_CHECK_LAUNCH("wgrad_halo2_kernel");
+        return SHM_OK;
+    }
     return mode ? launch_wgrad_halo_t<1>(tmX, tmDY, p, st) : launch_wgrad_halo_t<0>(tmX, tmDY, p, st);
 }
 

@@ -4,6 +4,7 @@
 // Replaces the ~13 eager TF ops per tfa InstanceNormalization (Generator_summary.txt:9-37) and the pooling /
 // Add / Concatenate layers of ShmGANwithSSpecSeg.py:245-323, :358-359, :388 and SpecSeg.py:37-83.
 #include "common.cuh"
+#include "../../include/shmgan_tools.h"
 
 namespace {
 

@@ -16,8 +16,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared_symbols():
-    with open(os.path.join(ROOT, "include", "shmgan.h")) as f:
-        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    text = ""
+    for name in sorted(os.listdir(os.path.join(ROOT, "include"))):       # shmgan.h (the boundary) and shmgan_tools.h (measurement hooks)
+        if name.endswith(".h"):
+            with open(os.path.join(ROOT, "include", name)) as f:
+                text += re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
     return sorted(set(re.findall(r"\b(shm_[a-z0-9_]+)\s*\(", text)))
 
 
