@@ -185,6 +185,8 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    rank_ms = []
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -195,6 +197,9 @@ def run_ours(a):
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         if world > 1:
+            per_rank = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(per_rank, ms)
+            rank_ms.clear(); rank_ms.extend(float(t) / steps for t in per_rank)      # every rank's own device time per step (skew diagnosis)
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
@@ -239,6 +244,7 @@ def run_ours(a):
     launches = (_lib.launches() - l0) // a.steps
     clk = clocks.stop() if rank == 0 else None
     value = world * B * a.steps / (ms * 1e-3)
+    rank_ms_train = list(rank_ms)
 
     freed[0].record(); freed[1].record()
     issue_copy(0)
@@ -259,6 +265,10 @@ def run_ours(a):
                        "batch_per_gpu": B, "global_batch": B * world, "image_size": S, "parallelism": "dp%d" % world,
                        "l2": "inputs+activations of one step >> 126 MB L2 (no flush needed)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "peaks": peak_src}
+    if world > 1:
+        line["rank_ms_per_step"] = [round(v, 3) for v in rank_ms_train]      # ms_per_step is their maximum
+        if os.environ.get("SHM_DP_NOREDUCE"):
+            line["diagnostic"] = "SHM_DP_NOREDUCE=1: gradient all-reduce skipped (replicas diverge) -- isolates straggler skew from communication"
 
     if not a.no_extras:
         # ---- inference img/s at N GPUs (BASELINE.json metric; configs[3] shape: SpecSeg mask + generator, batch 64 at 512 x 512):

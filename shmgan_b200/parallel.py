@@ -41,6 +41,8 @@ class GradReducer:
         self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
         self.pending: List = []
         self.bytes_reduced = 0
+        import os
+        self.skip = os.environ.get("SHM_DP_NOREDUCE", "0") == "1"
 
     def broadcast_params(self, flats: Sequence[torch.Tensor], src: int = 0):
         for f in flats:
@@ -50,6 +52,8 @@ class GradReducer:
         """Starts summing flat[lo:hi] over the ranks, one collective per bucket.  On CUDA the collectives are ordered after
         the work already queued on the current stream and run on NCCL's stream; `wait()` joins them."""
         hi = flat.numel() if hi < 0 else hi
+        if self.skip:                                   # SHM_DP_NOREDUCE=1: diagnostic only (isolates straggler skew from communication)
+            return
         for a, b in bucket_ranges(hi, self.bucket_elems, lo):
             self.pending.append(dist.all_reduce(flat[a:b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True))
             self.bytes_reduced += (b - a) * flat.element_size()
