@@ -169,7 +169,8 @@ def run_ours(a):
 
     net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B), dtype=a.dtype, allow_random_specseg=True).build()
     if world > 1:
-        net.enable_data_parallel()
+        net.enable_data_parallel(bucket_mb=float(os.environ.get("SHM_DP_BUCKET_MB", "25")))
+        net.dp_overlap = os.environ.get("SHM_DP_OVERLAP", "1") != "0"
     g = torch.Generator(device="cuda").manual_seed(1234 + rank)
     pol = [torch.rand((B, S, S, 3), generator=g, device="cuda") for _ in range(4)]
     dev_in = pol + [net.calculate_estimate_diffuse(*pol)]

@@ -219,6 +219,7 @@ class ShmGANwithSSpecSeg:
         self.step_count = 0
         self.table = LS.LossTable()
         self._reducer = None
+        self.dp_overlap = True                              # all-reduce G's gradient ranges while the last backward sweep still runs
         self._pending_losses = None                         # (pinned host copy of the loss table, event) of the last train_step
         self._loss_host = [None, None]
         # the discriminator's weight-gradient sweep (12 passes of small, bandwidth-heavy layers) is independent of the generator-loss
@@ -476,7 +477,7 @@ class ShmGANwithSSpecSeg:
         # gradient buffer is all-reduced (NCCL's stream) as soon as its last weight-gradient kernel is enqueued, while the rest of the
         # backward keeps computing; only the encoder / attention head of the buffer is reduced after the sweep
         hook = None
-        if self._reducer is not None:
+        if self._reducer is not None and self.dp_overlap:
             def hook(stage):
                 lo, hi = G.grad_range(stage)
                 self._reducer.reduce_async(G.store.grad, lo, hi)
@@ -487,7 +488,10 @@ class ShmGANwithSSpecSeg:
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         if self._reducer is not None:
-            hook("head")
+            if hook is not None:
+                hook("head")
+            else:
+                self._reducer.reduce_async(G.store.grad)     # dp_overlap = False: one reduction of the whole buffer after the sweep
             self._reducer.wait()
 
         # ---- clip_by_value(+-1) + Adam (:860-871); both optimisers use g_lr (:169-174)
