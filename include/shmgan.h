@@ -43,6 +43,9 @@ typedef struct {
 const char* shm_last_error(void);
 int  shm_version(void);
 int  shm_sm_count(void);                 /* SMs of the current device (148 on B200) */
+/* zero-fill of a device buffer on `stream` (tf.zeros / tf.zeros_like at ShmGANwithSSpecSeg.py:206,470-471 and the zero-initialised gradient
+ * accumulators of tape.gradient :859,:868) */
+int  shm_zero(void* ptr, int64_t bytes, void* stream);
 
 /* ---- convolutions: Keras Conv2D ShmGANwithSSpecSeg.py:244,254,263,272,281,301,308,315,322,326,365,387,410-411,
  *      SpecSeg.py:34-88; Conv2DTranspose ShmGANwithSSpecSeg.py:298,305,312,319, SpecSeg.py:64,70,76,82;

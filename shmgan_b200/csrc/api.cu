@@ -24,3 +24,13 @@ int shm_num_sms() {
 extern "C" const char* shm_last_error(void) { return g_err; }
 extern "C" int shm_version(void) { return 100; }
 extern "C" int shm_sm_count(void) { return shm_num_sms(); }
+
+// zero-fill of a caller-owned device buffer on the caller's stream (gradient buffers, loss seeds, accumulator arenas): one memset node instead of a
+// framework fill kernel -- the step launches nothing but this library's kernels and memsets
+extern "C" int shm_zero(void* ptr, int64_t bytes, void* stream) {
+    SHM_REQUIRE(ptr != nullptr && bytes >= 0, "shm_zero: bad args");
+    if (bytes == 0) return SHM_OK;
+    cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) SHM_FAIL(SHM_ECUDA, "shm_zero: %s", cudaGetErrorString(e));
+    return SHM_OK;
+}

@@ -17,10 +17,10 @@ IDX = {k: i for i, k in enumerate(SLOTS)}
 
 class LossTable:
     def __init__(self, device="cuda"):
-        self.buf = torch.zeros(len(SLOTS), dtype=torch.float32, device=device)
+        self.buf = ops.zeros((len(SLOTS),), torch.float32, device)
 
     def zero(self):
-        self.buf.zero_()
+        ops.zero_(self.buf)
 
     def slot(self, name):
         return C.c_void_p(self.buf.data_ptr() + 4 * IDX[name])

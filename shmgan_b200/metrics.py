@@ -39,9 +39,9 @@ def image_metrics(gen_rgb: torch.Tensor, target_rgb: torch.Tensor) -> Dict[str, 
     assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.shape == b.shape and a.shape[3] == 3
     n, h, w, _ = a.shape
     per = h * w * 3
-    sq = torch.zeros((n,), dtype=torch.float64, device=a.device)
+    sq = ops.zeros((n,), torch.float64, a.device)
     call("shm_sqerr_per_image", _p(a), _p(b), n, per, _p(sq), _stream())
-    de = torch.zeros((n, 2), dtype=torch.float64, device=a.device)
+    de = ops.zeros((n, 2), torch.float64, a.device)
     call("shm_delta_e", _p(a), _p(b), n, h * w, _p(de), _stream())
     ss = ssim_rescaled(a, b, 5.0)
     sq_h, de_h, ss_h = sq.cpu().tolist(), de.cpu().tolist(), ss.cpu().tolist()

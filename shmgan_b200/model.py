@@ -210,7 +210,7 @@ class ShmGANwithSSpecSeg:
         self.pg = process_group
         if device is not None:
             torch.cuda.set_device(device)
-        self.specular_candidate = torch.zeros((1, self.image_size, self.image_size, 1), device="cuda")   # :206
+        self.specular_candidate = ops.zeros((1, self.image_size, self.image_size, 1), torch.float32)   # :206
         self.G = self.D = self.SpecSeg = None
         self._rng = random.Random(seed)
         self.drop_bits: Optional[Sequence[bool]] = None     # set to pin the 5 Bernoulli draws of the next step
@@ -399,8 +399,8 @@ class ShmGANwithSSpecSeg:
 
         # ---- losses (:669-844): values into the table, seed gradients for the two backward sweeps
         # D-loss seeds: total_D + total_Cls = (D1_cls + D3_cls)/6 + (D2_rf + D4_rf)/6 + 10.5 D4_cls (+ NST, no D dependence)
-        dD_rfA, dD_clsA = torch.zeros_like(rfA), torch.zeros_like(clsA)
-        dD_rfB, dD_clsB = torch.zeros_like(rfB), torch.zeros_like(clsB)
+        dD_rfA, dD_clsA = ops.zeros_like(rfA), ops.zeros_like(clsA)
+        dD_rfB, dD_clsB = ops.zeros_like(rfB), ops.zeros_like(clsB)
         # G-loss seeds through D: total_G contains (D1_rf + D3_rf)/6
         dG_rfA, dG_rfB = ops.new((B, s32, s32, 1), f32), ops.new((5 * B, s32, s32, 1), f32)
         sixth = 1.0 / 6.0
@@ -424,7 +424,7 @@ class ShmGANwithSSpecSeg:
         for k in range(5):
             w = 10.0 * (10.0 if k == 4 else 0.2)
             LS.l1(cyc_rgb[k * B:(k + 1) * B], origs[k], tab.slot("L1_c%d" % k), 1.0, d_cyc_rgb[k * B:(k + 1) * B], w)   # :745-751
-        d_cyc_Y = torch.zeros((5 * B, S, S, 1), dtype=f32, device=cyc_Y.device)
+        d_cyc_Y = ops.zeros((5 * B, S, S, 1), f32, cyc_Y.device)
         self.ssim_values = []
         for k in range(5):
             Yk, dYk = cyc_Y[k * B:(k + 1) * B], d_cyc_Y[k * B:(k + 1) * B]
@@ -439,7 +439,7 @@ class ShmGANwithSSpecSeg:
         # ---- backward: D weight gradients (:859), then the generator loss through D (dgrad only) and G (:868)
         D.store.zero_grad()
         G.store.zero_grad()
-        d_dattn = torch.zeros_like(d_attn) if self.live_mask else None
+        d_dattn = ops.zeros_like(d_attn) if self.live_mask else None
 
         def d_weight_sweep():
             D.backward(tapeA, dD_rfA, dD_clsA, wgrad=True, need_dx=False, dattn=d_dattn, attn_nb=B)
@@ -463,7 +463,7 @@ class ShmGANwithSSpecSeg:
             ops.axpy(1.0, dxA, d_gen_rgb)
             ops.axpy(1.0, dxB, d_cyc_rgb)
         ops.yuv2rgb_bwd(d_cyc_rgb, lpB, d_cyc_Y, accumulate=True)
-        g_dattn = [torch.zeros_like(a) for a in g_attn] if self.live_mask else None
+        g_dattn = [ops.zeros_like(a) for a in g_attn] if self.live_mask else None
         any_dropped = any(bits)
         d_cyc_in = G.backward(tape5, ops.cast(d_cyc_Y, dt), g_dattn, attn_nb=B, need_dx=any_dropped)
         d_gen_Y = ops.new((B, S, S, 1), f32)

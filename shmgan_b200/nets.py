@@ -211,7 +211,7 @@ class ParamStore:
             c.tc_version = self.version
 
     def zero_grad(self):
-        self.grad.zero_()
+        ops.zero_(self.grad)
         for c in self.padded_convs:
             c.zero_pad_grad()
         self._finalized = False
@@ -621,7 +621,7 @@ class SpecSegNet:
         """Zero-initialised scratch whose padding channels are never written (cached per shape across calls)."""
         t = self._zbuf.get(key)
         if t is None or tuple(t.shape) != tuple(shape):
-            t = torch.zeros(shape, dtype=self.dtype, device=self.store.flat.device)
+            t = ops.zeros(shape, self.dtype, self.store.flat.device)
             self._zbuf[key] = t
         return t
 

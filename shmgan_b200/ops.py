@@ -60,9 +60,9 @@ def arena_begin():
     """Start of a train / inference step: recycle the arena (clears the part the previous step used, on the current stream)."""
     global _ARENA, _ARENA_USED, _ARENA_ON
     if _ARENA is None:
-        _ARENA = torch.zeros(ARENA_DOUBLES, dtype=torch.float64, device="cuda")
+        _ARENA = zeros((ARENA_DOUBLES,), torch.float64)
     elif _ARENA_USED:
-        _ARENA[:_ARENA_USED].zero_()
+        zero_(_ARENA[:_ARENA_USED])
     _ARENA_USED, _ARENA_ON = 0, True
 
 
@@ -77,7 +77,7 @@ def zeros64(shape, device) -> torch.Tensor:
     for v in shape:
         n *= int(v)
     if not _ARENA_ON or _ARENA_USED + n > ARENA_DOUBLES or _ARENA.device != torch.device(device):
-        return torch.zeros(shape, dtype=torch.float64, device=device)
+        return zeros(shape, torch.float64, device)
     t = _ARENA[_ARENA_USED:_ARENA_USED + n].view(shape)
     _ARENA_USED += (n + 1) // 2 * 2                      # keep 16-byte alignment (double2 loads)
     return t
@@ -127,6 +127,22 @@ def _check_nhwc(t: torch.Tensor):
 
 def new(shape, dtype, device="cuda"):
     return torch.empty(shape, dtype=dtype, device=device)
+
+
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    """In-place zero fill of a dense tensor through the library (one memset on the current stream, no framework kernel)."""
+    assert t.is_contiguous()
+    if t.numel():
+        call("shm_zero", _p(t), t.numel() * t.element_size(), _stream())
+    return t
+
+
+def zeros(shape, dtype, device="cuda") -> torch.Tensor:
+    return zero_(torch.empty(shape, dtype=dtype, device=device))
+
+
+def zeros_like(t: torch.Tensor) -> torch.Tensor:
+    return zero_(torch.empty(t.shape, dtype=t.dtype, device=t.device))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -323,7 +339,7 @@ class Conv:
         dw = self.dw
         if pad:
             if self.dw_pad is None:
-                self.dw_pad = torch.zeros((self.kh, self.kw, self.cin_pad, self.cout), dtype=torch.float32, device=x.device)
+                self.dw_pad = zeros((self.kh, self.kw, self.cin_pad, self.cout), torch.float32, x.device)
             dw = self.dw_pad
         if tc and self.c3to1_ok(x) and not self.has_bias:
             _prof("bw", "wgrad", self.name, fl, nb, lambda: call("shm_c3to1_wgrad", _p(x), n, h, w, self.cin, ld(x), _p(dy), _p(dw), dt(x), _stream()))
@@ -345,7 +361,7 @@ class Conv:
 
     def zero_pad_grad(self):
         if self.dw_pad is not None:
-            self.dw_pad.zero_()
+            zero_(self.dw_pad)
 
     def fold_pad_grad(self):
         """dw[tap, :cin, :] = dw_pad[tap, :cin, :] (the padded rows are gradients of weights that do not exist)."""
@@ -381,7 +397,7 @@ class PaddedConv(Conv):
                      self.cin_dev, self.cout_dev, BF16, 0)
         if self.w_tc is None:
             self.w_tc = new((self.kh * self.kw * self.cin_dev * self.cout_dev,), torch.bfloat16)
-            self.b_dev = torch.zeros((self.cout_dev,), dtype=torch.float32, device=self.w.device)
+            self.b_dev = zeros((self.cout_dev,), torch.float32, self.w.device)
         call("shm_conv2d_tc_prep_weights_padded", C.byref(d), _p(self.w), self.cin, self.seg_real, self.seg_pad, self.cout, _p(self.w_tc), _stream())
         if self.has_bias:
             call("shm_cast", _p(self.b), F32, _p(self.b_dev), F32, self.cout, _stream())
@@ -601,7 +617,7 @@ class RunningMean:
     (tf.reduce_mean(self.stddev_arr) at :548 / test.py:246); `mean()` reads it back (synchronises)."""
 
     def __init__(self, device="cuda"):
-        self.acc = torch.zeros(2, dtype=torch.float64, device=device)
+        self.acc = zeros((2,), torch.float64, device)
 
     def append(self, t: torch.Tensor):
         assert t.dtype == torch.float32 and t.is_contiguous()
