@@ -859,6 +859,148 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// Resident-weight stride-2 scatter kernel: Conv2DTranspose(3, s=2) forward and the dgrad of a stride-2 Conv2D(3) whose N = 64 output columns
+// and K <= 128 reduction channels let ALL nine weight tiles stay in shared memory (9 x K/64 x 8 KB <= 147 KB): up4T (128 -> 64) and d2's dgrad.
+// The streamed form (conv_multi_kernel<64, 2, 1>) pulls an 8 KB weight tile per four N = 64 MMAs (~35 B/clk/SM on top of the halo tiles) and ran
+// at 470-520 TFLOP/s, half of what an N = 64 MMA stream can do; here the only stream is ONE 18 x 10 halo box per k-chunk, exactly as in
+// conv_halo_kernel, and the nine taps scatter into four parity-class accumulators (4 x 64 columns, double-buffered = all 512 TMEM columns).
+// ------------------------------------------------------------------------------------------------
+struct ScatResParams {
+    int tdy[9], tdx[9], wrow[9], acc[9], first[9];   // tap offset inside the halo (0..1), first weight row, parity class 2*ry+rx, first tap of its class
+    int tiles_x, tiles_y, total_tiles;
+    int Hout, Wout, ldout, nstore;
+    const float* bias; int act;
+    bf16* out;
+};
+template <int KC>
+struct ScatResCfg {
+    static constexpr int W_TILE = 64 * 128;
+    static constexpr int W_BYTES = 9 * KC * W_TILE;
+    static constexpr int FIXED = 1024 + 256 + BIAS_SMEM;
+    static constexpr int FIT = (227 * 1024 - FIXED - W_BYTES) / HALO_STAGE;
+    static constexpr int STAGES = FIT < 4 ? FIT : 4;
+    static_assert(STAGES >= 2, "resident scatter kernel shared memory");
+    static constexpr int SMEM = W_BYTES + STAGES * HALO_STAGE + FIXED;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ScatResParams p) {
+    using Cfg = ScatResCfg<KC>;
+    constexpr int BN = 64, SET = 4 * BN;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sW = smem;                                   // [9 taps][KC][64 rows x 128 B]
+    uint8_t* sA = smem + Cfg::W_BYTES;                    // [STAGES][HALO_STAGE]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::STAGES * HALO_STAGE);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + Cfg::STAGES;
+    uint64_t* tfull = bars + 2 * Cfg::STAGES;             // [2]
+    uint64_t* tempty = tfull + 2;                         // [2]
+    uint64_t* wbar = tempty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+    float* sbias = reinterpret_cast<float*>(sA + Cfg::STAGES * HALO_STAGE + 256);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int per_img = p.tiles_x * p.tiles_y;
+    stage_bias(sbias, p.bias, BN);
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        mbar_init(wbar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one_sync()) {
+            mbar_expect_tx(wbar, Cfg::W_BYTES);
+            for (int t = 0; t < 9; ++t)
+                for (int kc = 0; kc < KC; ++kc)
+                    tma_load_2d(sW + (t * KC + kc) * Cfg::W_TILE, &tmB, wbar, kc * 64, p.wrow[t]);
+        }
+        __syncwarp();
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const int img = tile / per_img; const int r = tile - img * per_img;
+            const int y0 = (r / p.tiles_x) * 16 - 1, x0 = (r % p.tiles_x) * 8 - 1;
+            for (int kc = 0; kc < KC; ++kc) {
+                mbar_wait(&empty[stage], phase ^ 1);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(&full[stage], HALO_BYTES);
+                    tma_load_4d(sA + stage * HALO_STAGE, &tmA, &full[stage], kc * 64, x0, y0, img);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = make_idesc(128, BN, 0, 0);
+        mbar_wait(wbar, 0);
+        int stage = 0; uint32_t phase = 0;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            mbar_wait(&tempty[as], ((local >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + as * SET;
+            for (int kc = 0; kc < KC; ++kc) {
+                mbar_wait(&full[stage], phase);
+                tc_fence_after();
+                const uint32_t a0 = smem_u32(sA + stage * HALO_STAGE);
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int t = 0; t < 9; ++t) {
+                        const uint64_t adesc = make_desc_sw128(a0 + (uint32_t)(p.tdy[t] * HALO_W + p.tdx[t]) * 128u, 16, HALO_W * 128);
+                        const uint64_t bdesc = make_desc_sw128(smem_u32(sW + (t * KC + kc) * Cfg::W_TILE), 16, 1024);
+                        const uint32_t dcol = d_tmem + p.acc[t] * BN;
+                        umma_bf16(dcol, adesc, bdesc, idesc, (kc == 0 && p.first[t]) ? 0u : 1u);
+#pragma unroll
+                        for (int k = 1; k < 4; ++k)
+                            umma_bf16(dcol, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, 1u);
+                    }
+                    umma_commit(&empty[stage]);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (elect_one_sync()) umma_commit(&tfull[as]);
+            __syncwarp();
+        }
+    } else {
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int ty = row >> 3, tx = row & 7;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
+            const int as = local & 1;
+            const int img = tile / per_img; const int r = tile - img * per_img;
+            const int qy = (r / p.tiles_x) * 16 + ty, qx = (r % p.tiles_x) * 8 + tx;
+            mbar_wait(&tfull[as], (local >> 1) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int a = 0; a < 4; ++a) {
+                const int oy = 2 * qy + (a >> 1), ox = 2 * qx + (a & 1);
+                const bool ok = oy < p.Hout && ox < p.Wout;
+                bf16* dst = p.out + ((long long)(img * p.Hout + (ok ? oy : 0)) * p.Wout + (ok ? ox : 0)) * p.ldout;
+                epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * SET + a * BN), p.bias ? sbias : nullptr, p.act, dst, ok, p.nstore);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
 // multi-accumulator halo kernel.  One TMA box per 64-channel k-chunk brings the halo of a tile of lattice points; every tap is
 // a shifted smem descriptor into it (as in conv_halo_kernel); each 64-channel weight tile (tap, k-chunk) is streamed through
 // its own ring and feeds one or two accumulators.  Two configurations:
@@ -1455,6 +1597,35 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
     // double-buffered TMEM.  No gain: up3T 0.397 -> 0.363 ms but d3 dgrad 0.316 -> 0.381 ms; a class with one or two taps streams a 43 KB halo
     // tile per 8-16 MMAs and is bound by the L2 -> SM path just like the four-accumulator form.  profiles/r02_negative_results.txt)
     if (int rc = encode_act_box(&tmA, in, K, Wq, Hq, N, ldin, HALO_W, HALO_H)) return rc;
+    if (Nn == 64 && ntaps == 9 && (K == 64 || K == 128)) {              // all nine weight tiles fit in shared memory: resident-weight kernel
+        static const bool res_on = []() { const char* e = getenv("SHM_SCAT_RES"); return !(e && e[0] == '0'); }();
+        if (res_on) {
+            ScatResParams q{};
+            bool seen[4] = {false, false, false, false};
+            for (int t = 0; t < 9; ++t) {
+                const ScatterTap& tp = taps[t];
+                const int a = tp.ry * 2 + tp.rx;
+                q.tdy[t] = tp.dy + 1; q.tdx[t] = tp.dx + 1; q.wrow[t] = tp.wrow; q.acc[t] = a; q.first[t] = seen[a] ? 0 : 1;
+                seen[a] = true;
+            }
+            q.tiles_x = Wq / 8; q.tiles_y = Hq / 16; q.total_tiles = N * q.tiles_x * q.tiles_y;
+            q.Hout = Hout; q.Wout = Wout; q.ldout = ldout; q.nstore = p.nstore; q.bias = bias; q.act = act; q.out = (bf16*)out;
+            if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 64)) return rc;
+            int grid = shm_num_sms();
+            if (grid > q.total_tiles) grid = q.total_tiles;
+            if (K == 64) {
+                static bool attr = false;
+                if (!attr) { cudaFuncSetAttribute(conv_scat_res_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScatResCfg<1>::SMEM); attr = true; }
+                conv_scat_res_kernel<1><<<grid, TC_THREADS, ScatResCfg<1>::SMEM, st>>>(tmA, tmB, q);
+            } else {
+                static bool attr = false;
+                if (!attr) { cudaFuncSetAttribute(conv_scat_res_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScatResCfg<2>::SMEM); attr = true; }
+                conv_scat_res_kernel<2><<<grid, TC_THREADS, ScatResCfg<2>::SMEM, st>>>(tmA, tmB, q);
+            }
+            SHM_CHECK_LAUNCH("conv_scat_res_kernel");
+            return SHM_OK;
+        }
+    }
     if (BN == 128 && pair_enabled() && p.m_tiles >= 2) {                // CTA pair: each SM streams half of every weight tile
         if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 64)) return rc;
         return launch_pair_t<1, 1>(tmA, tmB, p, st);
