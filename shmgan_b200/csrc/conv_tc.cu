@@ -1030,6 +1030,9 @@ struct MultiParams {
     int nstore;                               // output channels that exist in `out` (<= Nn; the rest are zero-padding columns)
     const float* bias; int act;
     bf16* out;
+    // CTA-pair scatter only: a tile is worked as `halves` (1 or 2) items; item half h runs the taps with half[t] == h into nacc accumulators whose
+    // parity classes are py / px [h * nacc + a] -- two classes per half keep the set at 2 x 128 columns, so the sets double-buffer in TMEM
+    int halves, half[9];
 };
 
 template <int BN, int NBUF, int NPAIR>
@@ -1216,7 +1219,8 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const int pairs_m = (p.m_tiles + 1) >> 1;
-    const int total = pairs_m * p.n_tiles;
+    const int halves = p.halves > 1 ? p.halves : 1;
+    const int total = pairs_m * p.n_tiles * halves;
     const int per_img = p.tiles_x * p.tiles_y;
     const int nclusters = gridDim.x >> 1, cid = blockIdx.x >> 1;
     const int set_cols = p.nacc * BN;
@@ -1245,7 +1249,8 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===== TMA producer (both CTAs): own halo tile + own half of every weight tile, signalled on the leader's full barriers =====
         int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
         for (int item = cid; item < total; item += nclusters) {
-            const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
+            const int h = item % halves, base = item / halves;
+            const int nt = base % p.n_tiles, mt = 2 * (base / p.n_tiles) + (int)rank;
             const int img = mt / per_img; const int r = mt - img * per_img;       // mt == m_tiles (odd tile count): img == N, zero-filled box
             const int y0 = (r / p.tiles_x) * p.TH + p.hy, x0 = (r % p.tiles_x) * 8 + p.hx;
             for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -1258,6 +1263,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 __syncwarp();
                 if (++sa == BIG_A_STAGES) { sa = 0; pha ^= 1; }
                 for (int t = 0; t < p.ntaps; ++t) {
+                    if (p.half[t] != h) continue;
                     mbar_wait(&emptyB[sb], phb ^ 1);
                     if (elect_one_sync()) {
                         const uint32_t lead = map_to_cta(&fullB[sb], 0);
@@ -1276,6 +1282,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int local = 0;
         for (int item = cid; item < total; item += nclusters, ++local) {
             const int as = local % NBUF;
+            const int h = item % halves;
             mbar_wait(&tempty[as], ((local / NBUF) & 1) ^ 1);
             tc_fence_after();
             const uint32_t d0 = tmem_base + as * set_cols;
@@ -1285,7 +1292,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const uint32_t a0 = smem_u32(sA + sa * BIG_A_ST);
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                    if (t < p.ntaps) {
+                    if (t < p.ntaps && p.half[t] == h) {
                         mbar_wait(&fullB[sb], phb);
                         tc_fence_after();
                         if (elect_one_sync()) {
@@ -1321,7 +1328,8 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int local = 0;
         for (int item = cid; item < total; item += nclusters, ++local) {
             const int as = local % NBUF;
-            const int nt = item % p.n_tiles, mt = 2 * (item / p.n_tiles) + (int)rank;
+            const int h = item % halves, base = item / halves;
+            const int nt = base % p.n_tiles, mt = 2 * (base / p.n_tiles) + (int)rank;
             const bool valid = mt < p.m_tiles;
             const int img = mt / per_img; const int r = mt - img * per_img;
             const int qy = (r / p.tiles_x) * p.TH + ty, qx = (r % p.tiles_x) * 8 + tx;
@@ -1329,7 +1337,8 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tc_fence_after();
 #pragma unroll 1
             for (int a = 0; a < p.nacc; ++a) {
-                const int oy = (qy + p.row_dy[a]) * p.OS + p.py[a], ox = qx * p.OS + p.px[a];
+                const int c = h * p.nacc + a;
+                const int oy = (qy + p.row_dy[c]) * p.OS + p.py[c], ox = qx * p.OS + p.px[c];
                 const bool ok = valid && oy < p.Hout && ox < p.Wout;
                 bf16* dst = p.out + ((long long)((valid ? img : 0) * p.Hout + (ok ? oy : 0)) * p.Wout + (ok ? ox : 0)) * p.ldout + nt * BN;
                 epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN), p.bias ? sbias + nt * BN : nullptr,
@@ -1511,7 +1520,7 @@ int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const MultiPar
         max_clusters = n < shm_num_sms() / 2 ? n : shm_num_sms() / 2;
         if (getenv("SHM_DEBUG")) fprintf(stderr, "[shmgan] conv_big2_kernel<%d, %d>: %d CTA pairs fit on %d SMs\n", NBUF, NPAIR, max_clusters, shm_num_sms());
     }
-    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * (p.halves > 1 ? p.halves : 1);
     const int clusters = max_clusters < pairs ? max_clusters : pairs;
     conv_big2_kernel<NBUF, NPAIR><<<2 * clusters, TC_THREADS, BIG2_SMEM, st>>>(tmA, tmB, p);
     SHM_CHECK_LAUNCH("conv_big2_kernel");
@@ -1628,6 +1637,22 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
     }
     if (BN == 128 && pair_enabled() && p.m_tiles >= 2) {                // CTA pair: each SM streams half of every weight tile
         if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 64)) return rc;
+        // two items per tile: parity classes {(0,0), (1,1)} (4 + 1 taps of a 3 x 3 kernel) and {(0,1), (1,0)} (2 + 2 taps).  Two accumulators per
+        // item leave room for a second set in TMEM, so the epilogue of one item overlaps the MMAs of the next (with all four classes in one item
+        // the set filled TMEM and the tensor pipe idled through every epilogue: 32-34 % active).  The halo tile is loaded once per half.
+        static const bool halves_on = []() { const char* e = getenv("SHM_SCAT_HALVES"); return !(e && e[0] == '0'); }();
+        if (halves_on) {
+            MultiParams q = p;
+            const int cls_half[4] = {0, 1, 1, 0}, cls_acc[4] = {0, 0, 1, 1};          // class 2*ry+rx -> (half, accumulator)
+            for (int t = 0; t < ntaps; ++t) {
+                const int a = taps[t].ry * 2 + taps[t].rx;
+                q.half[t] = cls_half[a]; q.acc[t][0] = cls_acc[a];
+            }
+            q.halves = 2; q.nacc = 2;
+            const int order[4] = {0, 3, 1, 2};                                         // [half * 2 + accumulator] -> class
+            for (int c = 0; c < 4; ++c) { q.row_dy[c] = 0; q.py[c] = order[c] >> 1; q.px[c] = order[c] & 1; }
+            return launch_pair_t<2, 1>(tmA, tmB, q, st);
+        }
         return launch_pair_t<1, 1>(tmA, tmB, p, st);
     }
     if (int rc = encode_w(&tmB, w_tc, K, wrows_total, BN)) return rc;
