@@ -50,6 +50,17 @@ def peaks():
         return 6650.0, 1590.0, 1400.0, "fallback"
 
 
+def make_config(B, S, dtype, world):
+    """The workload both arms are measured on (BASELINE.json configs[1] shape; configs[2] at world > 1)."""
+    return {"workload": "batch %d/GPU @%dx%d, %s mode: one G+D train step (6 G + 12 D + 1 SpecSeg passes, both backward sweeps, "
+                        "clip+Adam) on 4 polarimetric images + pseudo-diffuse, live mask; configs[1] shape%s%s"
+                        % (B, S, S, "bf16 tcgen05" if dtype == "bf16" else "fp32 parity",
+                           " (configs[1]'s literal fp32 parity mode is timed beside it: parity_mode_fp32)" if dtype == "bf16" else "",
+                           "" if world == 1 else "; configs[2] data-parallel, global batch %d" % (B * world)),
+            "batch_per_gpu": B, "global_batch": B * world, "image_size": S, "parallelism": "dp%d" % world,
+            "l2": "inputs+activations of one step >> 126 MB L2 (no flush needed)"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -140,7 +151,8 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": min(a.warmup, 1), "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "G+D train step, 4 polarimetric images + pseudo-diffuse, 256x256 (configs[1]/[2] shape), one sample per step on the CPU"},
+            # the same workload description as our arm; the CPU steps a BOUNDED SAMPLE of it (one of the batch's samples per step: see cpu_baseline.sample)
+            "config": make_config(a.batch, a.size, a.dtype, max(1, a.gpus)),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -258,13 +270,7 @@ def run_ours(a):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if a.dtype == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": "batch %d/GPU @%dx%d, %s mode: one G+D train step (6 G + 12 D + 1 SpecSeg passes, both backward sweeps, "
-                                   "clip+Adam) on 4 polarimetric images + pseudo-diffuse, live mask; configs[1] shape%s%s"
-                                   % (B, S, S, "bf16 tcgen05" if a.dtype == "bf16" else "fp32 parity",
-                                      " (configs[1]'s literal fp32 parity mode is timed beside it: parity_mode_fp32)" if a.dtype == "bf16" else "",
-                                      "" if world == 1 else "; configs[2] data-parallel, global batch %d" % (B * world)),
-                       "batch_per_gpu": B, "global_batch": B * world, "image_size": S, "parallelism": "dp%d" % world,
-                       "l2": "inputs+activations of one step >> 126 MB L2 (no flush needed)"},
+            "config": make_config(B, S, a.dtype, world),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "peaks": peak_src}
     if world > 1:
         line["rank_ms_per_step"] = [round(v, 3) for v in rank_ms_train]      # ms_per_step is their maximum

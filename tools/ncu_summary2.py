@@ -48,6 +48,7 @@ def main():
         for j in range(wi, len(work)):
             if work[j]["kernel"].split("<")[0] == base:
                 label, wi = work[j]["label"], j + 1
+                d["family"] = work[j].get("family", base)
                 d["algorithmic_flops_per_launch"] = work[j]["algorithmic_flops"]
                 d["algorithmic_bytes_per_launch"] = work[j]["algorithmic_bytes"]
                 break
@@ -59,6 +60,7 @@ def main():
             d["gbs_algorithmic_isolated"] = d["algorithmic_bytes_per_launch"] / t / 1e9
             d["dram_over_algorithmic"] = d["dram_bytes_per_launch"] / d["algorithmic_bytes_per_launch"]
         d["note"] = "ncu --set full --clock-control none, ONE cold launch (tools/prof_kernels.py)"
+        d["workload"] = label
         res[label] = d
         lines.append("%-58s %-34s %8.1f us %7.0f TF/s  dram %7.1f MB (x%.2f alg)  tensor %5.1f%%  l1/smem %5.1f%%  L2 %5.1f%%  dram-tp %5.1f%%  regs %3d" % (
             label, short, d["duration_us"], d.get("tflops_isolated", 0), d["dram_bytes_per_launch"] / 1e6, d.get("dram_over_algorithmic", 0),

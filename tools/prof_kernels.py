@@ -35,8 +35,14 @@ def x(n, s, c):
     return torch.randn((n, s, s, c), device="cuda", generator=g).bfloat16()
 
 
+FAMILY = {"conv_big2_kernel<2, 2>": "conv_multi_kernel (big)", "conv_big2_kernel<2, 1>": "conv_multi_kernel (scatter)",
+          "conv_scat_res_kernel<2>": "conv_multi_kernel (scatter)", "conv_multi_kernel<64, 2, 1>": "conv_multi_kernel (scatter)",
+          "conv_tc_kernel<128>": "conv_tc_kernel", "wgrad_halo2_kernel": "wgrad_halo_kernel<1>", "wgrad_tc_kernel<128>": "wgrad_tc_kernel"}
+
+
 def note(label, kernel, flops, nbytes):
-    ROWS.append({"label": label, "kernel": kernel, "algorithmic_flops": flops, "algorithmic_bytes": nbytes})
+    fam = FAMILY.get(kernel, "conv_halo_kernel" if kernel.startswith("conv_halo_kernel") else kernel)      # bench.py's per-kernel table keys
+    ROWS.append({"label": label, "kernel": kernel, "family": fam, "algorithmic_flops": flops, "algorithmic_bytes": nbytes})
 
 
 def fwd(label, kernel, c, xin, stats=False):
@@ -75,15 +81,16 @@ fwd("big pair fwd 128->128 @128x128 N=80", "conv_big2_kernel<2, 2>", L["enc2b"],
 fwd("halo fwd + IN stats 64->64 @256x256 N=80", "conv_halo_kernel<1, 64, 128, 1>", L["enc1b"], X["64@256"], stats=True)
 fwd("halo fwd + IN stats 128->64 @256x256 N=80 (dec4a)", "conv_halo_kernel<2, 64, 128, 1>", L["dec4a"], X["128@256"], stats=True)
 fwd("halo fwd 64->128 @256x256 N=80 (enc2a at level-1 size)", "conv_halo_kernel<1, 128, 128, 1>", L["enc2a"], X["64@256"])
-fwd("scatter pair fwd ConvT 256->128 @64->128 N=80 (up3T)", "conv_big2_kernel<1, 1>", L["up3T"], X["256@64"])
-fwd("scatter fwd ConvT 128->64 @128->256 N=80 (up4T)", "conv_multi_kernel<64, 2, 1>", L["up4T"], X["128@128"])
+fwd("scatter pair fwd ConvT 256->128 @64->128 N=80 (up3T)", "conv_big2_kernel<2, 1>", L["up3T"], X["256@64"])
+fwd("scatter (resident weights) fwd ConvT 128->64 @128->256 N=80 (up4T)", "conv_scat_res_kernel<2>", L["up4T"], X["128@128"])
 fwd("generic fwd 128->256 s2 @64->32 N=160 (d3)", "conv_tc_kernel<128>", L["d3"], X["128@64x160"])
 fwd("generic fwd 1x1 512->512 @16x16 N=80 (bott)", "conv_tc_kernel<128>", L["bott"], X["512@16"])
 dgrad("generic dgrad ConvT 256->128 (gather at stride 2, up3T)", "conv_tc_kernel<128>", L["up3T"], (N, 64, 64, 256))
-dgrad("scatter pair dgrad 128->256 s2 (d3)", "conv_big2_kernel<1, 1>", L["d3"], (160, 64, 64, 128))
+dgrad("scatter pair dgrad 128->256 s2 (d3)", "conv_big2_kernel<2, 1>", L["d3"], (160, 64, 64, 128))
 wgrad("wgrad halo MODE 0 64->64 @256x256 N=80", "wgrad_halo_kernel<0>", L["enc1b"], X["64@256"])
 wgrad("wgrad halo MODE 0 128->64 @256x256 N=80 (dec4a)", "wgrad_halo_kernel<0>", L["dec4a"], X["128@256"])
-wgrad("wgrad halo MODE 1 512->256 @64x64 N=80", "wgrad_halo_kernel<1>", L["dec2a"], X["512@64"])
+wgrad("wgrad halo pair 512->256 @64x64 N=80", "wgrad_halo2_kernel", L["dec2a"], X["512@64"])
+wgrad("wgrad halo MODE 1 128->128 @128x128 N=80 (single CTA: Cin % 256 != 0)", "wgrad_halo_kernel<1>", L["enc2b"], X["128@128"])
 wgrad("wgrad s2 MODE 1 ConvT 256->128 (up3T)", "wgrad_s2_kernel<1>", L["up3T"], X["256@64"])
 wgrad("wgrad s2 MODE 0 ConvT 128->64 (up4T)", "wgrad_s2_kernel<0>", L["up4T"], X["128@128"])
 wgrad("wgrad generic 512->1024 s2 @16->8 N=160 (d5)", "wgrad_tc_kernel<128>", L["d5"], X["512@16x160"])
