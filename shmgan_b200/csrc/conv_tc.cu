@@ -868,30 +868,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 struct ScatResParams {
     int tdy[9], tdx[9], wrow[9], acc[9], first[9];   // tap offset inside the halo (0..1), first weight row, parity class 2*ry+rx, first tap of its class
     int tiles_x, tiles_y, total_tiles;
-    int Hout, Wout, ldout, nstore;
     const float* bias; int act;
-    bf16* out;
 };
+// one output map per parity class (py, px): the class's pixels (2*qy + py, 2*qx + px) as a dense (C, Wq, Hq, N) tensor with doubled strides
+struct ScatOutMaps { CUtensorMap m[4]; };
 template <int KC>
 struct ScatResCfg {
     static constexpr int W_TILE = 64 * 128;
     static constexpr int W_BYTES = 9 * KC * W_TILE;
-    static constexpr int FIXED = 1024 + 256 + BIAS_SMEM;
-    static constexpr int FIT = (227 * 1024 - FIXED - W_BYTES) / HALO_STAGE;
+    static constexpr int STG_TILE = 128 * 128;                       // one staged accumulator: 128 pixel rows x 64 bf16
+    static constexpr int STG_BYTES = 2 * STG_TILE;
+    static constexpr int FIXED = 1024 + 256 + 256;                   // alignment slack, barriers, 64 bias floats
+    static constexpr int FIT = (227 * 1024 - FIXED - W_BYTES - STG_BYTES) / HALO_STAGE;
     static constexpr int STAGES = FIT < 4 ? FIT : 4;
     static_assert(STAGES >= 2, "resident scatter kernel shared memory");
-    static constexpr int SMEM = W_BYTES + STAGES * HALO_STAGE + FIXED;
+    static constexpr int SMEM = W_BYTES + STG_BYTES + STAGES * HALO_STAGE + FIXED;
 };
 
 template <int KC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ScatResParams p) {
+conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ScatOutMaps om,
+                     const ScatResParams p) {
     using Cfg = ScatResCfg<KC>;
     constexpr int BN = 64, SET = 4 * BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sW = smem;                                   // [9 taps][KC][64 rows x 128 B]
-    uint8_t* sA = smem + Cfg::W_BYTES;                    // [STAGES][HALO_STAGE]
+    uint8_t* sStage = smem + Cfg::W_BYTES;                // [2][128 rows x 128 B] output staging (1024-aligned)
+    uint8_t* sA = sStage + Cfg::STG_BYTES;                // [STAGES][HALO_STAGE]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sA + Cfg::STAGES * HALO_STAGE);
     uint64_t* full = bars;
     uint64_t* empty = bars + Cfg::STAGES;
@@ -906,6 +910,7 @@ conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     stage_bias(sbias, p.bias, BN);
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+        for (int a = 0; a < 4; ++a) prefetch_tmap(&om.m[a]);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
         mbar_init(wbar, 1);
@@ -973,27 +978,57 @@ conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             __syncwarp();
         }
     } else {
+        // ===== epilogue.  A thread owns one pixel ROW of an accumulator, and the four parity classes land on output pixels two apart, so direct
+        // stores put the 32 lanes of every STG.128 on 32 different 128-byte lines (32 L1 wavefronts per instruction, ~4000 per tile -- as long as the
+        // tile's MMAs: ncu showed the tensor pipe 27 % active and L1 75 % busy).  Instead each accumulator is packed, staged in shared memory in the
+        // TMA swizzle and handed to the TMA engine as ONE 16 x 8-pixel box of its parity class (om.m[class]: the class's pixels as a dense tensor
+        // with doubled pixel / row strides; image borders are clipped by the map).
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
-        const int ty = row >> 3, tx = row & 7;
+        const bool leader = quad == 0 && lane == 0;
         int local = 0;
+        uint32_t cnt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
             const int as = local & 1;
             const int img = tile / per_img; const int r = tile - img * per_img;
-            const int qy = (r / p.tiles_x) * 16 + ty, qx = (r % p.tiles_x) * 8 + tx;
+            const int y0t = (r / p.tiles_x) * 16, x0t = (r % p.tiles_x) * 8;
             mbar_wait(&tfull[as], (local >> 1) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int a = 0; a < 4; ++a) {
-                const int oy = 2 * qy + (a >> 1), ox = 2 * qx + (a & 1);
-                const bool ok = oy < p.Hout && ox < p.Wout;
-                bf16* dst = p.out + ((long long)(img * p.Hout + (ok ? oy : 0)) * p.Wout + (ok ? ox : 0)) * p.ldout;
-                epi_row<BN / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * SET + a * BN), p.bias ? sbias : nullptr, p.act, dst, ok, p.nstore);
+            for (int a = 0; a < 4; ++a, ++cnt) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * SET + a * BN);
+                uint32_t r32[2][32];
+                tmem_ld32_nw(taddr, r32[0]);
+                tmem_ld32_nw(taddr + 32, r32[1]);
+                uint4 pk[8];
+                tmem_wait_ld32(r32[0]);
+                epi_pack<32>(r32[0], p.bias ? sbias : nullptr, p.act, pk);
+                tmem_wait_ld32(r32[1]);
+                epi_pack<32>(r32[1], p.bias ? sbias + 32 : nullptr, p.act, pk + 4);
+                if (a == 3) {                              // the last accumulator of the set is in registers: hand the TMEM buffer back
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tempty[as]);
+                }
+                const uint32_t sb = smem_u32(sStage + (cnt & 1) * Cfg::STG_TILE);
+                // the bulk store that read this staging tile two accumulators ago must be done reading it
+                if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t addr = sb + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c].x), "r"(pk[c].y), "r"(pk[c].z), "r"(pk[c].w) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (leader) {
+                    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                 ::"l"(&om.m[a]), "r"(sb), "r"(0), "r"(x0t), "r"(y0t), "r"(img) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
         }
+        if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // every bulk store has completed
     }
     tc_fence_before();
     __syncthreads();
@@ -1481,6 +1516,22 @@ int encode_act_box(CUtensorMap* tm, const void* base, int C, int W, int H, int N
     return SHM_OK;
 }
 
+// output map of ONE parity class of a stride-2 scatter: `base` = the class's first pixel; dims (C, Wq, Hq, N) with pixel stride 2 * ld and row
+// stride 2 * Wout * ld; box (C, 8, 16, 1) in the 128-byte swizzle (C = 64)
+int encode_out_parity(CUtensorMap* tm, const void* base, int C, int Wq, int Hq, int N, int Hout, int Wout, int ld) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled entry point not found");
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wq, (cuuint64_t)Hq, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)ld * 4, (cuuint64_t)Wout * ld * 4, (cuuint64_t)Hout * Wout * ld * 2};
+    cuuint32_t box[4] = {(cuuint32_t)C, 8, 16, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) SHM_FAIL(SHM_ECUDA, "cuTensorMapEncodeTiled(scatter output Wq=%d Hq=%d N=%d ld=%d) failed: %d", Wq, Hq, N, ld, (int)r);
+    return SHM_OK;
+}
+
 // stride-1 3x3 layers the halo kernel serves: K, Nn in {64, 128} with all nine weight tiles resident (K * Nn <= 8192)
 bool halo_ok(int H, int W, int K, int Nn, int kh, int kw, int stride) {
     return kh == 3 && kw == 3 && stride == 1 && H % 16 == 0 && W % 8 == 0 && (K == 64 || K == 128) && (Nn == 64 || Nn == 128) && K * Nn <= 8192;
@@ -1606,7 +1657,7 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
     // double-buffered TMEM.  No gain: up3T 0.397 -> 0.363 ms but d3 dgrad 0.316 -> 0.381 ms; a class with one or two taps streams a 43 KB halo
     // tile per 8-16 MMAs and is bound by the L2 -> SM path just like the four-accumulator form.  profiles/r02_negative_results.txt)
     if (int rc = encode_act_box(&tmA, in, K, Wq, Hq, N, ldin, HALO_W, HALO_H)) return rc;
-    if (Nn == 64 && ntaps == 9 && (K == 64 || K == 128)) {              // all nine weight tiles fit in shared memory: resident-weight kernel
+    if (Nn == 64 && p.nstore == 64 && ntaps == 9 && (K == 64 || K == 128)) {   // all nine weight tiles fit in shared memory: resident-weight kernel
         static const bool res_on = []() { const char* e = getenv("SHM_SCAT_RES"); return !(e && e[0] == '0'); }();
         if (res_on) {
             ScatResParams q{};
@@ -1618,18 +1669,24 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
                 seen[a] = true;
             }
             q.tiles_x = Wq / 8; q.tiles_y = Hq / 16; q.total_tiles = N * q.tiles_x * q.tiles_y;
-            q.Hout = Hout; q.Wout = Wout; q.ldout = ldout; q.nstore = p.nstore; q.bias = bias; q.act = act; q.out = (bf16*)out;
+            q.bias = bias; q.act = act;
             if (int rc = encode_w(&tmB, w_tc, K, wrows_total, 64)) return rc;
+            ScatOutMaps om;
+            for (int a = 0; a < 4; ++a) {
+                const int py = a >> 1, px = a & 1;
+                if (int rc = encode_out_parity(&om.m[a], (const bf16*)out + ((long long)py * Wout + px) * ldout, 64, (Wout - px + 1) / 2, (Hout - py + 1) / 2, N,
+                                               Hout, Wout, ldout)) return rc;
+            }
             int grid = shm_num_sms();
             if (grid > q.total_tiles) grid = q.total_tiles;
             if (K == 64) {
                 static bool attr = false;
                 if (!attr) { cudaFuncSetAttribute(conv_scat_res_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScatResCfg<1>::SMEM); attr = true; }
-                conv_scat_res_kernel<1><<<grid, TC_THREADS, ScatResCfg<1>::SMEM, st>>>(tmA, tmB, q);
+                conv_scat_res_kernel<1><<<grid, TC_THREADS, ScatResCfg<1>::SMEM, st>>>(tmA, tmB, om, q);
             } else {
                 static bool attr = false;
                 if (!attr) { cudaFuncSetAttribute(conv_scat_res_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScatResCfg<2>::SMEM); attr = true; }
-                conv_scat_res_kernel<2><<<grid, TC_THREADS, ScatResCfg<2>::SMEM, st>>>(tmA, tmB, q);
+                conv_scat_res_kernel<2><<<grid, TC_THREADS, ScatResCfg<2>::SMEM, st>>>(tmA, tmB, om, q);
             }
             SHM_CHECK_LAUNCH("conv_scat_res_kernel");
             return SHM_OK;
