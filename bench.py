@@ -245,8 +245,20 @@ def run_ours(a):
         loss_box[0] = net.total_Generator_loss              # already read back from the device by train_step (loss table D2H)
         e2e_i[0] += 1
 
+    # CUDA-graph replay of the step (net.cuda_graph; SHM_CUDA_GRAPH=0 keeps the eager launches): one graph per drop-bit pattern, so the
+    # warm-up walks all 32 patterns once -- every TIMED step, with its own random pattern, is then a replay.
+    use_graph = os.environ.get("SHM_CUDA_GRAPH", "1") != "0"
+    net.cuda_graph = use_graph
     for _ in range(max(a.warmup, 3)):
         step_resident()
+    if use_graph:
+        for pat in range(32):
+            net.drop_bits = [bool((pat >> j) & 1) for j in range(5)]
+            step_resident()
+        net.drop_bits = None
+        torch.cuda.synchronize()
+        use_graph = net.cuda_graph                          # False if the capture failed and the model fell back to eager launches
+        trace("graphs captured: %d" % len(net._graphs))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -271,7 +283,9 @@ def run_ours(a):
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if a.dtype == "bf16" else "f32", "data": "synthetic",
             "config": make_config(B, S, a.dtype, world),
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "peaks": peak_src}
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "peaks": peak_src,
+            "launch_mode": ("cuda graph replay (one graph per drop-bit pattern, %d captured in the warm-up; gpu_launches = kernels per replay)" % len(net._graphs))
+                           if use_graph else "eager launches"}
     if world > 1:
         line["rank_ms_per_step"] = [round(v, 3) for v in rank_ms_train]      # ms_per_step is their maximum
         if os.environ.get("SHM_DP_NOREDUCE"):
@@ -328,6 +342,7 @@ def run_ours(a):
         # them -- a rank-0-only step would wait for its peers forever); only rank 0 records the per-launch CUDA events.
         if rank == 0:
             ops.PROF = []
+        net.cuda_graph = False                               # per-launch CUDA events: eager launches on every rank
         net.overlap = False                                  # per-launch events need the kernels of one step serialised on one stream
         for _ in range(2):
             step_resident()
@@ -521,6 +536,7 @@ def run_ours(a):
     trace("printing / leaving")
     if world > 1:
         dist.barrier()                                       # leave together: rank 0's bookkeeping above has no collective in it
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

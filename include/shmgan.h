@@ -132,6 +132,10 @@ int shm_mul_mask(const void* x, const void* keep, void* out, int64_t n, float sc
 /* counter-based RNG (Philox-4x32-10): normal(0, sigma) / Bernoulli keep mask */
 int shm_rng_normal(void* out, int64_t n, uint64_t seed, uint64_t offset, float sigma, int dtype, void* stream);
 int shm_rng_keep(void* out, int64_t n, uint64_t seed, uint64_t offset, float keep_prob, int dtype, void* stream);
+/* the same with the counter offset read from device memory when the kernel runs: a train_step captured in a CUDA graph (model.py, cuda_graph=True)
+ * replays with a fresh GaussianNoise / Dropout stream every step (:352, :363) */
+int shm_rng_normal_dev(void* out, int64_t n, uint64_t seed, const uint64_t* offset_dev, float sigma, int dtype, void* stream);
+int shm_rng_keep_dev(void* out, int64_t n, uint64_t seed, const uint64_t* offset_dev, float keep_prob, int dtype, void* stream);
 int shm_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, void* stream);
 /* strided copy / convert of an [npix, C] plane set: dst[p*ldd + c] = src[p*lds + c]  (Y-channel extraction :486-490, batch stacking) */
 int shm_cast2d(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, int64_t npix, int C, void* stream);
@@ -198,6 +202,10 @@ int shm_scale_by_mean(const float* x, const double* acc, float mul, float* out, 
 int shm_lsgan(const float* a, int64_t n, float target, float* loss_out, float weight, float* da, float gscale, int accumulate, void* stream);
 /* mean_b softmax-CE(labels[5], logits[b]) :695-714; dlogits (+)= gscale*(sum(labels)*softmax - labels)/B */
 int shm_softmax_ce(const float* logits, int B, const float labels[5], float* loss_out, float weight, float* dlogits, float gscale, int accumulate, void* stream);
+/* the same two with the target / the 5 labels read from device memory when the kernel runs: TARGET_LABELS is redrawn every step (:986), and a
+ * train_step captured in a CUDA graph (model.py, cuda_graph=True) must see the current draw */
+int shm_lsgan_dev(const float* a, int64_t n, const float* target_dev, float* loss_out, float weight, float* da, float gscale, int accumulate, void* stream);
+int shm_softmax_ce_dev(const float* logits, int B, const float* labels5_dev, float* loss_out, float weight, float* dlogits, float gscale, int accumulate, void* stream);
 /* mean|a-b| :744-751;  da (+)= gscale*sign(a-b)/n */
 int shm_l1(const float* a, const float* b, int64_t n, float* loss_out, float weight, float* da, float gscale, int accumulate, void* stream);
 /* mean (a-b)^2 */
@@ -231,6 +239,9 @@ int shm_spec_loss(const float* Y, const float* cbcr, const float* yuv, const flo
  *      (1/world for the data-parallel average).  */
 int shm_clip_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
                   float eps, float clip, float gscale, void* stream);
+/* lr_t read from device memory when the kernel runs (CUDA-graph replays of train_step: the ExponentialDecay / bias-correction factor of :169-175 moves every step) */
+int shm_clip_adam_dev(float* param, const float* grad, float* m, float* v, int64_t n, const float* lr_t_dev, float beta1, float beta2,
+                      float eps, float clip, float gscale, void* stream);
 
 /* ---- rows SURVEY.md 8(f) marks "next": loader contract, degree of polarisation, test-time metrics (csrc/extras.cu) ---- */
 /* datasetLoader.py:48-62: decoded uint8 images src [N,Hs,Ws,3] -> tf.image.resize(bilinear, half-pixel centres) to [N,Ho,Wo,3] fp32,

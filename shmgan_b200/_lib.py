@@ -62,6 +62,8 @@ _SIG = {
     "shm_mul_mask": [_P, _P, _P, _L, _F, _I, _P],
     "shm_rng_normal": [_P, _L, _U64, _U64, _F, _I, _P],
     "shm_rng_keep": [_P, _L, _U64, _U64, _F, _I, _P],
+    "shm_rng_normal_dev": [_P, _L, _U64, _P, _F, _I, _P],
+    "shm_rng_keep_dev": [_P, _L, _U64, _P, _F, _I, _P],
     "shm_cast": [_P, _I, _P, _I, _L, _P],
     "shm_cast2d": [_P, _I, _I, _P, _I, _I, _L, _I, _P],
     "shm_axpy": [_F, _P, _P, _L, _I, _P],
@@ -89,6 +91,8 @@ _SIG = {
     "shm_c3to1_wgrad": [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P],
     "shm_lsgan": [_P, _L, _F, _P, _F, _P, _F, _I, _P],
     "shm_softmax_ce": [_P, _I, C.POINTER(C.c_float), _P, _F, _P, _F, _I, _P],
+    "shm_lsgan_dev": [_P, _L, _P, _P, _F, _P, _F, _I, _P],
+    "shm_softmax_ce_dev": [_P, _I, _P, _P, _F, _P, _F, _I, _P],
     "shm_l1": [_P, _P, _L, _P, _F, _P, _F, _I, _P],
     "shm_mse": [_P, _P, _L, _P, _F, _P, _F, _I, _P],
     "shm_mse_ycc": [_P, _P, _P, _L, _P, _F, _P, _F, _P],
@@ -101,6 +105,7 @@ _SIG = {
     "shm_ssim_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P],
     "shm_spec_loss": [_P, _P, _P, _P, _L, _P, _F, _P],
     "shm_clip_adam": [_P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _P],
+    "shm_clip_adam_dev": [_P, _P, _P, _P, _L, _P, _F, _F, _F, _F, _F, _P],
     "shm_load_u8_bilinear": [_P, _I, _I, _I, _P, _I, _I, _I, _P],
     "shm_dop": [_P, _P, _P, _P, _P, _P, _L, _P],
     "shm_sqerr_per_image": [_P, _P, _I, _L, _P, _P],
@@ -143,6 +148,12 @@ def load():
 def launches() -> int:
     """Number of kernel-launching C-ABI calls made so far (bench.py's `gpu_launches` evidence)."""
     return _launches
+
+
+def count_replayed(n: int):
+    """A CUDA-graph replay re-launches the n kernels recorded at capture without passing through call()."""
+    global _launches
+    _launches += int(n)
 
 
 def call(name: str, *args):

@@ -16,13 +16,14 @@ inline int flat_grid(long long total, int block = 256) {
 }
 
 // ---- elementwise reductions ----------------------------------------------------------------------
-// mode 0: (a - target)^2 ; mode 1: |a - b| ; mode 2: (a - b)^2
+// mode 0: (a - target)^2 (target = *b when b != NULL: a device-resident scalar) ; mode 1: |a - b| ; mode 2: (a - b)^2
 template <int MODE>
 __global__ void __launch_bounds__(256) ew_loss_kernel(const float* __restrict__ a, const float* __restrict__ b, float target, long long n,
                                                       float* __restrict__ loss_out, float weight, float* __restrict__ da, float gscale, int accumulate) {
     __shared__ double sm[32];
     float acc = 0.f;
     const float inv_n = 1.0f / (float)n;
+    if (MODE == 0 && b != nullptr) target = __ldg(b);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float d = a[i] - (MODE == 0 ? target : b[i]);
         float g;
@@ -35,10 +36,14 @@ __global__ void __launch_bounds__(256) ew_loss_kernel(const float* __restrict__ 
 }
 
 struct Labels5 { float v[5]; };
-__global__ void softmax_ce_kernel(const float* __restrict__ logits, int B, Labels5 lab, float* __restrict__ loss_out, float weight,
-                                  float* __restrict__ dlogits, float gscale, int accumulate) {
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, int B, Labels5 lab, const float* __restrict__ lab_dev,
+                                  float* __restrict__ loss_out, float weight, float* __restrict__ dlogits, float gscale, int accumulate) {
     __shared__ double sm[32];
     float acc = 0.f;
+    if (lab_dev != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j) lab.v[j] = __ldg(lab_dev + j);
+    }
     const float lsum = lab.v[0] + lab.v[1] + lab.v[2] + lab.v[3] + lab.v[4];
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
         float z[5], m = -INFINITY;
@@ -351,7 +356,8 @@ __global__ void ssim_bwd_minmax_kernel(const float* __restrict__ mmA, const int*
 
 // ---- clip + Adam --------------------------------------------------------------------------------
 __global__ void clip_adam_kernel(float* __restrict__ param, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
-                                 long long n, float lr_t, float b1, float b2, float eps, float clip, float gscale) {
+                                 long long n, float lr_t, const float* __restrict__ lr_dev, float b1, float b2, float eps, float clip, float gscale) {
+    if (lr_dev != nullptr) lr_t = __ldg(lr_dev);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float g = grad[i] * gscale;
         g = fminf(fmaxf(g, -clip), clip);
@@ -362,7 +368,8 @@ __global__ void clip_adam_kernel(float* __restrict__ param, const float* __restr
     }
 }
 __global__ void clip_adam_vec_kernel(float4* __restrict__ param, const float4* __restrict__ grad, float4* __restrict__ m, float4* __restrict__ v,
-                                     long long n4, float lr_t, float b1, float b2, float eps, float clip, float gscale) {
+                                     long long n4, float lr_t, const float* __restrict__ lr_dev, float b1, float b2, float eps, float clip, float gscale) {
+    if (lr_dev != nullptr) lr_t = __ldg(lr_dev);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float4 g4 = __ldg(grad + i);
         float4 p4 = param[i], m4 = m[i], v4 = v[i];
@@ -396,7 +403,8 @@ __device__ __forceinline__ uint4 philox(uint64_t seed, uint64_t ctr) {
 __device__ __forceinline__ float u01(uint32_t x) { return ((float)(x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
 
 template <typename T, bool NORMAL>
-__global__ void rng_kernel(T* __restrict__ out, long long n, uint64_t seed, uint64_t offset, float param) {
+__global__ void rng_kernel(T* __restrict__ out, long long n, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ offset_dev, float param) {
+    if (offset_dev != nullptr) offset = __ldg(reinterpret_cast<const unsigned long long*>(offset_dev));
     const long long n4 = (n + 3) / 4;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const uint4 r = philox(seed, offset + (uint64_t)i);
@@ -441,7 +449,23 @@ extern "C" int shm_softmax_ce(const float* logits, int B, const float labels[5],
     SHM_REQUIRE(logits && labels && B > 0, "shm_softmax_ce: bad args");
     Labels5 l;
     for (int j = 0; j < 5; ++j) l.v[j] = labels[j];
-    softmax_ce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, B, l, loss_out, weight, dlogits, gscale, accumulate);
+    softmax_ce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, B, l, nullptr, loss_out, weight, dlogits, gscale, accumulate);
+    SHM_CHECK_LAUNCH("softmax_ce_kernel");
+    return SHM_OK;
+}
+// target / labels read from device memory when the kernel runs: TARGET_LABELS is redrawn every step (ShmGANwithSSpecSeg.py:986) and a step
+// captured in a CUDA graph must see the current value
+extern "C" int shm_lsgan_dev(const float* a, int64_t n, const float* target_dev, float* loss_out, float weight, float* da, float gscale, int accumulate, void* stream) {
+    SHM_REQUIRE(a && target_dev && n > 0, "shm_lsgan_dev: bad args");
+    ew_loss_kernel<0><<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(a, target_dev, 0.f, n, loss_out, weight, da, gscale, accumulate);
+    SHM_CHECK_LAUNCH("lsgan_kernel");
+    return SHM_OK;
+}
+extern "C" int shm_softmax_ce_dev(const float* logits, int B, const float* labels5_dev, float* loss_out, float weight, float* dlogits,
+                                  float gscale, int accumulate, void* stream) {
+    SHM_REQUIRE(logits && labels5_dev && B > 0, "shm_softmax_ce_dev: bad args");
+    Labels5 l{};
+    softmax_ce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, B, l, labels5_dev, loss_out, weight, dlogits, gscale, accumulate);
     SHM_CHECK_LAUNCH("softmax_ce_kernel");
     return SHM_OK;
 }
@@ -527,40 +551,64 @@ extern "C" int shm_ssim_bwd(const float* Y, const float* cbcr, const float* mmA,
     return SHM_OK;
 }
 
-extern "C" int shm_clip_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
-                             float eps, float clip, float gscale, void* stream) {
-    SHM_REQUIRE(param && grad && m && v && n >= 0, "shm_clip_adam: bad args");
+namespace {
+int clip_adam_launch(float* param, const float* grad, float* m, float* v, int64_t n, float lr_t, const float* lr_dev, float beta1, float beta2,
+                     float eps, float clip, float gscale, void* stream) {
     if (n == 0) return SHM_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const uintptr_t al = reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v);
     const long long n4 = ((al & 15) == 0) ? n / 4 : 0;
     if (n4 > 0) {
-        clip_adam_vec_kernel<<<flat_grid(n4), 256, 0, st>>>((float4*)param, (const float4*)grad, (float4*)m, (float4*)v, n4, lr_t, beta1, beta2, eps, clip, gscale);
+        clip_adam_vec_kernel<<<flat_grid(n4), 256, 0, st>>>((float4*)param, (const float4*)grad, (float4*)m, (float4*)v, n4, lr_t, lr_dev, beta1, beta2, eps, clip, gscale);
         SHM_CHECK_LAUNCH("clip_adam_vec_kernel");
     }
     if (n4 * 4 < n) {
         const long long off = n4 * 4;
-        clip_adam_kernel<<<flat_grid(n - off), 256, 0, st>>>(param + off, grad + off, m + off, v + off, n - off, lr_t, beta1, beta2, eps, clip, gscale);
+        clip_adam_kernel<<<flat_grid(n - off), 256, 0, st>>>(param + off, grad + off, m + off, v + off, n - off, lr_t, lr_dev, beta1, beta2, eps, clip, gscale);
         SHM_CHECK_LAUNCH("clip_adam_kernel");
     }
     return SHM_OK;
 }
+}  // namespace
 
-extern "C" int shm_rng_normal(void* out, int64_t n, uint64_t seed, uint64_t offset, float sigma, int dtype, void* stream) {
-    SHM_REQUIRE(out && n >= 0, "shm_rng_normal: bad args");
+extern "C" int shm_clip_adam(float* param, const float* grad, float* m, float* v, int64_t n, float lr_t, float beta1, float beta2,
+                             float eps, float clip, float gscale, void* stream) {
+    SHM_REQUIRE(param && grad && m && v && n >= 0, "shm_clip_adam: bad args");
+    return clip_adam_launch(param, grad, m, v, n, lr_t, nullptr, beta1, beta2, eps, clip, gscale, stream);
+}
+// the step size read from device memory at run time: a step captured in a CUDA graph replays with the current bias-corrected learning rate
+extern "C" int shm_clip_adam_dev(float* param, const float* grad, float* m, float* v, int64_t n, const float* lr_t_dev, float beta1, float beta2,
+                                 float eps, float clip, float gscale, void* stream) {
+    SHM_REQUIRE(param && grad && m && v && lr_t_dev && n >= 0, "shm_clip_adam_dev: bad args");
+    return clip_adam_launch(param, grad, m, v, n, 0.f, lr_t_dev, beta1, beta2, eps, clip, gscale, stream);
+}
+
+namespace {
+int rng_launch(void* out, int64_t n, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, float param, int dtype, bool normal, void* stream) {
     if (n == 0) return SHM_OK;
     DISPATCH_DTYPE(dtype, T, {
-        rng_kernel<T, true><<<flat_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>((T*)out, n, seed, offset, sigma);
-        SHM_CHECK_LAUNCH("rng_normal_kernel");
+        if (normal) rng_kernel<T, true><<<flat_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>((T*)out, n, seed, offset, offset_dev, param);
+        else        rng_kernel<T, false><<<flat_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>((T*)out, n, seed, offset, offset_dev, param);
+        SHM_CHECK_LAUNCH("rng_kernel");
         return SHM_OK;
     })
 }
+}  // namespace
+
+extern "C" int shm_rng_normal(void* out, int64_t n, uint64_t seed, uint64_t offset, float sigma, int dtype, void* stream) {
+    SHM_REQUIRE(out && n >= 0, "shm_rng_normal: bad args");
+    return rng_launch(out, n, seed, offset, nullptr, sigma, dtype, true, stream);
+}
 extern "C" int shm_rng_keep(void* out, int64_t n, uint64_t seed, uint64_t offset, float keep_prob, int dtype, void* stream) {
     SHM_REQUIRE(out && n >= 0, "shm_rng_keep: bad args");
-    if (n == 0) return SHM_OK;
-    DISPATCH_DTYPE(dtype, T, {
-        rng_kernel<T, false><<<flat_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>((T*)out, n, seed, offset, keep_prob);
-        SHM_CHECK_LAUNCH("rng_keep_kernel");
-        return SHM_OK;
-    })
+    return rng_launch(out, n, seed, offset, nullptr, keep_prob, dtype, false, stream);
+}
+// the Philox counter offset read from device memory at run time (CUDA-graph replays draw a fresh stream every step)
+extern "C" int shm_rng_normal_dev(void* out, int64_t n, uint64_t seed, const uint64_t* offset_dev, float sigma, int dtype, void* stream) {
+    SHM_REQUIRE(out && offset_dev && n >= 0, "shm_rng_normal_dev: bad args");
+    return rng_launch(out, n, seed, 0, offset_dev, sigma, dtype, true, stream);
+}
+extern "C" int shm_rng_keep_dev(void* out, int64_t n, uint64_t seed, const uint64_t* offset_dev, float keep_prob, int dtype, void* stream) {
+    SHM_REQUIRE(out && offset_dev && n >= 0, "shm_rng_keep_dev: bad args");
+    return rng_launch(out, n, seed, 0, offset_dev, keep_prob, dtype, false, stream);
 }

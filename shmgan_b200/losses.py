@@ -31,11 +31,19 @@ class LossTable:
 
 
 def lsgan(a, target, slot, weight=1.0, da=None, gscale=0.0, accumulate=False):
-    """weight * mean((a - target)^2); da (+)= gscale * 2 (a - target) / n."""
-    call("shm_lsgan", _p(a), a.numel(), float(target), slot, float(weight), _p(da), float(gscale), int(accumulate), _stream())
+    """weight * mean((a - target)^2); da (+)= gscale * 2 (a - target) / n.  target: a float, or a one-element fp32 CUDA tensor read when the
+    kernel runs (CUDA-graph replays)."""
+    if isinstance(target, torch.Tensor):
+        call("shm_lsgan_dev", _p(a), a.numel(), _p(target), slot, float(weight), _p(da), float(gscale), int(accumulate), _stream())
+    else:
+        call("shm_lsgan", _p(a), a.numel(), float(target), slot, float(weight), _p(da), float(gscale), int(accumulate), _stream())
 
 
 def softmax_ce(logits, labels5, slot, weight=1.0, dlogits=None, gscale=0.0, accumulate=False):
+    """labels5: five floats, or a five-element fp32 CUDA tensor read when the kernel runs."""
+    if isinstance(labels5, torch.Tensor):
+        call("shm_softmax_ce_dev", _p(logits), logits.shape[0], _p(labels5), slot, float(weight), _p(dlogits), float(gscale), int(accumulate), _stream())
+        return
     lab = (C.c_float * 5)(*[float(v) for v in labels5])
     call("shm_softmax_ce", _p(logits), logits.shape[0], lab, slot, float(weight), _p(dlogits), float(gscale), int(accumulate), _stream())
 

@@ -21,6 +21,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import losses as LS
+from . import _lib as L
 from . import nets, ops
 from .ops import _p, _stream, call
 
@@ -227,6 +228,13 @@ class ShmGANwithSSpecSeg:
         # tensor-bound generator kernels; likewise D(xA) forward runs beside the cyclic generator forward
         self.overlap = True
         self._side = None
+        # CUDA-graph replay of train_step (bf16 / fp32 alike, with or without the data-parallel all-reduce): the ~600 launches of a step are
+        # captured once per (drop bits, batch) and replayed with one cudaGraphLaunch; everything that moves from step to step (Philox offsets, Adam's lr_t, TARGET_LABELS)
+        # lives in a small device block the kernels read when they run.  Off by default; `net.cuda_graph = True` turns it on.
+        self.cuda_graph = False
+        self.graph_warmup = 2                               # eager steps before the first capture (lazy allocations, function attributes)
+        self._graphs, self._graph_pool, self._g_in, self._gp = {}, None, None, None
+        self._graph_eager_steps = 0
 
     # -- model builders (same names as the reference) --------------------------------------------------------------
     def build_generator(self):
@@ -305,17 +313,136 @@ class ShmGANwithSSpecSeg:
         for k in _LOSS_ATTRS:                               # the previous step's scalars (read or not) are stale now
             self.__dict__.pop(k, None)
         self.__dict__.pop("gen_rgb_output", None)
-        ops.arena_begin()
-        G, D = self.G.net, self.D.net
-        G.store.refresh_tc_all()                            # bf16 weight copies of every layer, one launch per network
-        D.store.refresh_tc_all()
         origs = [t.contiguous() for t in (orig0, orig45, orig90, orig135, origED)]
         B, S = origs[0].shape[0], origs[0].shape[1]
         assert S == self.image_size and all(tuple(t.shape) == (B, S, S, 3) and t.dtype == torch.float32 for t in origs)
+        bits = list(self.drop_bits) if self.drop_bits is not None else [self._rng.random() < self.randomness for _ in range(5)]
+        if self.cuda_graph and self.d_noise is None and ops.PROF is None:
+            self._train_step_graph(origs, bits)
+        else:
+            self._train_step_body(origs, bits, None)
+            self._start_loss_readback()
+        return None
+
+    # -- CUDA-graph mode -------------------------------------------------------------------------------------------------
+    class _GraphParams:
+        """Device block of the per-step scalars: f = [lr_t(D), lr_t(G), T, labels(0, 0, 0, 0, T)] fp32, i = [noise offset, keep offset] int64."""
+
+        def __init__(self):
+            self.f = ops.zeros((8,), torch.float32)
+            self.i = ops.zeros((2,), torch.int64)
+            self.lr_D, self.lr_G, self.T, self.labels = self.f[0:1], self.f[1:2], self.f[2:3], self.f[3:8]
+            self.off_noise, self.off_keep = self.i[0:1], self.i[1:2]
+
+    _PUBLISHED = ("specular_candidate", "gen_input", "gen_Y", "gen_rgb", "averageCbCr", "ds_yuv", "cyc_Y", "cyc_gen0_rgb", "cyc_gen45_rgb",
+                  "cyc_gen90_rgb", "cyc_gen135_rgb", "cyc_genED_rgb", "RealFake_gen_D1", "label_gen_D1", "RealFake_target_D2",
+                  "label_target_D2", "RealFake_cyc_D3", "label_cyc_D3", "RealFake_orig_D4", "label_orig0_D4", "label_orig45_D4",
+                  "label_orig90_D4", "label_orig135_D4", "label_origED_D4", "ssim_values")
+
+    def _write_graph_params(self):
+        """This step's scalars, computed on the host exactly as the eager path computes them, copied into the device block (a pageable
+        source: cudaMemcpyAsync stages it at call time, so the host may run ahead of the GPU)."""
+        G, D, T = self.G.net.store, self.D.net.store, float(self.TARGET_LABELS)
+        f = torch.tensor([D.lr_t(self.g_lr, self.beta1, self.beta2), G.lr_t(self.g_lr, self.beta1, self.beta2), T, 0.0, 0.0, 0.0, 0.0, T],
+                         dtype=torch.float32)
+        i = torch.tensor([(4 * self.step_count) << 32, (4 * self.step_count + 2) << 32], dtype=torch.int64)
+        self._gp.f.copy_(f, non_blocking=True)
+        self._gp.i.copy_(i, non_blocking=True)
+
+    def _train_step_graph(self, origs, bits):
+        B = origs[0].shape[0]
+        if self._gp is None:
+            self._gp = ShmGANwithSSpecSeg._GraphParams()
+        if self._g_in is None or tuple(self._g_in[0].shape) != tuple(origs[0].shape):
+            self._g_in = [ops.new(tuple(o.shape), torch.float32) for o in origs]
+            self._graphs.clear()                            # captured against the old input buffers
+        for dst, src in zip(self._g_in, origs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)           # cudaMemcpyAsync, device to device
+        self._write_graph_params()
+        key = (tuple(bool(b) for b in bits), B)
+        entry = self._graphs.get(key)
+        if entry is None and self._graph_eager_steps < max(2, self.graph_warmup):    # (layers join the batched weight refresh in step 2)
+            self._graph_eager_steps += 1                    # same code path as the capture, executed eagerly
+            self._train_step_body(self._g_in, bits, self._gp)
+            self._start_loss_readback()
+            return
+        G, D = self.G.net.store, self.D.net.store
+        in_graph_opt = self._reducer is None                # data parallel: all-reduce + clip + Adam follow the replay as ordinary launches
+        if entry is None:
+            if self._graph_pool is None:
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.launches()
+            saved = (self.step_count, [(st.step, st.version, getattr(st, "_finalized", False)) for st in (D, G)])
+            try:
+                # thread_local: other threads (NCCL's watchdog) may keep calling the CUDA API while this thread captures
+                with torch.cuda.graph(g, pool=self._graph_pool, capture_error_mode="thread_local"):
+                    self._train_step_body(self._g_in, bits, self._gp, with_opt=in_graph_opt)   # records the launches; the host bookkeeping runs here
+            except Exception as ex:                         # e.g. a collective that cannot be captured: stay eager from here on
+                import warnings
+                warnings.warn("train_step: CUDA-graph capture failed (%s: %s); continuing eagerly" % (type(ex).__name__, ex))
+                self.cuda_graph = False
+                self.step_count = saved[0]
+                for st, (a, b, c) in zip((D, G), saved[1]):
+                    st.step, st.version, st._finalized = a, b, c
+                if self._reducer is not None:
+                    self._reducer.pending = []
+                torch.cuda.synchronize()
+                self._train_step_body(origs, bits, None)
+                self._start_loss_readback()
+                return
+            entry = (g, {k: self.__dict__[k] for k in self._PUBLISHED if k in self.__dict__}, L.launches() - n0)
+            self._graphs[key] = entry
+            g.replay()
+        else:
+            g, pub, nk = entry
+            g.replay()
+            L.count_replayed(nk)
+            # the bookkeeping _train_step_body does on the host
+            self.__dict__.update(pub)
+            self.last_drop_bits = list(bits)
+            for st in (D, G):
+                if in_graph_opt:
+                    st.step += 1
+                    st.version += 1
+                st._finalized = True
+            self.step_count += 1
+        if not in_graph_opt:
+            self._reduce_and_step()
+        self._start_loss_readback()
+
+    def release_graphs(self):
+        """Drops the captured graphs, their memory pool and the static input buffers (the next train_step captures afresh)."""
+        self._graphs.clear()
+        self._graph_pool = self._g_in = None
+        self._graph_eager_steps = 0
+
+    def _reduce_and_step(self):
+        """Data-parallel tail of a replayed step: all-reduce of both flat gradient buffers (NCCL's stream), then clip + Adam on the average.
+        (Measured at 8 GPUs, profiles/r02_negative_results.txt #5: reducing after the sweep costs < 0.2 ms against the overlapped form.)"""
+        G, D, r = self.G.net.store, self.D.net.store, self._reducer
+        r.reduce_async(D.grad)
+        r.reduce_async(G.grad)
+        r.wait()
+        gscale = 1.0 / r.world
+        D.adam_step(self.g_lr, self.beta1, self.beta2, 1e-7, 1.0, gscale)
+        G.adam_step(self.g_lr, self.beta1, self.beta2, 1e-7, 1.0, gscale)
+
+    def _train_step_body(self, origs, bits, gp, with_opt=True):
+        """One step on the current stream.  gp: the device block of per-step scalars (graph mode) or None (host scalars in the launches).
+        with_opt = False stops after the backward sweeps: no gradient all-reduce, no clip + Adam (`_reduce_and_step` does them) -- what a
+        data-parallel step records into its CUDA graph, so that no NCCL kernel ever sits inside a graph."""
+        reducer = self._reducer if with_opt else None
+        ops.arena_begin(whole=gp is not None)
+        G, D = self.G.net, self.D.net
+        G.store.refresh_tc_all()                            # bf16 weight copies of every layer, one launch per network
+        D.store.refresh_tc_all()
+        B, S = origs[0].shape[0], origs[0].shape[1]
         dt, f32 = self.dtype, torch.float32
         npix = B * S * S
-        T = float(self.TARGET_LABELS)
-        bits = list(self.drop_bits) if self.drop_bits is not None else [self._rng.random() < self.randomness for _ in range(5)]
+        T = float(self.TARGET_LABELS) if gp is None else gp.T
         self.last_drop_bits = bits
         tab = self.table
         tab.zero()
@@ -356,9 +483,9 @@ class ShmGANwithSSpecSeg:
         if self.d_noise is not None:
             noise, keep = ops.cast(self.d_noise.contiguous(), dt), ops.cast(self.d_keep.contiguous(), dt)
         else:
-            noise = ops.rng_normal((2 * B, S, S, 3), self.noise_seed, (4 * self.step_count) << 32, 0.1, dt)
-            keep = ops.rng_keep((2 * B, s32, s32, D.blocks[-1].conv.cout), self.noise_seed, (4 * self.step_count + 2) << 32,
-                                1.0 - self.dropout_amnt, dt)
+            noise = ops.rng_normal((2 * B, S, S, 3), self.noise_seed, (4 * self.step_count) << 32 if gp is None else gp.off_noise, 0.1, dt)
+            keep = ops.rng_keep((2 * B, s32, s32, D.blocks[-1].conv.cout), self.noise_seed,
+                                (4 * self.step_count + 2) << 32 if gp is None else gp.off_keep, 1.0 - self.dropout_amnt, dt)
         side = self._side_stream()
         if side is not None:
             side.wait_stream(torch.cuda.current_stream())
@@ -411,7 +538,7 @@ class ShmGANwithSSpecSeg:
         LS.lsgan(rfA[:B], 0.0, tab.slot("D2_rf"), 1.0, dD_rfA[:B], 2.0 * sixth)
         LS.lsgan(rfB[5 * B:], T, tab.slot("D4_rf_only"), 5.0, dD_rfB[5 * B:], 5.0 * sixth)           # :723-727
         LS.lsgan(rfB[:5 * B], 0.0, tab.slot("D4_rf_only"), 5.0, dD_rfB[:5 * B], 5.0 * sixth)
-        LS.softmax_ce(clsA[:B], [0, 0, 0, 0, T], tab.slot("D1_cls"), 1.0, dD_clsA[:B], sixth)         # :702
+        LS.softmax_ce(clsA[:B], [0, 0, 0, 0, T] if gp is None else gp.labels, tab.slot("D1_cls"), 1.0, dD_clsA[:B], sixth)   # :702
         for k in range(5):
             onehot = [1.0 if j == k else 0.0 for j in range(5)]
             LS.softmax_ce(clsB[k * B:(k + 1) * B], onehot, tab.slot("D3_cls"), 1.0, dD_clsB[k * B:(k + 1) * B], sixth)      # :695-700
@@ -447,8 +574,8 @@ class ShmGANwithSSpecSeg:
             if self.live_mask:
                 D.attention_backward(d_attn_saved, d_dattn)
             D.store.finalize_grads()
-            if self._reducer is not None:
-                self._reducer.reduce_async(D.store.grad)
+            if reducer is not None:
+                reducer.reduce_async(D.store.grad)
 
         if side is not None:
             side.wait_stream(torch.cuda.current_stream())
@@ -477,27 +604,28 @@ class ShmGANwithSSpecSeg:
         # gradient buffer is all-reduced (NCCL's stream) as soon as its last weight-gradient kernel is enqueued, while the rest of the
         # backward keeps computing; only the encoder / attention head of the buffer is reduced after the sweep
         hook = None
-        if self._reducer is not None and self.dp_overlap:
+        if reducer is not None and self.dp_overlap:
             def hook(stage):
                 lo, hi = G.grad_range(stage)
-                self._reducer.reduce_async(G.store.grad, lo, hi)
+                reducer.reduce_async(G.store.grad, lo, hi)
         G.backward(tape1, ops.cast(d_gen_Y, dt), g_dattn, attn_nb=B, need_dx=False, hook=hook)
         if self.live_mask:
             G.attention_backward(g_attn_saved, g_dattn)
         G.store.finalize_grads()
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
-        if self._reducer is not None:
+        if reducer is not None:
             if hook is not None:
                 hook("head")
             else:
-                self._reducer.reduce_async(G.store.grad)     # dp_overlap = False: one reduction of the whole buffer after the sweep
-            self._reducer.wait()
+                reducer.reduce_async(G.store.grad)           # dp_overlap = False: one reduction of the whole buffer after the sweep
+            reducer.wait()
 
         # ---- clip_by_value(+-1) + Adam (:860-871); both optimisers use g_lr (:169-174)
-        gscale = 1.0 if self._reducer is None else 1.0 / self._reducer.world
-        D.store.adam_step(self.g_lr, self.beta1, self.beta2, 1e-7, 1.0, gscale)
-        G.store.adam_step(self.g_lr, self.beta1, self.beta2, 1e-7, 1.0, gscale)
+        if with_opt:
+            gscale = 1.0 if reducer is None else 1.0 / reducer.world
+            D.store.adam_step(self.g_lr, self.beta1, self.beta2, 1e-7, 1.0, gscale, lr_dev=None if gp is None else gp.lr_D)
+            G.store.adam_step(self.g_lr, self.beta1, self.beta2, 1e-7, 1.0, gscale, lr_dev=None if gp is None else gp.lr_G)
         self.step_count += 1
 
         # ---- published tensors / scalars (reference attribute names)
@@ -514,8 +642,6 @@ class ShmGANwithSSpecSeg:
         self.RealFake_orig_D4 = [rfB[(5 + k) * B:(6 + k) * B] for k in range(5)]
         (self.label_orig0_D4, self.label_orig45_D4, self.label_orig90_D4, self.label_orig135_D4,
          self.label_origED_D4) = [clsB[(5 + k) * B:(6 + k) * B] for k in range(5)]
-        self._start_loss_readback()
-        return None
 
     def _start_loss_readback(self):
         """Asynchronous device->host copy of the loss table into pinned memory; the scalars are published when first read

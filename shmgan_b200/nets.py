@@ -227,15 +227,23 @@ class ParamStore:
             c.fold_pad_grad()
         self._finalized = True
 
-    def adam_step(self, lr0=2e-5, beta1=0.5, beta2=0.99, eps=1e-7, clip=1.0, gscale=1.0,
-                  decay_steps=10000.0, decay_rate=0.95):
-        """clip_by_value(+-1) + Keras Adam with ExponentialDecay (ShmGANwithSSpecSeg.py:169-175, :860-871)."""
-        self.finalize_grads()
+    def lr_t(self, lr0=2e-5, beta1=0.5, beta2=0.99, decay_steps=10000.0, decay_rate=0.95) -> float:
+        """Step size of the NEXT adam_step: ExponentialDecay learning rate x Adam bias correction (ShmGANwithSSpecSeg.py:169-175)."""
         t = self.step + 1
         lr = lr0 * decay_rate ** (self.step / decay_steps)
-        lr_t = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
-        ops.call("shm_clip_adam", ops._p(self.flat), ops._p(self.grad), ops._p(self.m), ops._p(self.v), self.n_train,
-                 lr_t, beta1, beta2, eps, clip, gscale, ops._stream())
+        return lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+
+    def adam_step(self, lr0=2e-5, beta1=0.5, beta2=0.99, eps=1e-7, clip=1.0, gscale=1.0,
+                  decay_steps=10000.0, decay_rate=0.95, lr_dev=None):
+        """clip_by_value(+-1) + Keras Adam with ExponentialDecay (ShmGANwithSSpecSeg.py:169-175, :860-871).
+        lr_dev: one-element fp32 CUDA tensor holding lr_t(), read when the kernel runs (a captured step is replayed with the current value)."""
+        self.finalize_grads()
+        if lr_dev is not None:
+            ops.call("shm_clip_adam_dev", ops._p(self.flat), ops._p(self.grad), ops._p(self.m), ops._p(self.v), self.n_train,
+                     ops._p(lr_dev), beta1, beta2, eps, clip, gscale, ops._stream())
+        else:
+            ops.call("shm_clip_adam", ops._p(self.flat), ops._p(self.grad), ops._p(self.m), ops._p(self.v), self.n_train,
+                     self.lr_t(lr0, beta1, beta2, decay_steps, decay_rate), beta1, beta2, eps, clip, gscale, ops._stream())
         self.step += 1
         self.version += 1
 

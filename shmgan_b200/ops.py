@@ -56,11 +56,14 @@ _ARENA_ON = False
 ARENA_DOUBLES = 8 << 20
 
 
-def arena_begin():
-    """Start of a train / inference step: recycle the arena (clears the part the previous step used, on the current stream)."""
+def arena_begin(whole: bool = False):
+    """Start of a train / inference step: recycle the arena (clears the part the previous step used, on the current stream).
+    whole: clear all of it -- a step being captured into a CUDA graph must not depend on how much the step before it happened to use."""
     global _ARENA, _ARENA_USED, _ARENA_ON
     if _ARENA is None:
         _ARENA = zeros((ARENA_DOUBLES,), torch.float64)
+    elif whole:
+        zero_(_ARENA)
     elif _ARENA_USED:
         zero_(_ARENA[:_ARENA_USED])
     _ARENA_USED, _ARENA_ON = 0, True
@@ -552,14 +555,21 @@ def axpy(alpha, x, y):
 
 
 def rng_normal(shape, seed, offset, sigma, dtype):
+    """offset: an int, or a one-element int64 CUDA tensor read when the kernel runs (CUDA-graph replays)."""
     out = new(shape, dtype)
-    call("shm_rng_normal", _p(out), out.numel(), seed, offset, float(sigma), dt(out), _stream())
+    if isinstance(offset, torch.Tensor):
+        call("shm_rng_normal_dev", _p(out), out.numel(), seed, _p(offset), float(sigma), dt(out), _stream())
+    else:
+        call("shm_rng_normal", _p(out), out.numel(), seed, offset, float(sigma), dt(out), _stream())
     return out
 
 
 def rng_keep(shape, seed, offset, keep_prob, dtype):
     out = new(shape, dtype)
-    call("shm_rng_keep", _p(out), out.numel(), seed, offset, float(keep_prob), dt(out), _stream())
+    if isinstance(offset, torch.Tensor):
+        call("shm_rng_keep_dev", _p(out), out.numel(), seed, _p(offset), float(keep_prob), dt(out), _stream())
+    else:
+        call("shm_rng_keep", _p(out), out.numel(), seed, offset, float(keep_prob), dt(out), _stream())
     return out
 
 

@@ -275,3 +275,54 @@ def test_random_specseg_weights_must_be_asked_for():
     assert rel_err(got, O.inference_step(Gp, Sp, rgb.double().cpu())["gen_rgb"]) < 1e-3
     with pytest.raises(ValueError):
         net.SpecSeg.load_keras_weights([v.numpy() for v in Sp.values()][:-1])
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_train_step_cuda_graph_replay_matches_eager(dtype):
+    """net.cuda_graph = True: the step is captured once per drop-bit pattern and replayed.  Six steps with two alternating bit patterns, a fresh
+    TARGET_LABELS draw every step (ShmGANwithSSpecSeg.py:986) and moving Adam / Philox counters must leave the same parameters, losses and
+    published tensors as six eager steps (fp32 atomics make the two runs agree to rounding, not bitwise); the replayed steps must also count
+    their kernels (gpu_launches evidence of bench.py)."""
+    from shmgan_b200 import _lib, model as M
+    S, B = 64, 2
+    g = torch.Generator().manual_seed(77)
+    pol = [torch.rand((B, S, S, 3), generator=g).cuda() for _ in range(4)]
+    batch = pol + [torch.minimum(torch.minimum(pol[0], pol[1]), torch.minimum(pol[2], pol[3]))]
+    patterns = [[True, False, True, False, False], [False, False, False, True, False]]
+    Ts = [0.9, 1.1, 0.83, 1.17, 0.95, 1.02]
+
+    def run(graph):
+        net = M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B, filter_size=16), dtype=dtype, allow_random_specseg=True).build()
+        net.noise_seed, net.cuda_graph = 11, graph                  # two eager warm-up steps, captures at steps 3 and 4, replays at 5 and 6
+        p0 = {n: getattr(net, n).net.store.flat.clone() for n in ("G", "D")}
+        losses, counts = [], []
+        for i, T in enumerate(Ts):
+            net.drop_bits, net.TARGET_LABELS = patterns[i % 2], T
+            n0 = _lib.launches()
+            net.train_step(*batch)
+            counts.append(_lib.launches() - n0)
+            losses.append((net.total_Generator_loss, net.D1_classification_loss, net.D2_RealFake_target))
+        torch.cuda.synchronize()
+        move = {n: (getattr(net, n).net.store.flat - p0[n]).double() for n in ("G", "D")}
+        return net, losses, counts, move
+
+    # Two eager runs differ too: fp32 atomics reorder the weight-gradient sums, and Adam's first steps move a parameter by ~lr * 5 * sign(g), so
+    # a gradient that is pure rounding noise (a conv bias in front of an instance norm) takes a different +-2e-5 walk in every run.  The graph
+    # run is held to 3 x what the second eager run measures (+ a floor), on the movement of the parameters over the six steps.
+    eager, le, ce, me = run(False)
+    eager2, le2, _, me2 = run(False)
+    graph, lg, cg, mg = run(True)
+    assert len(graph._graphs) == 2 and graph.step_count == eager.step_count == len(Ts)
+    assert graph.G.net.store.step == eager.G.net.store.step and graph.D.net.store.step == eager.D.net.store.step
+    assert min(cg[4:]) > 100 and cg[4] == cg[2] and cg[5] == cg[3]      # the replays (steps 5, 6) count the kernels recorded at capture
+    tol = 2e-4 if dtype == "fp32" else 5e-2
+    for a, b in zip(le, lg):
+        for x, y in zip(a, b):
+            assert y == pytest.approx(x, rel=tol, abs=tol * 1e-2)
+    for name in ("G", "D"):
+        base = float(me[name].norm())
+        noise_l2, noise_max = float((me2[name] - me[name]).norm()) / base, float((me2[name] - me[name]).abs().max())
+        got_l2, got_max = float((mg[name] - me[name]).norm()) / base, float((mg[name] - me[name]).abs().max())
+        assert base > 0 and got_l2 <= 3.0 * noise_l2 + 5e-3 and got_max <= 3.0 * noise_max + 1e-6, (name, got_l2, noise_l2, got_max, noise_max)
+    assert rel_err(graph.gen_rgb, eager.gen_rgb.double().cpu()) < (1e-3 if dtype == "fp32" else 5e-2)
+    assert rel_err(graph.cyc_genED_rgb, eager.cyc_genED_rgb.double().cpu()) < (1e-3 if dtype == "fp32" else 5e-2)
