@@ -326,3 +326,36 @@ def test_train_step_cuda_graph_replay_matches_eager(dtype):
         assert base > 0 and got_l2 <= 3.0 * noise_l2 + 5e-3 and got_max <= 3.0 * noise_max + 1e-6, (name, got_l2, noise_l2, got_max, noise_max)
     assert rel_err(graph.gen_rgb, eager.gen_rgb.double().cpu()) < (1e-3 if dtype == "fp32" else 5e-2)
     assert rel_err(graph.cyc_genED_rgb, eager.cyc_genED_rgb.double().cpu()) < (1e-3 if dtype == "fp32" else 5e-2)
+
+
+def test_inference_step_cuda_graph_replay_matches_eager():
+    """inference_step under net.cuda_graph: the first call is eager, the second records, later calls replay -- on NEW input images each time;
+    after a training step the graph recorded against the old weights is dropped and a new one recorded."""
+    from shmgan_b200 import _lib, model as M
+    S, B = 64, 2
+    g = torch.Generator().manual_seed(5)
+    imgs = [torch.rand((B, S, S, 3), generator=g).cuda() for _ in range(5)]
+    mk = lambda: M.ShmGANwithSSpecSeg(M.default_args(image_size=S, batch_size=B, filter_size=16), dtype="bf16", allow_random_specseg=True).build()
+    eager, graph = mk(), mk()
+    graph.cuda_graph = True
+    for i, img in enumerate(imgs[:4]):
+        want = eager.inference_step(img, cyclic=(i == 3)).clone()
+        n0 = _lib.launches()
+        got = graph.inference_step(img, cyclic=(i == 3))
+        assert _lib.launches() - n0 > 50
+        # same kernels in the same order; only the fp64 atomics of the instance-norm statistics may land in another order (a bf16 ulp here and there)
+        assert rel_err(got, want.double().cpu()) < 2e-2, i
+        assert rel_err(graph.specular_candidate, eager.specular_candidate.double().cpu()) < 2e-2
+    assert abs(eager.stddev_arr.mean() - graph.stddev_arr.mean()) < 1e-12 and len(eager.stddev_arr) == len(graph.stddev_arr)
+    assert sum(1 for k in graph._graphs if k[0] == "infer") == 1      # the cyclic call (first of its kind) ran eagerly
+    pol = [torch.rand((B, S, S, 3), generator=g).cuda() for _ in range(4)]
+    batch = pol + [torch.minimum(torch.minimum(pol[0], pol[1]), torch.minimum(pol[2], pol[3]))]
+    for net in (eager, graph):
+        net.cuda_graph = False
+        net.drop_bits, net.noise_seed = [False] * 5, 3
+        net.train_step(*batch)
+    graph.cuda_graph = True
+    for _ in range(3):                                          # eager (already warm) -> would replay a STALE graph if the key ignored the weights
+        got = graph.inference_step(imgs[4])
+    assert rel_err(got, eager.inference_step(imgs[4]).double().cpu()) < 5e-2
+    assert sum(1 for k in graph._graphs if k[0] == "infer") == 1
