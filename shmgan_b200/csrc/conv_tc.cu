@@ -58,6 +58,12 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, ui
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// the same box into L2 only: no shared-memory destination, no barrier -- hides the HBM part of a later tma_load_4d's latency when the kernel
+// cannot afford another shared-memory stage
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+                 ::"l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
@@ -885,8 +891,9 @@ struct ScatResCfg {
     static constexpr int SMEM = W_BYTES + STG_BYTES + STAGES * HALO_STAGE + FIXED;
 };
 
+constexpr int SCAT_RES_THREADS = 320;   // producer + MMA issuer + EIGHT epilogue warps (two per TMEM lane quadrant, 32 columns each)
 template <int KC>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(SCAT_RES_THREADS, 1)
 conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ScatOutMaps om,
                      const ScatResParams p) {
     using Cfg = ScatResCfg<KC>;
@@ -912,7 +919,7 @@ conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         prefetch_tmap(&tmA); prefetch_tmap(&tmB);
         for (int a = 0; a < 4; ++a) prefetch_tmap(&om.m[a]);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 4); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 8); }
         mbar_init(wbar, 1);
         fence_barrier_init();
     }
@@ -934,6 +941,16 @@ conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const int img = tile / per_img; const int r = tile - img * per_img;
             const int y0 = (r / p.tiles_x) * 16 - 1, x0 = (r % p.tiles_x) * 8 - 1;
+            // With the weights and the store staging resident there is room for two halo stages only: a stage is refilled when its 36 MMAs
+            // (~2100 cycles) retire, and the refill takes a full HBM round trip (~3000 cycles) -- ncu showed the tensor pipe at 32 % of a 55 %
+            // ceiling with DRAM at 38 %.  The halo boxes of this CTA's NEXT tile are prefetched into L2 here, one tile time ahead.
+            const int nxt = tile + gridDim.x;
+            if (nxt < p.total_tiles && elect_one_sync()) {
+                const int nimg = nxt / per_img; const int nr = nxt - nimg * per_img;
+                for (int kc = 0; kc < KC; ++kc)
+                    tma_prefetch_4d(&tmA, kc * 64, (nr % p.tiles_x) * 8 - 1, (nr / p.tiles_x) * 16 - 1, nimg);
+            }
+            __syncwarp();
             for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(&empty[stage], phase ^ 1);
                 if (elect_one_sync()) {
@@ -983,9 +1000,13 @@ conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         // tile's MMAs: ncu showed the tensor pipe 27 % active and L1 75 % busy).  Instead each accumulator is packed, staged in shared memory in the
         // TMA swizzle and handed to the TMA engine as ONE 16 x 8-pixel box of its parity class (om.m[class]: the class's pixels as a dense tensor
         // with doubled pixel / row strides; image borders are clipped by the map).
+        // EIGHT warps: with four, ncu's source view had the epilogue warps issuing ~95 % of the time (bias + LeakyReLU + pack of 4 x 64 columns per
+        // thread and tile is ~1300 instructions against ~4200 cycles of MMAs, plus the tcgen05.ld / barrier / store latencies): 7900 cycles per tile.
+        // Warps 2-5 take columns 0-31 of their TMEM lane quadrant, warps 6-9 columns 32-63.
         const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
-        const bool leader = quad == 0 && lane == 0;
+        const bool leader = warp == 2 && lane == 0;
         int local = 0;
         uint32_t cnt = 0;
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++local) {
@@ -996,15 +1017,12 @@ conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             tc_fence_after();
 #pragma unroll 1
             for (int a = 0; a < 4; ++a, ++cnt) {
-                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * SET + a * BN);
-                uint32_t r32[2][32];
-                tmem_ld32_nw(taddr, r32[0]);
-                tmem_ld32_nw(taddr + 32, r32[1]);
-                uint4 pk[8];
-                tmem_wait_ld32(r32[0]);
-                epi_pack<32>(r32[0], p.bias ? sbias : nullptr, p.act, pk);
-                tmem_wait_ld32(r32[1]);
-                epi_pack<32>(r32[1], p.bias ? sbias + 32 : nullptr, p.act, pk + 4);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * SET + a * BN + half * 32);
+                uint32_t r32[32];
+                tmem_ld32_nw(taddr, r32);
+                uint4 pk[4];
+                tmem_wait_ld32(r32);
+                epi_pack<32>(r32, p.bias ? sbias + half * 32 : nullptr, p.act, pk);
                 if (a == 3) {                              // the last accumulator of the set is in registers: hand the TMEM buffer back
                     tc_fence_before();
                     __syncwarp();
@@ -1013,14 +1031,14 @@ conv_scat_res_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                 const uint32_t sb = smem_u32(sStage + (cnt & 1) * Cfg::STG_TILE);
                 // the bulk store that read this staging tile two accumulators ago must be done reading it
                 if (leader) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t addr = sb + (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4);
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t addr = sb + (uint32_t)row * 128u + (uint32_t)(((half * 4 + c) ^ (row & 7)) << 4);
                     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c].x), "r"(pk[c].y), "r"(pk[c].z), "r"(pk[c].w) : "memory");
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (leader) {
                     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                                  ::"l"(&om.m[a]), "r"(sb), "r"(0), "r"(x0t), "r"(y0t), "r"(img) : "memory");
@@ -1682,11 +1700,11 @@ int launch_scatter(int N, int Hq, int Wq, int K, int Nn, const void* in, int ldi
             if (K == 64) {
                 static bool attr = false;
                 if (!attr) { cudaFuncSetAttribute(conv_scat_res_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScatResCfg<1>::SMEM); attr = true; }
-                conv_scat_res_kernel<1><<<grid, TC_THREADS, ScatResCfg<1>::SMEM, st>>>(tmA, tmB, om, q);
+                conv_scat_res_kernel<1><<<grid, SCAT_RES_THREADS, ScatResCfg<1>::SMEM, st>>>(tmA, tmB, om, q);
             } else {
                 static bool attr = false;
                 if (!attr) { cudaFuncSetAttribute(conv_scat_res_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ScatResCfg<2>::SMEM); attr = true; }
-                conv_scat_res_kernel<2><<<grid, TC_THREADS, ScatResCfg<2>::SMEM, st>>>(tmA, tmB, om, q);
+                conv_scat_res_kernel<2><<<grid, SCAT_RES_THREADS, ScatResCfg<2>::SMEM, st>>>(tmA, tmB, om, q);
             }
             SHM_CHECK_LAUNCH("conv_scat_res_kernel");
             return SHM_OK;
