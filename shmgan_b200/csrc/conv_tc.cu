@@ -1251,12 +1251,14 @@ constexpr int BIG2_SMEM = BIG_A_STAGES * BIG_A_ST + B2_STAGES * B2_ST + 1024 + 5
 
 // NBUF / NPAIR as in conv_multi_kernel: <2, 2> = "big" (two accumulators per weight tile, double-buffered), <1, 1> = stride-2 "scatter" with
 // 128 columns (four parity accumulators = all of TMEM; pairing halves its weight stream, which is what bounds it)
-// EIGHT epilogue warps per CTA (two per TMEM lane quadrant, 64 of the 128 columns each).  With four, the stride-2 scatter configuration was bound
-// by its epilogue warps' issue rate, like conv_scat_res_kernel before it: 2 accumulators x 128 columns of bias + activation + pack + scattered
-// stores per thread against 64-80 MMAs of 64 cycles per item (ncu: tensor pipe 42-46 %).
-constexpr int BIG2_THREADS = 320;
+// Epilogue warps per CTA: four for the stride-1 "big" configuration, EIGHT (two per TMEM lane quadrant, 64 of the 128 columns each) for the
+// stride-2 scatter configuration.  With four, the scatter epilogue was bound by its warps' issue rate, like conv_scat_res_kernel before it
+// (2 accumulators x 128 columns of bias + activation + pack + scattered stores per thread against 64-80 MMAs of 64 cycles per item; ncu: tensor
+// pipe 42-46 %): +5 %.  The big configuration has 144+ MMAs per item to hide its epilogue behind and LOST 1.7 % with eight warps (eight spinning
+// mbarrier waiters instead of four beside the MMA issuer), so it keeps four.
+template <int NPAIR> struct Big2Epi { static constexpr int WARPS = NPAIR == 1 ? 8 : 4, THREADS = 64 + 32 * WARPS, COLS = 512 / WARPS; };
 template <int NBUF, int NPAIR>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(BIG2_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Big2Epi<NPAIR>::THREADS, 1)
 conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const MultiParams p) {
     constexpr int BN = 128;
     extern __shared__ uint8_t smem_raw[];
@@ -1269,7 +1271,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint64_t* fullB = emptyA + BIG_A_STAGES;             // leader only
     uint64_t* emptyB = fullB + B2_STAGES;
     uint64_t* tfull = emptyB + B2_STAGES;                // [2]
-    uint64_t* tempty = tfull + 2;                        // [2] leader only: 8 epilogue warps x 2 CTAs
+    uint64_t* tempty = tfull + 2;                        // [2] leader only: the epilogue warps of both CTAs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
     float* sbias = reinterpret_cast<float*>(sB + B2_STAGES * B2_ST + 512);
 
@@ -1292,7 +1294,7 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // slot only after the multicast commit that released it.
         for (int i = 0; i < BIG_A_STAGES; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
         for (int i = 0; i < B2_STAGES; ++i) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 2 * Big2Epi<NPAIR>::WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc_2sm(tmem_slot, 512);
@@ -1380,7 +1382,8 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp >= 2) {
         // ===== epilogue (both CTAs): own accumulators -> bias + activation -> bf16 -> global; hands the buffer back to the LEADER's MMA warp =====
         const int quad = warp & 3;
-        const int ch = ((warp - 2) >> 2) * 64;           // this warp's 64 of the accumulator's 128 columns
+        constexpr int CW = Big2Epi<NPAIR>::COLS;         // columns of the accumulator this warp handles: all 128, or 64 (eight warps)
+        const int ch = ((warp - 2) >> 2) * CW;
         const int row = quad * 32 + lane;
         const int ty = row >> 3, tx = row & 7;
         int local = 0;
@@ -1399,8 +1402,8 @@ conv_big2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int oy = (qy + p.row_dy[c]) * p.OS + p.py[c], ox = qx * p.OS + p.px[c];
                 const bool ok = valid && oy < p.Hout && ox < p.Wout;
                 bf16* dst = p.out + ((long long)((valid ? img : 0) * p.Hout + (ok ? oy : 0)) * p.Wout + (ok ? ox : 0)) * p.ldout + nt * BN + ch;
-                epi_row<2>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN + ch), p.bias ? sbias + nt * BN + ch : nullptr,
-                           p.act, dst, ok, p.nstore - nt * BN - ch);
+                epi_row<CW / 32>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * set_cols + a * BN + ch), p.bias ? sbias + nt * BN + ch : nullptr,
+                                 p.act, dst, ok, p.nstore - nt * BN - ch);
             }
             tc_fence_before();
             __syncwarp();
@@ -1585,7 +1588,7 @@ int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const MultiPar
     static int max_clusters = 0;
     if (max_clusters == 0) {
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(shm_num_sms() & ~1); cfg.blockDim = dim3(BIG2_THREADS); cfg.dynamicSmemBytes = BIG2_SMEM;
+        cfg.gridDim = dim3(shm_num_sms() & ~1); cfg.blockDim = dim3(Big2Epi<NPAIR>::THREADS); cfg.dynamicSmemBytes = BIG2_SMEM;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
@@ -1596,7 +1599,7 @@ int launch_pair_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const MultiPar
     }
     const int pairs = ((p.m_tiles + 1) / 2) * p.n_tiles * (p.halves > 1 ? p.halves : 1);
     const int clusters = max_clusters < pairs ? max_clusters : pairs;
-    conv_big2_kernel<NBUF, NPAIR><<<2 * clusters, BIG2_THREADS, BIG2_SMEM, st>>>(tmA, tmB, p);
+    conv_big2_kernel<NBUF, NPAIR><<<2 * clusters, Big2Epi<NPAIR>::THREADS, BIG2_SMEM, st>>>(tmA, tmB, p);
     SHM_CHECK_LAUNCH("conv_big2_kernel");
     return SHM_OK;
 }
