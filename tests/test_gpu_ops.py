@@ -434,6 +434,16 @@ def test_im2col_col2im_k3s2():
     xbuf = torch.zeros((N, H, W, 8), device="cuda", dtype=torch.bfloat16)       # bf16 source in a wider buffer
     xbuf[..., :C] = dev(x, torch.bfloat16)
     assert torch.equal(ops.im2col_k3s2(xbuf[..., :C]).double().cpu(), want)
+    # the strip kernel of the discriminator's dense bf16 RGB input (W/2 a multiple of 32): one and two strips per row, odd image count
+    for (n2, h2, w2) in ((1, 4, 64), (3, 6, 128), (2, 2, 192)):
+        x2 = bf16_round(randn((n2, h2, w2, 3), 63))
+        xp2 = torch.zeros((n2, h2 + 1, w2 + 1, 3), dtype=F64)
+        xp2[:, :h2, :w2] = x2
+        want2 = torch.zeros((n2, h2 // 2, w2 // 2, 64), dtype=F64)
+        for ky in range(3):
+            for kx in range(3):
+                want2[..., (ky * 3 + kx) * 3:(ky * 3 + kx + 1) * 3] = xp2[:, ky:ky + h2:2, kx:kx + w2:2]
+        assert torch.equal(ops.im2col_k3s2(dev(x2, torch.bfloat16)).double().cpu(), want2), (n2, h2, w2)
     g = bf16_round(randn((N, H // 2, W // 2, 64), 62))
     dx = ops.col2im_k3s2(dev(g, torch.bfloat16), C, H, W, torch.float32)
     lhs = float((want * g).sum())
