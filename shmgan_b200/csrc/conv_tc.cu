@@ -2471,8 +2471,9 @@ __global__ void prep_w_both_kernel(const float* __restrict__ w, PrepSet a, PrepS
 // the same for MANY layers in one launch: the per-step weight refresh of a network (~40 layers) is launch-bound otherwise.
 // blockIdx.x -> (job, chunk of 2048 elements) through the jobs' block_begin prefix; blockIdx.y = layout (0 forward, 1 dgrad).
 struct PrepJob { const float* w; PrepSet a, b; long long tap_elems, total; int block_begin, nblocks; };
-constexpr int PREP_CHUNK = 2048;
+constexpr int PREP_CHUNK = 8192;
 __global__ void __launch_bounds__(256) prep_w_multi_kernel(const PrepJob* __restrict__ jobs, int njobs) {
+    __shared__ float tile[PREP_CHUNK + 128];
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {
         const int mid = (lo + hi + 1) >> 1;
@@ -2482,6 +2483,25 @@ __global__ void __launch_bounds__(256) prep_w_multi_kernel(const PrepJob* __rest
     const PrepSet s = blockIdx.y == 0 ? J.a : J.b;
     const long long beg = (long long)((int)blockIdx.x - J.block_begin) * PREP_CHUNK;
     const long long end = beg + PREP_CHUNK < J.total ? beg + PREP_CHUNK : J.total;
+    // The layout whose k runs along the source's SLOW axis (forward of a Conv2D, dgrad of a Conv2DTranspose: w_ns == 1) is a transpose:
+    // read straight, consecutive threads fetched 4 bytes of 32 different sectors (0.13 ms per network and step).  A chunk is whole rows of K
+    // outputs, i.e. R = chunk / K consecutive n per k in the source: read those runs with n fastest into shared memory, write k fastest.
+    if (s.w_ns == 1 && s.w_ks != 1 && s.K <= 1024 && PREP_CHUNK % s.K == 0 && beg % s.K == 0) {
+        const int K = s.K, len = (int)(end - beg), R = len / K;                 // len is a multiple of K (total = taps * Nn * K)
+        const long long row0 = beg / K;
+        for (int j = threadIdx.x; j < len; j += 256) {
+            const int kk = j / R, rr = j - kk * R;
+            const long long row = row0 + rr;
+            const long long tap = row / s.Nn; const int n = (int)(row - tap * s.Nn);
+            tile[rr * (K + 1) + kk] = (kk < s.k_real && n < s.n_real) ? __ldg(J.w + tap * J.tap_elems + (long long)kk * s.w_ks + n) : 0.f;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < len; j += 256) {
+            const int rr = j / K, kk = j - rr * K;
+            s.o[beg + j] = __float2bfloat16_rn(tile[rr * (K + 1) + kk]);
+        }
+        return;
+    }
     for (long long i = beg + threadIdx.x; i < end; i += 256) {
         const int k = (int)(i % s.K);
         const long long t2 = i / s.K;
