@@ -360,7 +360,9 @@ class ShmGANwithSSpecSeg:
             if dst.data_ptr() != src.data_ptr():
                 dst.copy_(src, non_blocking=True)           # cudaMemcpyAsync, device to device
         self._write_graph_params()
-        key = (tuple(bool(b) for b in bits), B)
+        in_graph_opt = self._reducer is None                # data parallel: all-reduce + clip + Adam follow the replay as ordinary launches
+        # everything the recorded launch sequence or its baked-in scalars depend on
+        key = (tuple(bool(b) for b in bits), B, in_graph_opt, self.overlap, self.noise_seed, self.dropout_amnt, self.beta1, self.beta2)
         entry = self._graphs.get(key)
         if entry is None and self._graph_eager_steps < max(2, self.graph_warmup):    # (layers join the batched weight refresh in step 2)
             self._graph_eager_steps += 1                    # same code path as the capture, executed eagerly
@@ -368,7 +370,6 @@ class ShmGANwithSSpecSeg:
             self._start_loss_readback()
             return
         G, D = self.G.net.store, self.D.net.store
-        in_graph_opt = self._reducer is None                # data parallel: all-reduce + clip + Adam follow the replay as ordinary launches
         if entry is None:
             if self._graph_pool is None:
                 self._graph_pool = torch.cuda.graph_pool_handle()
