@@ -315,6 +315,56 @@ __global__ void col2im_k3s2_kernel(const bf16* __restrict__ dP, int H, int W, in
     }
 }
 
+// The same for the training step's shape (C = 3, dense bf16 dx, W % 64 == 0): a warp produces 64 pixels of one input row.  Lane l loads the nine
+// values (kx, c) of patch row ky of output pixel ox0 + l -- from the one or two output rows that reach this input row -- and owns input pixels
+// 2 (ox0 + l) (taps kx = 0 of its own output pixel and kx = 2 of its left neighbour's, by shuffle) and 2 (ox0 + l) + 1 (tap kx = 1).  Same
+// summation order as the generic kernel (ky, then kx ascending): identical results, 384 contiguous bytes per warp store.
+__global__ void __launch_bounds__(256) col2im3_strip_kernel(const bf16* __restrict__ dP, int H, int W, long long strips, bf16* __restrict__ dx) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Ho = H >> 1, Wo = W >> 1, spr = W >> 6;
+    const long long strip = (long long)blockIdx.x * 8 + warp;
+    if (strip >= strips) return;
+    const int sx = (int)(strip % spr); const long long t = strip / spr; const int iy = (int)(t % H); const long long n = t / H;
+    const int ox = (sx << 5) + lane;
+    float even[3] = {0.f, 0.f, 0.f}, odd[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ty = iy - ky;
+        const bool rowok = ty >= 0 && !(ty & 1) && (ty >> 1) < Ho;      // warp-uniform
+        if (!rowok) continue;
+        // the nine values sit at elements 9 ky .. 9 ky + 8 of the 64-element patch row: two aligned 16-byte loads (window of 16 elements starting
+        // at element 8 * (9 ky / 8)) instead of nine 2-byte ones
+        const bf16* prow = dP + ((n * Ho + (ty >> 1)) * Wo + ox) * 64;
+        const int j0 = (ky * 9) >> 3, e0 = ky * 9 - (j0 << 3);          // ky = 0, 1, 2 -> window 0, 1, 2; first element 0, 1, 2
+        auto window = [&](const bf16* r, float* w9) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(r) + j0), b = __ldg(reinterpret_cast<const uint4*>(r) + j0 + 1);
+            const uint32_t u[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int i = 0; i < 9; ++i) {
+                const int e = e0 + i;
+                w9[i] = __uint_as_float((e & 1) ? (u[e >> 1] & 0xffff0000u) : (u[e >> 1] << 16));
+            }
+        };
+        float v[9];
+        window(prow, v);
+        float left[3];                                                   // kx = 2 of output pixel ox - 1
+#pragma unroll
+        for (int c = 0; c < 3; ++c) left[c] = __shfl_up_sync(0xffffffffu, v[6 + c], 1);
+        if (lane == 0) {
+            float lv[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (ox > 0) window(prow - 64, lv);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) left[c] = lv[6 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { even[c] += v[c]; even[c] += left[c]; odd[c] += v[3 + c]; }
+    }
+    // six bf16 = three 4-byte words per lane
+    __nv_bfloat162 w0 = __floats2bfloat162_rn(even[0], even[1]), w1 = __floats2bfloat162_rn(even[2], odd[0]), w2 = __floats2bfloat162_rn(odd[1], odd[2]);
+    uint32_t* o = reinterpret_cast<uint32_t*>(dx + ((n * H + iy) * W + 2 * ox) * 3);
+    o[0] = *reinterpret_cast<uint32_t*>(&w0); o[1] = *reinterpret_cast<uint32_t*>(&w1); o[2] = *reinterpret_cast<uint32_t*>(&w2);
+}
+
 struct Slots { int s[5]; int n; };
 template <typename T>
 __global__ void assemble_bwd_kernel(const T* __restrict__ din, int ldin, Slots sl, float* __restrict__ dgen, long long npix) {
@@ -499,6 +549,10 @@ extern "C" int shm_col2im_k3s2(const void* dP_bf16, int N, int H, int W, int C, 
     const int pb = same_pad_before(H, 3, 2);
     cudaStream_t st = (cudaStream_t)stream;
     if (dst_dtype == SHM_F32) col2im_k3s2_kernel<float><<<flat_grid(npix), 256, 0, st>>>((const bf16*)dP_bf16, H, W, C, pb, (float*)dx, lddx, npix);
+    else if (dst_dtype == SHM_BF16 && C == 3 && lddx == 3 && pb == 0 && W % 64 == 0 && (reinterpret_cast<uintptr_t>(dx) & 3) == 0) {
+        const long long strips = (long long)N * H * (W / 64);
+        col2im3_strip_kernel<<<(unsigned)((strips + 7) / 8), 256, 0, st>>>((const bf16*)dP_bf16, H, W, strips, (bf16*)dx);
+    }
     else if (dst_dtype == SHM_BF16) col2im_k3s2_kernel<bf16><<<flat_grid(npix), 256, 0, st>>>((const bf16*)dP_bf16, H, W, C, pb, (bf16*)dx, lddx, npix);
     else SHM_FAIL(SHM_EINVAL, "shm_col2im_k3s2: bad dtype %d", dst_dtype);
     SHM_CHECK_LAUNCH("col2im_k3s2_kernel");

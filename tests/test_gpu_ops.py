@@ -444,6 +444,15 @@ def test_im2col_col2im_k3s2():
             for kx in range(3):
                 want2[..., (ky * 3 + kx) * 3:(ky * 3 + kx + 1) * 3] = xp2[:, ky:ky + h2:2, kx:kx + w2:2]
         assert torch.equal(ops.im2col_k3s2(dev(x2, torch.bfloat16)).double().cpu(), want2), (n2, h2, w2)
+    # ... and the strip form of col2im (dense bf16 dx, W a multiple of 64) against a scatter-add restatement
+    for (n2, h2, w2) in ((1, 4, 64), (3, 6, 128)):
+        g2 = bf16_round(randn((n2, h2 // 2, w2 // 2, 64), 64))
+        acc = torch.zeros((n2, h2 + 1, w2 + 1, 3), dtype=F64)
+        for ky in range(3):
+            for kx in range(3):
+                acc[:, ky:ky + h2:2, kx:kx + w2:2] += g2[..., (ky * 3 + kx) * 3:(ky * 3 + kx + 1) * 3]
+        got2 = ops.col2im_k3s2(dev(g2, torch.bfloat16), 3, h2, w2, torch.bfloat16)
+        assert got2.dtype == torch.bfloat16 and rel_err(got2, acc[:, :h2, :w2]) < 1e-2, (n2, h2, w2)
     g = bf16_round(randn((N, H // 2, W // 2, 64), 62))
     dx = ops.col2im_k3s2(dev(g, torch.bfloat16), C, H, W, torch.float32)
     lhs = float((want * g).sum())

@@ -10,3 +10,10 @@ for _ in range(10): y = ops.im2col_k3s2(x)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 print("im2col_k3s2 160x256x256x3 bf16: %.3f ms  %.0f GB/s" % (ms, (x.numel() * 2 + y.numel() * 2) / ms / 1e6))
+g = torch.randn((96, 128, 128, 64), device="cuda").bfloat16()
+for _ in range(3): d = ops.col2im_k3s2(g, 3, 256, 256, torch.bfloat16)
+e0.record()
+for _ in range(10): d = ops.col2im_k3s2(g, 3, 256, 256, torch.bfloat16)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 10
+print("col2im_k3s2 96x128x128x64 -> 96x256x256x3 bf16: %.3f ms  %.0f GB/s (64 of the 128 bytes of a patch row are ever read)" % (ms, (g.numel() + d.numel() * 2) / ms / 1e6))
