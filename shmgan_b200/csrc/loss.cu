@@ -4,6 +4,7 @@
 //   clip_by_value + Keras Adam                                        ShmGANwithSSpecSeg.py:860-871, :169-175
 // Every loss kernel ADDS weight * value into loss_out[0] (fp32, device) so a step reads all scalars back with one copy.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
 
@@ -100,15 +101,23 @@ __device__ __forceinline__ void load3(const float* Yp, const float* cbcr, int HW
     else { const float* s = Yp + ((long long)n * HW + p) * 3; v[0] = s[0]; v[1] = s[1]; v[2] = s[2]; }
 }
 
-// per-image min / max / argmin / argmax over the [HW,3] values; one block per image
-__global__ void __launch_bounds__(1024) minmax3_kernel(const float* __restrict__ Yp, const float* __restrict__ cbcr, int HW,
-                                                       float* __restrict__ mm, int* __restrict__ idx) {
+// per-image min / max / argmin / argmax over the [HW,3] values.  One CLUSTER of eight 1024-thread blocks per image (one block per image left
+// 132 of the 148 SMs idle at batch 16: 39 us per call, five calls per step): every block scans an eighth of the image, block 0 of the cluster
+// collects the eight partial results through distributed shared memory.
+constexpr int MM_CLUSTER = 8;
+__global__ void __cluster_dims__(MM_CLUSTER, 1, 1) __launch_bounds__(1024) minmax3_kernel(const float* __restrict__ Yp, const float* __restrict__ cbcr, int HW,
+                                                                                          float* __restrict__ mm, int* __restrict__ idx) {
     __shared__ float smn[32], smx[32];
     __shared__ int simn[32], simx[32];
-    const int n = blockIdx.x;
+    __shared__ float res_v[2];
+    __shared__ int res_i[2];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int n = blockIdx.x / MM_CLUSTER;
     float mn = INFINITY, mx = -INFINITY;
     int imn = 0x7fffffff, imx = 0x7fffffff;
-    for (int p = threadIdx.x; p < HW; p += blockDim.x) {
+    for (int p = rank * (int)blockDim.x + threadIdx.x; p < HW; p += MM_CLUSTER * blockDim.x) {
         float v[3];
         load3(Yp, cbcr, HW, n, p, v);
 #pragma unroll
@@ -138,8 +147,25 @@ __global__ void __launch_bounds__(1024) minmax3_kernel(const float* __restrict__
             if (omn < mn || (omn == mn && oimn < imn)) { mn = omn; imn = oimn; }
             if (omx > mx || (omx == mx && oimx < imx)) { mx = omx; imx = oimx; }
         }
+        if (lane == 0) { res_v[0] = mn; res_v[1] = mx; res_i[0] = imn; res_i[1] = imx; }
+    }
+    cluster.sync();                                        // every block's partial result is in its shared memory
+    if (rank == 0 && w == 0) {
+        mn = INFINITY; mx = -INFINITY; imn = 0x7fffffff; imx = 0x7fffffff;
+        if (lane < MM_CLUSTER) {
+            const float* rv = cluster.map_shared_rank(res_v, lane);
+            const int* ri = cluster.map_shared_rank(res_i, lane);
+            mn = rv[0]; mx = rv[1]; imn = ri[0]; imx = ri[1];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float omn = __shfl_xor_sync(0xffffffffu, mn, o), omx = __shfl_xor_sync(0xffffffffu, mx, o);
+            const int oimn = __shfl_xor_sync(0xffffffffu, imn, o), oimx = __shfl_xor_sync(0xffffffffu, imx, o);
+            if (omn < mn || (omn == mn && oimn < imn)) { mn = omn; imn = oimn; }
+            if (omx > mx || (omx == mx && oimx < imx)) { mx = omx; imx = oimx; }
+        }
         if (lane == 0) { mm[n * 2] = mn; mm[n * 2 + 1] = mx; idx[n * 2] = imn; idx[n * 2 + 1] = imx; }
     }
+    cluster.sync();                                        // no block leaves while block 0 may still read its shared memory
 }
 
 // gram[n][c*3+d] += sum_p x_c x_d   (un-normalised; the 1/HW is applied by the consumers)
@@ -486,7 +512,7 @@ extern "C" int shm_spec_loss(const float* Y, const float* cbcr, const float* yuv
 extern "C" int shm_minmax3(const float* Y_or_yuv, const float* cbcr, int N, int HW, float* mm, int32_t* idx, void* stream) {
     SHM_REQUIRE(Y_or_yuv && mm && idx && N > 0 && HW > 0, "shm_minmax3: bad args");
     SHM_REQUIRE((long long)HW * 3 < 0x7fffffffLL, "shm_minmax3: image too large");
-    minmax3_kernel<<<N, 1024, 0, (cudaStream_t)stream>>>(Y_or_yuv, cbcr, HW, mm, idx);
+    minmax3_kernel<<<N * MM_CLUSTER, 1024, 0, (cudaStream_t)stream>>>(Y_or_yuv, cbcr, HW, mm, idx);
     SHM_CHECK_LAUNCH("minmax3_kernel");
     return SHM_OK;
 }
