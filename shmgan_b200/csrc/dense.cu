@@ -123,8 +123,27 @@ __global__ void __launch_bounds__(256) pw1_fwd_kernel(const bf16* __restrict__ x
     for (int j = 0; j < 8; ++j) wv[j] = __ldg(w + part * 8 + j);
     const float b = bias ? __ldg(bias) : 0.f;
     const long long ppb = 256 / TPP;
-    // the trip count is uniform over the block (p0), so the full-mask shuffles below are always converged
-    for (long long p0 = (long long)blockIdx.x * ppb; p0 < npix; p0 += (long long)gridDim.x * ppb) {
+    // the trip count is uniform over the block (p0), so the full-mask shuffles below are always converged.
+    // Four pixels per trip while four full strides remain: one 16-byte load in flight per thread left the kernel latency-bound (4.1 TB/s).
+    const long long stride = (long long)gridDim.x * ppb;
+    long long p0 = (long long)blockIdx.x * ppb;
+    for (; p0 + 3 * stride + ppb <= npix; p0 += 4 * stride) {
+        const long long p = p0 + threadIdx.x / TPP;
+        uint4 xv[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = __ldg(reinterpret_cast<const uint4*>(x + (p + u * stride) * ldx + part * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[8], s = 0.f;
+            unpack8(xv[u], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s = fmaf(v[j], wv[j], s);
+#pragma unroll
+            for (int o = TPP / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (part == 0) y[p + u * stride] = __float2bfloat16_rn(act_fwd(s + b, act));
+        }
+    }
+    for (; p0 < npix; p0 += stride) {
         const long long p = p0 + threadIdx.x / TPP;
         const bool ok = p < npix;
         float s = 0.f;
@@ -153,7 +172,32 @@ __global__ void __launch_bounds__(256) pw1_bwd_kernel(const bf16* __restrict__ x
 #pragma unroll
     for (int j = 0; j < 8; ++j) { wv[j] = __ldg(w + part * 8 + j); acc[j] = 0.f; }
     const long long ppb = 256 / TPP;
-    for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / TPP; p < npix; p += (long long)gridDim.x * ppb) {
+    const long long stride = (long long)gridDim.x * ppb;
+    long long p = (long long)blockIdx.x * ppb + threadIdx.x / TPP;
+    // four pixels per trip (four 16-byte loads in flight per thread), then the remainder one by one
+    for (; p + 3 * stride < npix; p += 4 * stride) {
+        uint4 xv[4];
+        float g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) xv[u] = __ldg(reinterpret_cast<const uint4*>(x + (p + u * stride) * ldx + part * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) g[u] = __bfloat162float(dy[p + u * stride]) * act_grad_from_post(__bfloat162float(y[p + u * stride]), act);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v[8];
+            unpack8(xv[u], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[j], g[u], acc[j]);
+            if (part == 0) accb += g[u];
+            if (dx) {
+                __nv_bfloat162 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(g[u] * wv[2 * j], g[u] * wv[2 * j + 1]);
+                *reinterpret_cast<uint4*>(dx + (p + u * stride) * lddx + part * 8) = *reinterpret_cast<uint4*>(h);
+            }
+        }
+    }
+    for (; p < npix; p += stride) {
         const float g = __bfloat162float(dy[p]) * act_grad_from_post(__bfloat162float(y[p]), act);
         float v[8];
         unpack8(__ldg(reinterpret_cast<const uint4*>(x + p * ldx + part * 8)), v);
